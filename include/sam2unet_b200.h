@@ -1,0 +1,121 @@
+/* sam2unet_b200.h — C ABI of the B200-native (sm_100a) SAM2-UNet hot path.
+ *
+ * One shared object (sam2_unet_b200/libsam2unet_b200.so), plain pointers and sizes, no PyTorch types.  Every
+ * entry point replaces the ATen call(s) the reference makes at the cited lines (paths relative to the
+ * reference repository hanguyenh2/SAM2-UNet); the reference has no FFI of its own for this path — its Python
+ * modules call torch.nn.functional directly — so these are the functions a reference-side binding (ctypes
+ * stub) would bind in place of those calls.
+ *
+ * Conventions
+ *   - return value: 0 = ok; > 0 = cudaError_t of the failed launch; -1 = invalid argument;
+ *     -2 = shape/alignment this kernel does not support; <= -100 = -(100 + CUresult) from the driver.
+ *     There is no CPU or library fallback behind any entry point.
+ *   - `dtype`: 0 = float32, 1 = bfloat16; it selects the element type of every `void*` activation tensor.
+ *     Parameters of norms / biases / BN and all statistics are float32; reductions accumulate in fp32/fp64.
+ *   - all tensors are device pointers owned by the caller; kernels never allocate; everything is enqueued on
+ *     `stream` (a cudaStream_t); activations are NHWC ("tokens x channels") row-major, `ld*` = row pitch in
+ *     elements.  Vector paths need 16-byte aligned pointers and channel counts / pitches that are multiples of 8.
+ */
+#ifndef SAM2UNET_B200_H
+#define SAM2UNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- GEMM family ------------------------------------------------------------------------------------------
+ * C[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear forward (sam2/modeling/backbones/hieradet.py:59,79,
+ * sam2/modeling/sam2_utils.py:127-132, SAM2UNet.py:57-63), its input gradient (W = pre-transposed weight), and
+ * conv forward / input gradient on im2col rows (SAM2UNet.py:83-86).  epi(v): v += bias[n]; pre_out = v;
+ * flags&1: v = gelu(v); flags&2: v *= gelu'(aux); flags&4: v += resid.
+ * backend: 0 auto (tcgen05 + TMA for bf16), 1 SIMT fp32-FMA, 2 tcgen05 required, 16+bn tcgen05 with N tile bn. */
+int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+             const float* bias, void* pre_out, int ld_pre, const void* aux, int ld_aux, const void* resid,
+             int ld_res, int flags, int dtype, int backend, void* stream);
+/* G[P,Q] += A[M,P]^T . B[M,Q] (fp32 G): weight gradients of the adapters (SAM2UNet.py:57-59) and convs
+ * (SAM2UNet.py:72-80); q_inner/q_taps map q = tap*Cin+ci to the [Cout,Cin,kh,kw] parameter layout (0,0: plain). */
+int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int ldg, long long M, int P, int Q,
+                   int q_inner, int q_taps, int dtype, void* stream);
+/* out[P] += column sums of A[M,P]: bias gradients. */
+int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype, void* stream);
+
+/* ---- LayerNorm (hieradet.py:99-100,104,120,134,166; eps 1e-6) ------------------------------------------- */
+int s2u_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      long long R, int C, float eps, int dtype, void* stream);
+/* dx = LN'(dy) + dres (dres may be NULL); the affine parameters are frozen (SAM2UNet.py:146-147). */
+int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      const void* dres, void* dx, long long R, int C, int dtype, void* stream);
+
+/* ---- element-wise helpers --------------------------------------------------------------------------------- */
+int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int dtype, void* stream);
+int s2u_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);
+/* 2x2/stride-2 max-pool of NHWC tokens and its argmax-routed gradient (hieradet.py:21-32,108-110,137-138). */
+int s2u_maxpool2_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream);
+int s2u_maxpool2_bwd(const void* x, const void* dout, void* dx, int B, int H, int W, int C, int dtype,
+                     void* stream);
+/* fp32 master -> compute-dtype shadow of a [R,C] parameter, optionally transposed. */
+int s2u_cast(const float* src, void* dst, int R, int C, int transpose, int dtype, void* stream);
+
+/* ---- windowed / global attention (hieradet.py:56-81,141-162; backbones/utils.py:16-55) ------------------ *
+ * qkv [B,H,W,3*nh*hd]; window = 0 means global; pool = 1 applies the 2x2 q max-pool inside each window;
+ * bias = the qkv bias (value of zero-padded tokens); out [B,Ho,Wo,nh*hd], lse [B,Ho,Wo,nh]. */
+int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
+                     int window, int pool, int dtype, void* stream);
+int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
+                     void* dqkv, int B, int H, int W, int nh, int hd, int window, int pool, int dtype, void* stream);
+
+/* ---- stem and convolutions -------------------------------------------------------------------------------- *
+ * 7x7/s4/p3 conv 3->E + bias + position-embedding table (backbones/utils.py:80-88, hieradet.py:268-283). */
+int s2u_patch_embed(const float* x, const float* w, const float* bias, const float* pos, void* out, int B, int S,
+                    int E, int dtype, void* stream);
+/* taps of a stride-1 conv gathered to [B*H*W, KH*KW*Cin] (SAM2UNet.py:68-125,9-26). */
+int s2u_im2col(const void* x, int ldx, void* out, int B, int H, int W, int Cin, int KH, int KW, int dil_h, int dil_w,
+               int pad_h, int pad_w, int dtype, void* stream);
+int s2u_conv_weight_pack(const float* w, void* wf, void* wd, int Cout, int Cin, int KH, int KW, int dtype,
+                         void* stream);
+
+/* ---- BatchNorm2d, eps 1e-5, momentum 0.1 (SAM2UNet.py:80,85,18,21) ---------------------------------------- */
+int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream);
+int s2u_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    long long* num_batches, float* scale, float* shift, float* save_mean, float* save_rstd,
+                    long long M, int C, float eps, float momentum, int training, void* stream);
+int s2u_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* resid, int ld_res,
+                 void* out, int ld_out, long long M, int C, int relu, int dtype, void* stream);
+int s2u_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, void* g, int ld_g, long long M, int C,
+                 int dtype, void* stream);
+int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x, int ldx, const float* mean,
+               const float* rstd, const float* gamma, double* sums, float* dgamma, float* dbeta, float* c1, float* c2,
+               void* dx, int ld_dx, long long M, int C, int dtype, void* stream);
+
+/* ---- bilinear resampling and heads (SAM2UNet.py:32-49,160-172) ------------------------------------------- */
+int s2u_resample_fwd(const void* x, int ldx, void* out, int ld_out, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                     const int* y_i0, const int* y_i1, const float* y_w0, const float* y_w1, const int* x_i0,
+                     const int* x_i1, const float* x_w0, const float* x_w1, int dtype, void* stream);
+int s2u_resample_bwd(const void* dout, int ld_do, void* dx, int ld_dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                     const int* y_idx, const float* y_w, int y_taps, const int* x_idx, const float* x_w, int x_taps,
+                     int dtype, void* stream);
+int s2u_resample1_fwd(const float* x, float* out, int B, int Hi, int Wi, int Ho, int Wo, const int* y_i0,
+                      const int* y_i1, const float* y_w0, const float* y_w1, const int* x_i0, const int* x_i1,
+                      const float* x_w0, const float* x_w1, void* stream);
+int s2u_resample1_bwd(const float* dout, float* dx, int B, int Hi, int Wi, int Ho, int Wo, const int* y_idx,
+                      const float* y_w, int y_taps, const int* x_idx, const float* x_w, int x_taps, void* stream);
+int s2u_head_fwd(const void* feat, int ldf, const float* w, const float* bias, float* out, long long M, int C,
+                 int dtype, void* stream);
+int s2u_head_bwd(const void* feat, int ldf, const float* w, const float* dlogit, void* dfeat, int ld_df,
+                 int accumulate, float* dw, float* db, long long M, int C, int dtype, void* stream);
+
+/* ---- structure_loss (train.py:21-29,76-79) and AdamW (train.py:48-52,83) --------------------------------- *
+ * sums: fp64 workspace of nheads*B*2 + nheads entries; weit: fp32 [B,H,W] workspace shared by the heads. */
+int s2u_structure_loss_fwd(const float* pred0, const float* pred1, const float* pred2, const float* mask,
+                           float* weit, double* sums, float* loss, int B, int H, int W, int nheads, void* stream);
+int s2u_structure_loss_bwd(const float* pred0, const float* pred1, const float* pred2, const float* mask,
+                           const float* weit, const double* sums, const float* gscale, float* grad0, float* grad1,
+                           float* grad2, int B, int H, int W, int nheads, void* stream);
+/* hyper (device): lr, 1-beta1^t, 1-beta2^t, gradient scale (1/world_size under data parallelism). */
+int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1,
+              float beta2, float eps, float wd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAM2UNET_B200_H */

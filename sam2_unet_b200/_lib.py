@@ -1,0 +1,96 @@
+"""ctypes binding of the C-ABI library (include/sam2unet_b200.h).
+
+There is no fallback: if the shared library is missing or a kernel launch fails, this raises.  The
+library is built in-tree by `python -m sam2_unet_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsam2unet_b200.so")
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+
+# name -> argument ctypes, mirrors include/sam2unet_b200.h (tests check both against the .so)
+SIGNATURES = {
+    "s2u_gemm": [P, I, P, I, P, I, I, I, I, P, P, I, P, I, P, I, I, I, I, P],
+    "s2u_gemm_wgrad": [P, I, P, I, P, I, L, I, I, I, I, I, P],
+    "s2u_colsum": [P, I, P, L, I, I, P],
+    "s2u_layernorm_fwd": [P, P, P, P, P, P, L, I, F, I, P],
+    "s2u_layernorm_bwd": [P, P, P, P, P, P, P, L, I, I, P],
+    "s2u_dgelu_mul": [P, P, P, L, I, P],
+    "s2u_add": [P, P, P, L, I, P],
+    "s2u_maxpool2_fwd": [P, P, I, I, I, I, I, P],
+    "s2u_maxpool2_bwd": [P, P, P, I, I, I, I, I, P],
+    "s2u_cast": [P, P, I, I, I, I, P],
+    "s2u_win_attn_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P],
+    "s2u_win_attn_bwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
+    "s2u_patch_embed": [P, P, P, P, P, I, I, I, I, P],
+    "s2u_im2col": [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "s2u_conv_weight_pack": [P, P, P, I, I, I, I, I, P],
+    "s2u_bn_stats": [P, I, P, L, I, I, P],
+    "s2u_bn_finalize": [P, P, P, P, P, P, P, P, P, P, L, I, F, F, I, P],
+    "s2u_bn_apply": [P, I, P, P, P, I, P, I, L, I, I, I, P],
+    "s2u_relu_bwd": [P, I, P, I, P, I, L, I, I, P],
+    "s2u_bn_bwd": [P, I, P, I, P, I, P, P, P, P, P, P, P, P, P, I, L, I, I, P],
+    "s2u_resample_fwd": [P, I, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, I, P],
+    "s2u_resample_bwd": [P, I, P, I, I, I, I, I, I, I, P, P, I, P, P, I, I, P],
+    "s2u_resample1_fwd": [P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P],
+    "s2u_resample1_bwd": [P, P, I, I, I, I, I, P, P, I, P, P, I, P],
+    "s2u_head_fwd": [P, I, P, P, P, L, I, I, P],
+    "s2u_head_bwd": [P, I, P, P, P, I, I, P, P, L, I, I, P],
+    "s2u_structure_loss_fwd": [P, P, P, P, P, P, P, I, I, I, I, P],
+    "s2u_structure_loss_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "s2u_adamw": [P, P, P, P, L, P, F, F, F, F, P],
+}
+
+_lib = None
+_launches = 0
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KernelError(
+                f"{LIB_PATH} not found: build it with `python -m sam2_unet_b200.build` — there is no CPU or "
+                "library fallback for the SAM2-UNet hot path")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        _lib = lib
+    return _lib
+
+
+def _describe(rc: int) -> str:
+    if rc == -1:
+        return "invalid argument"
+    if rc == -2:
+        return "unsupported shape / alignment for this kernel"
+    if rc <= -100:
+        return f"cuTensorMapEncodeTiled failed with CUresult {-rc - 100}"
+    return f"CUDA error {rc}"
+
+
+def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point and raise on a non-zero status."""
+    global _launches
+    rc = getattr(load(), name)(*args)
+    _launches += 1
+    if rc != 0:
+        raise KernelError(f"{name} failed: {_describe(rc)}")
+
+
+def launch_count() -> int:
+    """Number of C-ABI calls made so far (each launches at least one kernel of this package)."""
+    return _launches

@@ -1,0 +1,296 @@
+// BatchNorm2d (eps 1e-5, momentum 0.1) around the RFB / decoder convolutions, on NHWC rows [M = B*H*W, C].
+// Reference: BasicConv2d = bn(conv(x)) with NO activation (/root/reference/SAM2UNet.py:68-86), DoubleConv =
+// conv-bn-relu twice (SAM2UNet.py:9-26), RFB tail relu(bn(conv_cat) + bn(conv_res)) (SAM2UNet.py:117-125).
+// Training mode normalises with the biased batch variance and updates the running statistics with the
+// unbiased one; eval mode uses the running statistics.  Per-channel sums are accumulated in fp64 so the
+// E[x^2]-E[x]^2 form loses nothing against ATen's Welford pass.
+#include "common.cuh"
+
+constexpr int BN_ROWS = 64;   // rows per block in the reduction kernels
+
+// sums[0..C) += sum x, sums[C..2C) += sum x^2
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int ldx, double* __restrict__ sums,
+                                                      long long M, int C) {
+  extern __shared__ float red[];              // [256/cg][2][cg*8]... laid out as [sub][2*C]
+  const int cg = C >> 3;                      // 8-channel groups
+  const int nsub = 256 / cg;                  // row lanes per block
+  const int g = threadIdx.x % cg, sub = threadIdx.x / cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const long long r0 = (long long)blockIdx.x * BN_ROWS;
+  if (sub < nsub) {
+    for (long long r = r0 + sub; r < min(M, r0 + BN_ROWS); r += nsub) {
+      const F8 v = ld8(x + r * ldx + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[sub * 2 * C + g * 8 + j] = s[j];
+      red[sub * 2 * C + C + g * 8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float t = 0.f;
+    for (int k = 0; k < nsub; ++k) t += red[k * 2 * C + i];
+    atomicAdd(sums + i, (double)t);
+  }
+}
+
+// one block: batch statistics -> (scale, shift) for the apply pass, saved (mean, rstd) for backward,
+// running-stat update; clears the accumulators for the next use.
+__global__ void bn_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_rstd, long long M, int C, float eps, float momentum,
+                                   int training) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    if (training) {
+      const double m = sums[c] / (double)M;
+      double var = sums[C + c] / (double)M - m * m;
+      if (var < 0) var = 0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      sums[c] = 0.0;
+      sums[C + c] = 0.0;
+    } else {
+      mean = running_mean[c];
+      rstd = rsqrtf(running_var[c] + eps);
+    }
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (save_mean) save_mean[c] = mean;
+    if (save_rstd) save_rstd[c] = rstd;
+  }
+  if (training && num_batches && threadIdx.x == 0) *num_batches += 1;
+}
+
+// out = act(x * scale + shift (+ resid)); out may be a channel slice of a wider (concat) buffer via ld_out
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const T* __restrict__ resid, int ld_res,
+                                T* __restrict__ out, int ld_out, long long M, int C, int relu) {
+  const int cg = C >> 3;
+  const long long total = M * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long r = i / cg;
+    F8 v = ld8(x + r * ldx + g * 8);
+    const F8 sc = ld8(scale + g * 8), sh = ld8(shift + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc.v[j], sh.v[j]);
+    if (resid) {
+      const F8 rr = ld8(resid + r * ld_res + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] += rr.v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = fmaxf(v.v[j], 0.f);
+    }
+    st8(out + r * ld_out + g * 8, v);
+  }
+}
+
+// g = dy * (y > 0): gradient through a ReLU given its OUTPUT y
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, int ld_dy, const T* __restrict__ y, int ld_y,
+                                T* __restrict__ g, int ld_g, long long M, int C) {
+  const int cg = C >> 3;
+  const long long total = M * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg);
+    const long long r = i / cg;
+    const F8 d = ld8(dy + r * ld_dy + c * 8), yy = ld8(y + r * ld_y + c * 8);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = yy.v[j] > 0.f ? d.v[j] : 0.f;
+    st8(g + r * ld_g + c * 8, o);
+  }
+}
+
+// sums[0..C) += sum g, sums[C..2C) += sum g * xhat, with g = dy * (y > 0 if y given)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ dy, int ld_dy,
+                                                           const T* __restrict__ y, int ld_y,
+                                                           const T* __restrict__ x, int ldx,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           double* __restrict__ sums, long long M, int C) {
+  extern __shared__ float red[];
+  const int cg = C >> 3;
+  const int nsub = 256 / cg;
+  const int g = threadIdx.x % cg, sub = threadIdx.x / cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const long long r0 = (long long)blockIdx.x * BN_ROWS;
+  if (sub < nsub) {
+    const F8 mu = ld8(mean + g * 8), rs = ld8(rstd + g * 8);
+    for (long long r = r0 + sub; r < min(M, r0 + BN_ROWS); r += nsub) {
+      F8 d = ld8(dy + r * ld_dy + g * 8);
+      const F8 v = ld8(x + r * ldx + g * 8);
+      if (y) {
+        const F8 yy = ld8(y + r * ld_y + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = yy.v[j] > 0.f ? d.v[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += d.v[j];
+        q[j] = fmaf(d.v[j], (v.v[j] - mu.v[j]) * rs.v[j], q[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[sub * 2 * C + g * 8 + j] = s[j];
+      red[sub * 2 * C + C + g * 8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float t = 0.f;
+    for (int k = 0; k < nsub; ++k) t += red[k * 2 * C + i];
+    atomicAdd(sums + i, (double)t);
+  }
+}
+
+// one block: dgamma/dbeta accumulate into the parameter gradients; per-channel coefficients for the apply pass
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2,
+                                       long long M, int C) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sb = sums[c], sg = sums[C + c];
+    dbeta[c] += (float)sb;
+    dgamma[c] += (float)sg;
+    c1[c] = (float)(sb / (double)M);
+    c2[c] = (float)(sg / (double)M);
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
+  }
+}
+
+// dx = gamma * rstd * (g - c1 - xhat * c2)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, int ld_dy, const T* __restrict__ y, int ld_y,
+                                    const T* __restrict__ x, int ldx, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ c1, const float* __restrict__ c2, T* __restrict__ dx,
+                                    int ld_dx, long long M, int C) {
+  const int cg = C >> 3;
+  const long long total = M * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long r = i / cg;
+    F8 d = ld8(dy + r * ld_dy + g * 8);
+    const F8 v = ld8(x + r * ldx + g * 8);
+    if (y) {
+      const F8 yy = ld8(y + r * ld_y + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d.v[j] = yy.v[j] > 0.f ? d.v[j] : 0.f;
+    }
+    const F8 mu = ld8(mean + g * 8), rs = ld8(rstd + g * 8), ga = ld8(gamma + g * 8), a = ld8(c1 + g * 8),
+             b = ld8(c2 + g * 8);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (v.v[j] - mu.v[j]) * rs.v[j];
+      o.v[j] = ga.v[j] * rs.v[j] * (d.v[j] - a.v[j] - xh * b.v[j]);
+    }
+    st8(dx + r * ld_dx + g * 8, o);
+  }
+}
+
+static inline int grid_for(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  if (g > 148LL * 16) g = 148LL * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static inline bool bn_c_ok(int C) { return C >= 8 && (C & 7) == 0 && (C >> 3) <= 256; }
+
+extern "C" {
+
+int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream) {
+  if (M <= 0 || !bn_c_ok(C) || (ldx & 7)) return S2U_EINVAL;
+  const int nsub = 256 / (C >> 3);
+  const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
+  S2U_DISPATCH_T(dtype, {
+    S2U_ALLOW_SMEM(bn_stats_kernel<T>);
+    bn_stats_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+int s2u_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    long long* num_batches, float* scale, float* shift, float* save_mean, float* save_rstd,
+                    long long M, int C, float eps, float momentum, int training, void* stream) {
+  if (C <= 0) return S2U_EINVAL;
+  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, gamma, beta, running_mean, running_var, num_batches,
+                                                         scale, shift, save_mean, save_rstd, M, C, eps, momentum,
+                                                         training);
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+int s2u_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* resid, int ld_res,
+                 void* out, int ld_out, long long M, int C, int relu, int dtype, void* stream) {
+  if (M <= 0 || !bn_c_ok(C) || (ldx & 7) || (ld_out & 7) || (resid && (ld_res & 7))) return S2U_EINVAL;
+  S2U_DISPATCH_T(dtype, {
+    bn_apply_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x, ldx, scale, shift, (const T*)resid, ld_res, (T*)out, ld_out, M, C, relu);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+int s2u_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, void* g, int ld_g, long long M, int C, int dtype,
+                 void* stream) {
+  if (M <= 0 || (C & 7) || (ld_dy & 7) || (ld_y & 7) || (ld_g & 7)) return S2U_EINVAL;
+  S2U_DISPATCH_T(dtype, {
+    relu_bwd_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, ld_dy, (const T*)y,
+                                                                                   ld_y, (T*)g, ld_g, M, C);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+// y == null: plain BN backward; y given: backward through relu(bn(x)) using the saved output for the mask
+int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x, int ldx, const float* mean,
+               const float* rstd, const float* gamma, double* sums, float* dgamma, float* dbeta, float* c1, float* c2,
+               void* dx, int ld_dx, long long M, int C, int dtype, void* stream) {
+  if (M <= 0 || !bn_c_ok(C) || (ldx & 7) || (ld_dy & 7) || (ld_dx & 7) || (y && (ld_y & 7))) return S2U_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nsub = 256 / (C >> 3);
+  const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
+  S2U_DISPATCH_T(dtype, {
+    S2U_ALLOW_SMEM(bn_bwd_reduce_kernel<T>);
+    bn_bwd_reduce_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
+                                                                    (const T*)x, ldx, mean, rstd, sums, M, C);
+  })
+  S2U_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<1, 256, 0, st>>>(sums, dgamma, dbeta, c1, c2, M, C);
+  S2U_LAUNCH_CHECK();
+  S2U_DISPATCH_T(dtype, {
+    bn_bwd_apply_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
+                                                                       (const T*)x, ldx, mean, rstd, gamma, c1, c2,
+                                                                       (T*)dx, ld_dx, M, C);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

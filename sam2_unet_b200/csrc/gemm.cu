@@ -1,0 +1,570 @@
+// GEMM family for the Hiera trunk, adapters and (via im2col) the decoder convolutions.
+//
+//   C[M,N] = epilogue( A[M,K] . W[N,K]^T )          "TN" GEMM: both operands K-major (nn.Linear layout,
+//                                                    /root/reference/sam2/modeling/backbones/hieradet.py:53-54)
+//   G[P,Q] += sum_m A[m,P] . B[m,Q]                  weight-gradient GEMM (reduction over rows)
+//
+// Two implementations of the TN GEMM share one epilogue:
+//   * gemm_umma_kernel  — bf16, tcgen05.mma (UMMA M=128, N=BN, K=16) with the accumulator in TMEM, operands
+//                         staged by TMA (128-byte swizzle) through an mbarrier ring.  This is the product path
+//                         for bf16 mode.
+//   * gemm_simt_kernel  — fp32-accurate FFMA GEMM used by fp32 mode (TF32 is not accurate enough for the
+//                         1e-3 parity bar, SURVEY.md section 7 hard part 6) and for operand shapes the TMA
+//                         path cannot describe (row pitch not a multiple of 16 bytes).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------ epilogue
+
+template <typename T>
+struct EpiView {
+  const float* bias;
+  T* pre_out;
+  const T* aux;
+  const T* resid;
+  int ld_pre, ld_aux, ld_res, flags;
+  __host__ EpiView(const GemmEpi& e)
+      : bias(e.bias), pre_out((T*)e.pre_out), aux((const T*)e.aux), resid((const T*)e.resid), ld_pre(e.ld_pre),
+        ld_aux(e.ld_aux), ld_res(e.ld_res), flags(e.flags) {}
+};
+
+template <typename T>
+__device__ __forceinline__ float epi_scalar(const EpiView<T>& e, float v, long long row, int col) {
+  if (e.bias) v += e.bias[col];
+  if (e.pre_out) stf(e.pre_out + row * e.ld_pre + col, v);
+  if (e.flags & GEMM_GELU) v = gelu_f(v);
+  if (e.flags & GEMM_DGELU) v *= dgelu_f(ldf(e.aux + row * e.ld_aux + col));
+  if (e.flags & GEMM_RESID) v += ldf(e.resid + row * e.ld_res + col);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------- SIMT GEMM
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W,
+                                                       int ldw, T* __restrict__ C, int ldc, int M, int N, int K,
+                                                       EpiView<T> epi) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 2;          // 0..63 row inside the tile
+  const int lk = (tid & 3) * 4;     // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + lk + j;
+      const long long ra = m0 + lr;
+      const int rw = n0 + lr;
+      As[lk + j][lr] = (ra < M && k < K) ? ldf(A + ra * lda + k) : 0.f;
+      Ws[lk + j][lr] = (rw < N && k < K) ? ldf(W + (long long)rw * ldw + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      stf(C + row * ldc + col, epi_scalar(epi, acc[i][j], row, col));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- weight-gradient GEMM
+// G[p, q] += sum_{m in chunk} A[m, p] * B[m, q]; output offset p*ldg + (q % q_inner)*q_taps + q / q_inner
+// (q_inner = Q, q_taps = 1 for a plain matrix; for conv weights q = tap*Cin + ci maps to [Cout][Cin][taps]).
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_wgrad_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B,
+                                                        int ldb, float* __restrict__ G, int ldg, long long M, int P,
+                                                        int Q, int q_inner, int q_taps, int rows_per_split) {
+  constexpr int BP = 64, BQ = 64, BK = 16;
+  __shared__ float As[BK][BP + 4];
+  __shared__ float Bs[BK][BQ + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int p0 = blockIdx.y * BP, q0 = blockIdx.x * BQ;
+  const long long mbeg = (long long)blockIdx.z * rows_per_split;
+  const long long mend = min(M, mbeg + (long long)rows_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lc = tid & 63;          // column inside the tile (coalesced along P / Q)
+  const int lk = tid >> 6;          // 0..3
+  for (long long m0 = mbeg; m0 < mend; m0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long m = m0 + lk * 4 + j;
+      As[lk * 4 + j][lc] = (m < mend && p0 + lc < P) ? ldf(A + m * lda + p0 + lc) : 0.f;
+      Bs[lk * 4 + j][lc] = (m < mend && q0 + lc < Q) ? ldf(B + m * ldb + q0 + lc) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty * 4 + i;
+    if (p >= P) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = q0 + tx * 4 + j;
+      if (q >= Q) continue;
+      atomicAdd(G + (long long)p * ldg + (long long)(q % q_inner) * q_taps + q / q_inner, acc[i][j]);
+    }
+  }
+}
+
+// out[p] += sum_m A[m, p]   (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ A, int lda, float* __restrict__ out,
+                                                    long long M, int P, int rows_per_block) {
+  const int p = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int sub = threadIdx.x >> 6;
+  const long long mbeg = (long long)blockIdx.y * rows_per_block;
+  const long long mend = min(M, mbeg + (long long)rows_per_block);
+  float s = 0.f;
+  if (p < P)
+    for (long long m = mbeg + sub; m < mend; m += 4) s += ldf(A + m * lda + p);
+  __shared__ float red[4][64];
+  red[sub][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (sub == 0 && p < P) atomicAdd(out + p, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// --------------------------------------------------------------------------------- tcgen05 / TMA GEMM
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();   // a lost arrive must fail loudly, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO: unused for swizzled K-major layouts
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+constexpr int BM = 128, BK = 64;
+
+template <int BN, int STAGES>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;      // + alignment slack
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  // cute::UMMA::InstrDescriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both, N>>3 @17, M>>4 @24
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128) gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                       const __grid_constant__ CUtensorMap tma_b,
+                                                       bf16* __restrict__ C, int ldc, int M, int N, int K,
+                                                       EpiView<bf16> epi) {
+  using cfg = Cfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * STAGES);
+
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer: one elected thread fills the ring
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      mbar_expect_tx(full_bar(s), (uint32_t)cfg::STAGE_BYTES);
+      const uint32_t sa = smem_base + (uint32_t)s * cfg::STAGE_BYTES;
+      tma_load_2d(sa, &tma_a, full_bar(s), kb * BK, m0);
+      tma_load_2d(sa + cfg::A_BYTES, &tma_b, full_bar(s), kb * BK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer: one thread drives the tensor core; the accumulator lives in TMEM
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t sa = smem_base + (uint32_t)s * cfg::STAGE_BYTES;
+      const uint64_t adesc = smem_desc_sw128(sa);
+      const uint64_t bdesc = smem_desc_sw128(sa + cfg::A_BYTES);
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) {
+        // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+        tc_mma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), cfg::IDESC,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+      }
+      tc_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+    }
+    tc_commit(tmem_full_bar);             // accumulator complete
+  }
+  __syncwarp();
+
+  // ---- epilogue: 4 warps, warp w owns TMEM lanes [32w, 32w+32) = tile rows; one row per thread
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  const long long row = (long long)m0 + warp * 32 + lane;
+  const bool row_ok = row < M;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
+    tc_wait_ld();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = n0 + c * 32 + g * 8;
+      if (col >= N) continue;                       // N is a multiple of 8 (checked on the host)
+      F8 v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = __uint_as_float(r[g * 8 + j]);
+      if (epi.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] += __ldg(epi.bias + col + j);
+      }
+      if (epi.pre_out) st8(epi.pre_out + row * epi.ld_pre + col, v);
+      if (epi.flags & GEMM_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = gelu_f(v.v[j]);
+      }
+      if (epi.flags & GEMM_DGELU) {
+        const F8 a = ld8(epi.aux + row * epi.ld_aux + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] *= dgelu_f(a.v[j]);
+      }
+      if (epi.flags & GEMM_RESID) {
+        const F8 a = ld8(epi.resid + row * epi.ld_res + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] += a.v[j];
+      }
+      st8(C + row * ldc + col, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---- host side: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    h = h * 1000003u ^ (size_t)k.rows;
+    h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+
+// 2-D bf16 row-major [rows, cols] with pitch ld elements; box = box_rows x 64 columns, 128-byte swizzle.
+static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return S2U_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -100 - (int)r;
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
+                  const GemmEpi& e, cudaStream_t st) {
+  using cfg = Cfg<BN, STAGES>;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, W, N, K, ldw, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          cfg::SMEM_BYTES);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  gemm_umma_kernel<BN, STAGES><<<grid, 128, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, EpiView<bf16>(e));
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// can the TMA/UMMA path describe this problem?
+static bool supported(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int N, int K,
+                      const GemmEpi& e) {
+  if (!aligned16(A) || !aligned16(W) || !aligned16(C)) return false;
+  if ((lda % 8) || (ldw % 8) || (ldc % 8) || (N % 8) || K < 8) return false;
+  if (e.pre_out && (!aligned16(e.pre_out) || (e.ld_pre % 8))) return false;
+  if ((e.flags & GEMM_DGELU) && (!aligned16(e.aux) || (e.ld_aux % 8))) return false;
+  if ((e.flags & GEMM_RESID) && (!aligned16(e.resid) || (e.ld_res % 8))) return false;
+  return true;
+}
+
+}  // namespace umma
+
+// ------------------------------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+// backend: 0 = auto (tcgen05 for bf16 when describable, else SIMT), 1 = force SIMT, 2 = force tcgen05,
+//          16+bn = force tcgen05 with tile width bn (32/64/128/256; tuning and tests)
+int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const float* bias,
+             void* pre_out, int ld_pre, const void* aux, int ld_aux, const void* resid, int ld_res, int flags,
+             int dtype, int backend, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return M == 0 ? 0 : S2U_EINVAL;
+  if ((flags & GEMM_DGELU) && !aux) return S2U_EINVAL;
+  if ((flags & GEMM_RESID) && !resid) return S2U_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmEpi e{bias, pre_out, aux, resid, ld_pre, ld_aux, ld_res, flags};
+  const bool want_umma = dtype == S2U_BF16 && backend != 1;
+  if (want_umma && umma::supported(A, lda, W, ldw, C, ldc, N, K, e)) {
+    int bn = backend >= 16 ? backend - 16 : 0;
+    if (bn == 0) {
+      if (N <= 32) bn = 32;
+      else if (N <= 64) bn = 64;
+      else {
+        // wide tiles amortise the A read; narrow ones fill the 148 SMs when the grid is small
+        const long long t256 = (long long)ceil_div(M, 128) * ceil_div(N, 256);
+        bn = (t256 >= 148 && N >= 256) ? 256 : 128;
+      }
+    }
+    const bf16 *a = (const bf16*)A, *w = (const bf16*)W;
+    bf16* c = (bf16*)C;
+    switch (bn) {
+      case 32: return umma::launch<32, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 64: return umma::launch<64, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 128: return umma::launch<128, 3>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 256: return umma::launch<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      default: return S2U_EINVAL;
+    }
+  }
+  if (backend >= 2) return S2U_EUNSUPPORTED;
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  S2U_DISPATCH_T(dtype, {
+    gemm_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)A, lda, (const T*)W, ldw, (T*)C, ldc, M, N, K, EpiView<T>(e));
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+// G[P,Q] (fp32, accumulated) += A[M,P]^T . B[M,Q]
+int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int ldg, long long M, int P, int Q,
+                   int q_inner, int q_taps, int dtype, void* stream) {
+  if (M <= 0 || P <= 0 || Q <= 0) return S2U_EINVAL;
+  if (q_inner <= 0) { q_inner = Q; q_taps = 1; }
+  const int tiles = ceil_div(P, 64) * ceil_div(Q, 64);
+  int splits = (int)((M + 255) / 256);
+  const int want = (4 * 148 + tiles - 1) / tiles;
+  if (splits > want) splits = want;
+  if (splits < 1) splits = 1;
+  int rows = (int)((M + splits - 1) / splits);
+  rows = (rows + 15) / 16 * 16;
+  splits = (int)((M + rows - 1) / rows);
+  dim3 grid(ceil_div(Q, 64), ceil_div(P, 64), splits);
+  S2U_DISPATCH_T(dtype, {
+    gemm_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, lda, (const T*)B, ldb, G, ldg, M, P, Q,
+                                                                 q_inner, q_taps, rows);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[P] (fp32, accumulated) += column sums of A[M,P]
+int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype, void* stream) {
+  if (M <= 0 || P <= 0) return S2U_EINVAL;
+  int blocks_y = (int)((M + 511) / 512);
+  if (blocks_y > 256) blocks_y = 256;
+  const int rows = (int)((M + blocks_y - 1) / blocks_y);
+  dim3 grid(ceil_div(P, 64), blocks_y);
+  S2U_DISPATCH_T(dtype, {
+    colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, lda, out, M, P, rows);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

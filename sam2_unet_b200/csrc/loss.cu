@@ -1,0 +1,177 @@
+// structure_loss (/root/reference/train.py:21-29) forward and backward for up to three prediction maps that
+// share one mask (train.py:76-79), and the fused AdamW step (train.py:48-52,83).
+//
+//   weit = 1 + 5 |avgpool31x31(mask) - mask|      (stride 1, zero pad 15, divisor always 961)
+//   bce  = mean over the whole batch of BCE-with-logits  (the reference's reduce="none" is the legacy boolean
+//          kwarg, i.e. reduction="mean"; the weighted ratio that follows returns the same scalar)
+//   I_b  = sum sigma(p) m weit,  U_b = sum (sigma(p) + m) weit,  loss = bce + mean_b (1 - (I_b+1)/(U_b-I_b+1))
+//
+// Pass 1 (one CTA per 32x64 pixel tile): separable 31-tap box sum of the mask in shared memory, weit written
+// once, per-image partial sums for every head by warp shuffles + one fp64 atomic per CTA and quantity.
+// Pass 2: closed-form gradient.  Algorithmic traffic: 12 B/pixel/head (read logit,
+// read mask, write grad) + 8 B/pixel for weit.
+#include "common.cuh"
+
+constexpr int LT_H = 32, LT_W = 64, LR = 15;
+constexpr int MAXH = 3;
+
+struct LossPtrs { const float* pred[MAXH]; float* grad[MAXH]; };
+
+// sums layout (fp64): [head][b][0] = I, [head][b][1] = U, then bce[head] at offset nheads*B*2 + head
+__global__ void __launch_bounds__(256) loss_fwd_kernel(LossPtrs p, const float* __restrict__ mask,
+                                                      float* __restrict__ weit, double* __restrict__ sums, int B,
+                                                      int H, int W, int nheads) {
+  __shared__ float tile[LT_H + 2 * LR][LT_W + 2 * LR + 2];   // mask halo tile
+  __shared__ float hsum[LT_H + 2 * LR][LT_W + 1];            // horizontal 31-tap sums
+  __shared__ float red[8][MAXH * 3];
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * LT_H, x0 = blockIdx.x * LT_W;
+  const float* mb = mask + (long long)b * H * W;
+  for (int i = threadIdx.x; i < (LT_H + 2 * LR) * (LT_W + 2 * LR); i += 256) {
+    const int ty = i / (LT_W + 2 * LR), tx = i - ty * (LT_W + 2 * LR);
+    const int y = y0 + ty - LR, x = x0 + tx - LR;
+    tile[ty][tx] = (y >= 0 && y < H && x >= 0 && x < W) ? mb[(long long)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (LT_H + 2 * LR) * LT_W; i += 256) {
+    const int ty = i / LT_W, tx = i - ty * LT_W;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k <= 2 * LR; ++k) s += tile[ty][tx + k];
+    hsum[ty][tx] = s;
+  }
+  __syncthreads();
+  float acc[MAXH * 3];
+#pragma unroll
+  for (int k = 0; k < MAXH * 3; ++k) acc[k] = 0.f;
+  for (int i = threadIdx.x; i < LT_H * LT_W; i += 256) {
+    const int ty = i / LT_W, tx = i - ty * LT_W;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k <= 2 * LR; ++k) s += hsum[ty + k][tx];
+    const float m = tile[ty + LR][tx + LR];
+    const float wv = 1.f + 5.f * fabsf(s * (1.f / 961.f) - m);
+    const long long o = ((long long)b * H + y) * W + x;
+    weit[o] = wv;
+    for (int h = 0; h < nheads; ++h) {
+      const float pv = p.pred[h][o];
+      const float sg = 1.f / (1.f + __expf(-pv));
+      acc[h * 3 + 0] += sg * m * wv;
+      acc[h * 3 + 1] += (sg + m) * wv;
+      acc[h * 3 + 2] += fmaxf(pv, 0.f) - pv * m + log1pf(__expf(-fabsf(pv)));
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < MAXH * 3; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nheads * 3) {
+    float t = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    const int h = threadIdx.x / 3, q = threadIdx.x % 3;
+    if (q < 2) atomicAdd(sums + ((long long)h * B + b) * 2 + q, (double)t);
+    else atomicAdd(sums + (long long)nheads * B * 2 + h, (double)t);
+  }
+}
+
+// loss[h] = bce_h / (B H W) + (1/B) sum_b (1 - N_b / D_b)
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, float* __restrict__ loss, int B, int H, int W,
+                                     int nheads) {
+  const int h = threadIdx.x;
+  if (h >= nheads) return;
+  double l = sums[(long long)nheads * B * 2 + h] / ((double)B * H * W);
+  for (int b = 0; b < B; ++b) {
+    const double I = sums[((long long)h * B + b) * 2], U = sums[((long long)h * B + b) * 2 + 1];
+    l += (1.0 - (I + 1.0) / (U - I + 1.0)) / (double)B;
+  }
+  loss[h] = (float)l;
+}
+
+// grad = gscale[h] * [ (s - m)/(B H W) - (1/B) s (1-s) w (m D - (1-m) N) / D^2 ]
+__global__ void loss_bwd_kernel(LossPtrs p, const float* __restrict__ mask, const float* __restrict__ weit,
+                                const double* __restrict__ sums, const float* __restrict__ gscale, int B, int H,
+                                int W, int nheads) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)B * hw;
+  const float inv_n = 1.f / (float)total, inv_b = 1.f / (float)B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const float m = mask[i], wv = weit[i];
+    for (int h = 0; h < nheads; ++h) {
+      const double I = sums[((long long)h * B + b) * 2], U = sums[((long long)h * B + b) * 2 + 1];
+      const float N = (float)(I + 1.0), D = (float)(U - I + 1.0);
+      const float pv = p.pred[h][i];
+      const float sg = 1.f / (1.f + __expf(-pv));
+      const float g = (sg - m) * inv_n - inv_b * sg * (1.f - sg) * wv * (m * D - (1.f - m) * N) / (D * D);
+      p.grad[h][i] = (gscale ? gscale[h] : 1.f) * g;
+    }
+  }
+}
+
+// AdamW on one flat fp32 buffer.  hyper (device): [0] lr, [1] 1-beta1^t, [2] 1-beta2^t, [3] gradient scale
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, const float* __restrict__ hyper, float beta1,
+                             float beta2, float eps, float wd) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gv = g[i] * gs;
+    float pv = p[i] * (1.f - lr * wd);
+    const float mv = beta1 * m[i] + (1.f - beta1) * gv;
+    const float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    pv -= step_size * mv / denom;
+    p[i] = pv;
+    m[i] = mv;
+    v[i] = vv;
+  }
+}
+
+extern "C" {
+
+int s2u_structure_loss_fwd(const float* pred0, const float* pred1, const float* pred2, const float* mask, float* weit,
+                           double* sums, float* loss, int B, int H, int W, int nheads, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || nheads < 1 || nheads > MAXH) return S2U_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  LossPtrs p{{pred0, pred1, pred2}, {nullptr, nullptr, nullptr}};
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * ((size_t)nheads * B * 2 + nheads), st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(ceil_div(W, LT_W), ceil_div(H, LT_H), B);
+  loss_fwd_kernel<<<grid, 256, 0, st>>>(p, mask, weit, sums, B, H, W, nheads);
+  S2U_LAUNCH_CHECK();
+  loss_finalize_kernel<<<1, 32, 0, st>>>(sums, loss, B, H, W, nheads);
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+int s2u_structure_loss_bwd(const float* pred0, const float* pred1, const float* pred2, const float* mask,
+                           const float* weit, const double* sums, const float* gscale, float* grad0, float* grad1,
+                           float* grad2, int B, int H, int W, int nheads, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || nheads < 1 || nheads > MAXH) return S2U_EINVAL;
+  LossPtrs p{{pred0, pred1, pred2}, {grad0, grad1, grad2}};
+  long long total = (long long)B * H * W;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  loss_bwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, mask, weit, sums, gscale, B, H, W, nheads);
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1, float beta2,
+              float eps, float wd, void* stream) {
+  if (n <= 0) return S2U_EINVAL;
+  long long gsz = (n + 255) / 256;
+  if (gsz > 148 * 16) gsz = 148 * 16;
+  adamw_kernel<<<(int)gsz, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, beta1, beta2, eps, wd);
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
