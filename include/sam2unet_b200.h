@@ -111,8 +111,9 @@ int s2u_structure_loss_fwd(const float* pred0, const float* pred1, const float* 
 int s2u_structure_loss_bwd(const float* pred0, const float* pred1, const float* pred2, const float* mask,
                            const float* weit, const double* sums, const float* gscale, float* grad0, float* grad1,
                            float* grad2, int B, int H, int W, int nheads, void* stream);
-/* hyper (device): lr, 1-beta1^t, 1-beta2^t, gradient scale (1/world_size under data parallelism). */
-int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1,
+/* hyper (device fp32[4]): lr, gradient scale (1/world_size under data parallelism), beta1^t, beta2^t; the last two
+ * start at 1 and are advanced on the device by every call, so the step is replayable from a CUDA graph. */
+int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, float* hyper, float beta1,
               float beta2, float eps, float wd, void* stream);
 
 #ifdef __cplusplus

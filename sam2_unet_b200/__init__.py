@@ -1,0 +1,14 @@
+"""sam2_unet_b200 — B200-native (sm_100a) SAM2-UNet training / inference hot path.
+
+Public surface (mirrors /root/reference/SAM2UNet.py and train.py):
+    SAM2UNet(checkpoint_path="", *, model_cfg="sam2_hiera_s.yaml", dtype="bf16")   nn.Module, forward -> out, out1, out2
+    structure_loss(pred, mask)                                                     train.py:21-29
+    FusedAdamW, TrainStep                                                          train.py:48-52,66-86
+"""
+from . import _lib  # noqa: F401
+from .config import trunk_config  # noqa: F401
+from .loss import structure_loss, structure_loss3  # noqa: F401
+from .model import SAM2UNet  # noqa: F401
+from .optim import FusedAdamW, TrainStep, cosine_lr  # noqa: F401
+
+__all__ = ["SAM2UNet", "structure_loss", "structure_loss3", "FusedAdamW", "TrainStep", "cosine_lr", "trunk_config"]

@@ -114,11 +114,18 @@ __global__ void loss_bwd_kernel(LossPtrs p, const float* __restrict__ mask, cons
   }
 }
 
-// AdamW on one flat fp32 buffer.  hyper (device): [0] lr, [1] 1-beta1^t, [2] 1-beta2^t, [3] gradient scale
+// AdamW on one flat fp32 buffer.  hyper (device, fp32): [0] lr, [1] gradient scale, [2] beta1^t, [3] beta2^t.
+// The step counter lives on the device ([2], [3] are advanced by adamw_tick_kernel right before the update), so a
+// captured CUDA graph replays the step without any host-side hyper-parameter traffic.
+__global__ void adamw_tick_kernel(float* __restrict__ hyper, float beta1, float beta2) {
+  hyper[2] *= beta1;
+  hyper[3] *= beta2;
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, const float* __restrict__ hyper, float beta1,
                              float beta2, float eps, float wd) {
-  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
+  const float lr = hyper[0], gs = hyper[1], bc1 = 1.f - hyper[2], bc2 = 1.f - hyper[3];
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -164,11 +171,13 @@ int s2u_structure_loss_bwd(const float* pred0, const float* pred1, const float* 
   return 0;
 }
 
-int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1, float beta2,
+int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, float* hyper, float beta1, float beta2,
               float eps, float wd, void* stream) {
   if (n <= 0) return S2U_EINVAL;
   long long gsz = (n + 255) / 256;
   if (gsz > 148 * 16) gsz = 148 * 16;
+  adamw_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, beta1, beta2);
+  S2U_LAUNCH_CHECK();
   adamw_kernel<<<(int)gsz, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, beta1, beta2, eps, wd);
   S2U_LAUNCH_CHECK();
   return 0;

@@ -1,0 +1,626 @@
+"""Forward / backward schedule of SAM2-UNet on the C-ABI kernels.
+
+The engine walks the reference's data flow (/root/reference/SAM2UNet.py:164-173 and
+sam2/modeling/backbones/hieradet.py:278-292,132-167) as an explicit list of kernel launches, keeps the
+tensors the backward needs on a tape, and runs the hand-derived backward of every stage.  PyTorch is used
+for device memory and streams only: every arithmetic operation on the path is a kernel of
+libsam2unet_b200.so (no ATen math, no cuBLAS/cuDNN, no CPU fallback).
+
+Data layout: NHWC tokens [B*H*W, C] in the compute dtype T (fp32 or bf16) everywhere inside the model;
+NCHW only at the public edges (the input image, the three [B,1,S,S] fp32 logit maps).
+Frozen trunk weights are held once in T in both orientations (W for the forward, W^T for the input
+gradient: the trunk needs no weight gradient, SAM2UNet.py:146-147).  Trainable parameters live in one flat
+fp32 master buffer (the nn.Parameters are views of it, state-dict layout unchanged) with a matching flat
+gradient buffer, so AdamW and the data-parallel all-reduce are single flat operations.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .config import TrunkConfig
+from .resample_tables import ResampleTables
+
+GELU, DGELU, RESID = 1, 2, 4
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class Ops:
+    """Thin typed wrappers over the C ABI; `dt` selects fp32 (0) or bf16 (1) activations."""
+
+    def __init__(self, dtype: torch.dtype, device: torch.device, gemm_backend: int = 0):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("dtype must be torch.float32 or torch.bfloat16")
+        self.T = dtype
+        self.dt = 0 if dtype == torch.float32 else 1
+        self.device = device
+        self.gemm_backend = gemm_backend
+        _lib.load()
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, *shape, dtype=None) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype or self.T, device=self.device)
+
+    # C[M,N] = epi(A[M,K] W[N,K]^T)
+    def gemm(self, A, W, C, bias=None, pre_out=None, aux=None, resid=None, flags=0, M=None, N=None, K=None,
+             lda=None, ldw=None, ldc=None, ld_pre=None, ld_aux=None, ld_res=None, backend=None):
+        M = A.shape[0] if M is None else M
+        K = A.shape[1] if K is None else K
+        N = W.shape[0] if N is None else N
+        _lib.call("s2u_gemm", A.data_ptr(), lda or A.stride(0), W.data_ptr(), ldw or W.stride(0), C.data_ptr(),
+                  ldc or C.stride(0), M, N, K, _ptr(bias), _ptr(pre_out),
+                  (ld_pre or pre_out.stride(0)) if pre_out is not None else 0, _ptr(aux),
+                  (ld_aux or aux.stride(0)) if aux is not None else 0, _ptr(resid),
+                  (ld_res or resid.stride(0)) if resid is not None else 0, flags, self.dt,
+                  self.gemm_backend if backend is None else backend, self.stream)
+        return C
+
+    def wgrad(self, A, B, G, M=None, P=None, Q=None, lda=None, ldb=None, ldg=None, q_inner=0, q_taps=0):
+        M = A.shape[0] if M is None else M
+        P = A.shape[1] if P is None else P
+        Q = B.shape[1] if Q is None else Q
+        _lib.call("s2u_gemm_wgrad", A.data_ptr(), lda or A.stride(0), B.data_ptr(), ldb or B.stride(0), G.data_ptr(),
+                  ldg if ldg is not None else Q, M, P, Q, q_inner, q_taps, self.dt, self.stream)
+
+    def colsum(self, A, out, M=None, P=None, lda=None):
+        _lib.call("s2u_colsum", A.data_ptr(), lda or A.stride(0), out.data_ptr(), A.shape[0] if M is None else M,
+                  A.shape[1] if P is None else P, self.dt, self.stream)
+
+    def ln_fwd(self, x, gamma, beta, y, mean, rstd, R, C):
+        _lib.call("s2u_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
+                  _ptr(rstd), R, C, 1e-6, self.dt, self.stream)
+
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dres, dx, R, C):
+        _lib.call("s2u_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), R, C, self.dt, self.stream)
+
+    def dgelu_mul(self, dy, pre, out):
+        _lib.call("s2u_dgelu_mul", dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), self.dt, self.stream)
+
+    def add(self, a, b, out):
+        _lib.call("s2u_add", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), self.dt, self.stream)
+
+    def maxpool_fwd(self, x, out, B, H, W, C):
+        _lib.call("s2u_maxpool2_fwd", x.data_ptr(), out.data_ptr(), B, H, W, C, self.dt, self.stream)
+
+    def maxpool_bwd(self, x, dout, dx, B, H, W, C):
+        _lib.call("s2u_maxpool2_bwd", x.data_ptr(), dout.data_ptr(), dx.data_ptr(), B, H, W, C, self.dt, self.stream)
+
+    def cast(self, src, dst, R, C, transpose=False):
+        _lib.call("s2u_cast", src.data_ptr(), dst.data_ptr(), R, C, 1 if transpose else 0, self.dt, self.stream)
+
+    def attn_fwd(self, qkv, bias, out, lse, B, H, W, nh, hd, window, pool):
+        _lib.call("s2u_win_attn_fwd", qkv.data_ptr(), bias.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, W, nh,
+                  hd, window, 1 if pool else 0, self.dt, self.stream)
+
+    def attn_bwd(self, qkv, bias, out, lse, dout, dqkv, B, H, W, nh, hd, window, pool):
+        _lib.call("s2u_win_attn_bwd", qkv.data_ptr(), bias.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                  dout.data_ptr(), dqkv.data_ptr(), B, H, W, nh, hd, window, 1 if pool else 0, self.dt, self.stream)
+
+    def patch_embed(self, x, w, bias, pos, out, B, S, E):
+        _lib.call("s2u_patch_embed", x.data_ptr(), w.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(), B,
+                  S, E, self.dt, self.stream)
+
+    def im2col(self, x, ldx, out, B, H, W, Cin, KH, KW, dh, dw, ph, pw):
+        _lib.call("s2u_im2col", x.data_ptr(), ldx, out.data_ptr(), B, H, W, Cin, KH, KW, dh, dw, ph, pw, self.dt,
+                  self.stream)
+
+    def conv_weight_pack(self, w, wf, wd, Cout, Cin, KH, KW):
+        _lib.call("s2u_conv_weight_pack", w.data_ptr(), _ptr(wf), _ptr(wd), Cout, Cin, KH, KW, self.dt, self.stream)
+
+    def bn_stats(self, x, ldx, sums, M, C):
+        _lib.call("s2u_bn_stats", x.data_ptr(), ldx, sums.data_ptr(), M, C, self.dt, self.stream)
+
+    def bn_finalize(self, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, rstd, M, C, training):
+        _lib.call("s2u_bn_finalize", sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                  _ptr(nbt), scale.data_ptr(), shift.data_ptr(), _ptr(mean), _ptr(rstd), M, C, 1e-5, 0.1,
+                  1 if training else 0, self.stream)
+
+    def bn_apply(self, x, ldx, scale, shift, resid, ld_res, out, ld_out, M, C, relu):
+        _lib.call("s2u_bn_apply", x.data_ptr() if isinstance(x, torch.Tensor) else x, ldx,
+                  scale.data_ptr() if isinstance(scale, torch.Tensor) else scale,
+                  shift.data_ptr() if isinstance(shift, torch.Tensor) else shift, _ptr(resid), ld_res,
+                  out.data_ptr() if isinstance(out, torch.Tensor) else out, ld_out, M, C, 1 if relu else 0, self.dt,
+                  self.stream)
+
+    def relu_bwd(self, dy, ld_dy, y, ld_y, g, ld_g, M, C):
+        _lib.call("s2u_relu_bwd", dy.data_ptr(), ld_dy, y.data_ptr(), ld_y, g.data_ptr(), ld_g, M, C, self.dt,
+                  self.stream)
+
+    def bn_bwd(self, dy, ld_dy, y, ld_y, x, ldx, mean, rstd, gamma, sums, dgamma, dbeta, c1, c2, dx, ld_dx, M, C):
+        _lib.call("s2u_bn_bwd", dy.data_ptr(), ld_dy, _ptr(y), ld_y, x.data_ptr(), ldx, mean.data_ptr(),
+                  rstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                  c1.data_ptr(), c2.data_ptr(), dx.data_ptr(), ld_dx, M, C, self.dt, self.stream)
+
+    def resample_fwd(self, x, ldx, out_ptr, ld_out, B, Hi, Ho, C, tab: ResampleTables):
+        f = tab.fwd_ptrs()
+        _lib.call("s2u_resample_fwd", x.data_ptr(), ldx, out_ptr, ld_out, B, Hi, Hi, Ho, Ho, C, *f, *f, self.dt,
+                  self.stream)
+
+    def resample_bwd(self, dout_ptr, ld_do, dx, ld_dx, B, Hi, Ho, C, tab: ResampleTables):
+        b = tab.bwd_ptrs()
+        _lib.call("s2u_resample_bwd", dout_ptr, ld_do, dx.data_ptr(), ld_dx, B, Hi, Hi, Ho, Ho, C, *b, *b, self.dt,
+                  self.stream)
+
+    def resample1_fwd(self, x, out, B, Hi, Ho, tab):
+        f = tab.fwd_ptrs()
+        _lib.call("s2u_resample1_fwd", x.data_ptr(), out.data_ptr(), B, Hi, Hi, Ho, Ho, *f, *f, self.stream)
+
+    def resample1_bwd(self, dout, dx, B, Hi, Ho, tab):
+        b = tab.bwd_ptrs()
+        _lib.call("s2u_resample1_bwd", dout.data_ptr(), dx.data_ptr(), B, Hi, Hi, Ho, Ho, *b, *b, self.stream)
+
+    def head_fwd(self, feat, ldf, w, bias, out, M):
+        _lib.call("s2u_head_fwd", feat.data_ptr(), ldf, w.data_ptr(), bias.data_ptr(), out.data_ptr(), M, 64, self.dt,
+                  self.stream)
+
+    def head_bwd(self, feat, ldf, w, dlogit, dfeat, ld_df, accumulate, dw, db, M):
+        _lib.call("s2u_head_bwd", feat.data_ptr(), ldf, w.data_ptr(), dlogit.data_ptr(), dfeat.data_ptr(), ld_df,
+                  1 if accumulate else 0, dw.data_ptr(), db.data_ptr(), M, 64, self.dt, self.stream)
+
+
+# ------------------------------------------------------------------------------------------------- engine
+
+
+@dataclass
+class _ConvSpec:
+    """One conv+BN unit of the RFB / decoder: where its parameters live in the flat buffers."""
+    name: str            # state-dict prefix of the conv (e.g. "rfb1.branch1.1.conv")
+    bn: str              # state-dict prefix of its BatchNorm
+    cin: int
+    kh: int
+    kw: int
+    dil: int
+
+
+class Engine:
+    def __init__(self, cfg: TrunkConfig, model: torch.nn.Module, dtype: torch.dtype, device, gemm_backend: int = 0):
+        self.cfg = cfg
+        self.model = model
+        self.device = torch.device(device)
+        self.ops = Ops(dtype, self.device, gemm_backend)
+        self.T = dtype
+        self._frozen: Dict[str, torch.Tensor] = {}
+        self._shadow: Dict[str, torch.Tensor] = {}
+        self._pos_cache: Dict[int, torch.Tensor] = {}
+        self._bn_ws: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.tape: Optional[dict] = None
+        self._prepare_frozen()
+        self._shadow_version = -1
+
+    # ------------------------------------------------------------------------------------------ weights
+
+    def _prepare_frozen(self):
+        """One-time re-layout of the frozen trunk (setup, not the hot path): W and W^T in the compute dtype."""
+        sd = dict(self.model.named_parameters())
+        T = self.T
+        fz = self._frozen
+        for i, spec in enumerate(self.cfg.blocks):
+            p = f"encoder.blocks.{i}.block."
+            for nm in ("attn.qkv", "attn.proj", "mlp.layers.0", "mlp.layers.1") + (("proj",) if spec.dim != spec.dim_out else ()):
+                w = sd[p + nm + ".weight"].detach()
+                fz[p + nm + ".w"] = w.to(T).contiguous()
+                fz[p + nm + ".wt"] = w.t().to(T).contiguous()
+                fz[p + nm + ".b"] = sd[p + nm + ".bias"].detach().float().contiguous()
+            for nm in ("norm1", "norm2"):
+                fz[p + nm + ".g"] = sd[p + nm + ".weight"].detach().float().contiguous()
+                fz[p + nm + ".b"] = sd[p + nm + ".bias"].detach().float().contiguous()
+        fz["pe.w"] = sd["encoder.patch_embed.proj.weight"].detach().float().contiguous()
+        fz["pe.b"] = sd["encoder.patch_embed.proj.bias"].detach().float().contiguous()
+        self._pos_cache.clear()
+
+    def _pos_table(self, hp: int) -> torch.Tensor:
+        """hieradet.py:268-276: input-independent, so it is built once per resolution (setup, torch ops)."""
+        if hp not in self._pos_cache:
+            enc = self.model.encoder
+            pe, pw = enc.pos_embed.detach().float(), enc.pos_embed_window.detach().float()
+            pos = F.interpolate(pe, size=(hp, hp), mode="bicubic")
+            pos = pos + pw.tile([a // b for a, b in zip(pos.shape, pw.shape)])
+            self._pos_cache[hp] = pos.permute(0, 2, 3, 1).contiguous().view(hp, hp, -1)
+        return self._pos_cache[hp]
+
+    def refresh_shadows(self):
+        """Compute-dtype operands of the TRAINABLE weights, rebuilt from the fp32 masters after every update."""
+        flat = self.model.flat
+        if self._shadow_version == flat.version:
+            return
+        ops, sh, T = self.ops, self._shadow, self.T
+        P = flat.views
+        for i, spec in enumerate(self.cfg.blocks):
+            p = f"encoder.blocks.{i}.prompt_learn."
+            C = spec.dim
+            for nm, (r, c) in (("0", (32, C)), ("2", (C, 32))):
+                key = p + nm
+                if key + ".w" not in sh:
+                    sh[key + ".w"] = ops.empty(r, c)
+                    sh[key + ".wt"] = ops.empty(c, r)
+                ops.cast(P[key + ".weight"], sh[key + ".w"], r, c, False)
+                ops.cast(P[key + ".weight"], sh[key + ".wt"], r, c, True)
+        for cs in self.model.conv_units:
+            key = cs.name
+            taps = cs.kh * cs.kw
+            if key + ".wf" not in sh:
+                sh[key + ".wf"] = ops.empty(64, taps * cs.cin)
+                sh[key + ".wd"] = ops.empty(cs.cin, taps * 64)
+            ops.conv_weight_pack(P[key + ".weight"], sh[key + ".wf"], sh[key + ".wd"], 64, cs.cin, cs.kh, cs.kw)
+        self._shadow_version = flat.version
+
+    def _bn_workspace(self, key: str, C: int) -> Dict[str, torch.Tensor]:
+        ws = self._bn_ws.get(key)
+        if ws is None:
+            dev = self.device
+            ws = dict(sums=torch.zeros(2 * C, dtype=torch.float64, device=dev),
+                      scale=torch.empty(C, dtype=torch.float32, device=dev),
+                      shift=torch.empty(C, dtype=torch.float32, device=dev),
+                      c1=torch.empty(C, dtype=torch.float32, device=dev),
+                      c2=torch.empty(C, dtype=torch.float32, device=dev))
+            self._bn_ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------ forward
+
+    def forward(self, x: torch.Tensor, training: bool, save: bool):
+        """x [B,3,S,S] fp32 NCHW -> (out, out1, out2) fp32 [B,1,S,S]; `save` keeps the tape for backward()."""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise ValueError("expected a square [B,3,S,S] image batch")
+        B, S = x.shape[0], x.shape[2]
+        if S % 32:
+            raise ValueError("input side must be a multiple of 32 (hieradet.py:272-274 tiles the window embedding)")
+        ops, cfg, fz = self.ops, self.cfg, self._frozen
+        self.refresh_shadows()
+        x = x.contiguous().float()
+        tape = dict(B=B, S=S, blocks=[], training=training) if save else None
+        H = S // 4
+        E = cfg.embed_dim
+        t = ops.empty(B * H * H, E)
+        ops.patch_embed(x, fz["pe.w"], fz["pe.b"], self._pos_table(H), t, B, S, E)
+        feats = []
+        W = H
+        for i, spec in enumerate(cfg.blocks):
+            t, H, W = self._block_fwd(i, spec, t, B, H, W, tape)
+            if spec.stage_end:
+                feats.append((t, H))
+        outs = self._decoder_fwd(feats, B, S, training, tape)
+        if save:
+            self.tape = tape
+        return outs
+
+    def _block_fwd(self, i, spec, x, B, H, W, tape):
+        ops, fz, sh = self.ops, self._frozen, self._shadow
+        P = self.model.flat.views
+        p = f"encoder.blocks.{i}.block."
+        a = f"encoder.blocks.{i}.prompt_learn."
+        C, C2, nh = spec.dim, spec.dim_out, spec.num_heads
+        hd = C2 // nh
+        R = B * H * W
+        f32 = torch.float32
+        # adapter (SAM2UNet.py:61-63): xa = x + gelu(gelu(x W1^T + b1) W2^T + b2)
+        h1, u = ops.empty(R, 32), ops.empty(R, 32)
+        ops.gemm(x, sh[a + "0.w"], u, bias=P[a + "0.bias"], pre_out=h1, flags=GELU)
+        h2, xa = ops.empty(R, C), ops.empty(R, C)
+        ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=x, flags=GELU | RESID)
+        # norm1 (hieradet.py:134)
+        n1 = ops.empty(R, C)
+        mean1, rstd1 = ops.empty(R, dtype=f32), ops.empty(R, dtype=f32)
+        ops.ln_fwd(xa, fz[p + "norm1.g"], fz[p + "norm1.b"], n1, mean1, rstd1, R, C)
+        pr = None
+        Ho, Wo = H, W
+        if C != C2:                                   # hieradet.py:137-138: shortcut = pool(proj(norm1(x)))
+            pr = ops.empty(R, C2)
+            ops.gemm(n1, fz[p + "proj.w"], pr, bias=fz[p + "proj.b"])
+            Ho, Wo = H // 2, W // 2
+            sc = ops.empty(B * Ho * Wo, C2)
+            ops.maxpool_fwd(pr, sc, B, H, W, C2)
+        else:
+            sc = xa
+        Ro = B * Ho * Wo
+        # qkv on real tokens only; padding, windows, q-pool live inside the attention kernel
+        qkv = ops.empty(R, 3 * C2)
+        ops.gemm(n1, fz[p + "attn.qkv.w"], qkv, bias=fz[p + "attn.qkv.b"])
+        o = ops.empty(Ro, C2)
+        lse = ops.empty(Ro, nh, dtype=f32)
+        ops.attn_fwd(qkv, fz[p + "attn.qkv.b"], o, lse, B, H, W, nh, hd, spec.window, spec.q_pool)
+        y = ops.empty(Ro, C2)
+        ops.gemm(o, fz[p + "attn.proj.w"], y, bias=fz[p + "attn.proj.b"], resid=sc, flags=RESID)
+        n2 = ops.empty(Ro, C2)
+        mean2, rstd2 = ops.empty(Ro, dtype=f32), ops.empty(Ro, dtype=f32)
+        ops.ln_fwd(y, fz[p + "norm2.g"], fz[p + "norm2.b"], n2, mean2, rstd2, Ro, C2)
+        hid = ops.empty(Ro, 4 * C2)
+        act = ops.empty(Ro, 4 * C2)
+        ops.gemm(n2, fz[p + "mlp.layers.0.w"], act, bias=fz[p + "mlp.layers.0.b"],
+                 pre_out=hid if tape is not None else None, flags=GELU)
+        z = ops.empty(Ro, C2)
+        ops.gemm(act, fz[p + "mlp.layers.1.w"], z, bias=fz[p + "mlp.layers.1.b"], resid=y, flags=RESID)
+        if tape is not None:
+            tape["blocks"].append(dict(x=x, h1=h1, u=u, h2=h2, xa=xa, mean1=mean1, rstd1=rstd1, pr=pr, qkv=qkv, o=o,
+                                       lse=lse, y=y, mean2=mean2, rstd2=rstd2, hid=hid, H=H, W=W, Ho=Ho, Wo=Wo))
+        return z, Ho, Wo
+
+    # conv (+ BN (+ residual) (+ ReLU)) on NHWC rows.  `src`: (tensor, ld, channel offset) of the input map.
+    def _conv_bn(self, cs: _ConvSpec, src, B, H, out, ld_out, out_off, relu, training, tape, resid=None, ld_res=0):
+        ops, sh = self.ops, self._shadow
+        P, Bf = self.model.flat.views, self.model.flat.buffers
+        x, ldx, xoff = src
+        M = B * H * H
+        taps = cs.kh * cs.kw
+        esz = x.element_size()
+        if taps == 1:
+            col, ldcol = x, ldx
+            col_ptr_off = xoff
+        else:
+            col = ops.empty(M, taps * cs.cin)
+            ph, pw = cs.dil * (cs.kh - 1) // 2, cs.dil * (cs.kw - 1) // 2
+            xin = x.view(-1)[xoff:] if xoff else x
+            ops.im2col(xin, ldx, col, B, H, H, cs.cin, cs.kh, cs.kw, cs.dil, cs.dil, ph, pw)
+            ldcol, col_ptr_off = taps * cs.cin, 0
+        raw = ops.empty(M, 64)
+        A = col.view(-1)[col_ptr_off:] if col_ptr_off else col
+        ops.gemm(A, sh[cs.name + ".wf"], raw, M=M, N=64, K=taps * cs.cin, lda=ldcol, ldw=taps * cs.cin, ldc=64)
+        ws = self._bn_workspace(cs.bn, 64)
+        mean = rstd = None
+        if training:
+            ops.bn_stats(raw, 64, ws["sums"], M, 64)
+            mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
+        ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
+                        Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"], mean,
+                        rstd, M, 64, training)
+        out_ptr = out.data_ptr() + out_off * esz
+        ops.bn_apply(raw, 64, ws["scale"], ws["shift"], resid, ld_res, out_ptr, ld_out, M, 64, relu)
+        if tape is not None:
+            tape["convs"][cs.name] = dict(col=col, ldcol=ldcol, coff=col_ptr_off, raw=raw, mean=mean, rstd=rstd, B=B,
+                                          H=H)
+
+    def _decoder_fwd(self, feats, B, S, training, tape):
+        ops = self.ops
+        units = {cs.name: cs for cs in self.model.conv_units}
+        P = self.model.flat.views
+        if tape is not None:
+            tape["convs"] = {}
+            tape["dec"] = {}
+        rfb_out = []
+        cats = []
+        for k, (f, H) in enumerate(feats):
+            r = f"rfb{k + 1}."
+            M = B * H * H
+            Cin = f.shape[1]
+            # up-stage concat buffer [skip | upsampled]: the RFB output is written straight into its left half
+            if k < 3:
+                dst, ld_dst = ops.empty(M, 128), 128
+            else:
+                dst, ld_dst = ops.empty(M, 64), 64
+            cat = ops.empty(M, 256)
+            s1 = ops.empty(M, 64)      # per-branch scratch maps
+            s2 = ops.empty(M, 64)
+            src = (f, Cin, 0)
+            self._conv_bn(units[r + "branch0.0.conv"], src, B, H, cat, 256, 0, False, training, tape)
+            inter = {}
+            for bi in (1, 2, 3):
+                t0, t1, t2 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
+                self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape)
+                self._conv_bn(units[r + f"branch{bi}.1.conv"], (t0, 64, 0), B, H, t1, 64, 0, False, training, tape)
+                self._conv_bn(units[r + f"branch{bi}.2.conv"], (t1, 64, 0), B, H, t2, 64, 0, False, training, tape)
+                self._conv_bn(units[r + f"branch{bi}.3.conv"], (t2, 64, 0), B, H, cat, 256, 64 * bi, False, training,
+                              tape)
+                inter[bi] = (t0, t1, t2)
+            res = ops.empty(M, 64)
+            self._conv_bn(units[r + "conv_res.conv"], src, B, H, res, 64, 0, False, training, tape)
+            self._conv_bn(units[r + "conv_cat.conv"], (cat, 256, 0), B, H, dst, ld_dst, 0, True, training, tape,
+                          resid=res, ld_res=64)
+            rfb_out.append((dst, ld_dst, H))
+            if tape is not None:
+                tape["dec"][r] = dict(f=f, cat=cat, dst=dst, ld_dst=ld_dst, H=H, Cin=Cin)
+            del s1, s2
+        # decoder: up1(x4, x3) -> side1 ; up2(., x2) -> side2 ; up3(., x1) -> head   (SAM2UNet.py:167-172)
+        cur, cur_ld, cur_h = rfb_out[3]
+        outs = {}
+        for stage, (k, head_name, scale) in enumerate(((2, "side1", 16), (1, "side2", 8), (0, "head", 4))):
+            u = f"up{stage + 1}."
+            catb, _, H = rfb_out[k]
+            if H != 2 * cur_h:
+                raise _lib.KernelError("decoder expects exact 2x pyramid levels (input side multiple of 32)")
+            M = B * H * H
+            tab = ResampleTables.get(cur_h, H, True, None, self.device)
+            ops.resample_fwd(cur, cur_ld, catb.data_ptr() + 64 * catb.element_size(), 128, B, cur_h, H, 64, tab)
+            mid, nxt = ops.empty(M, 64), ops.empty(M, 64)
+            self._conv_bn(units[u + "conv.double_conv.0"], (catb, 128, 0), B, H, mid, 64, 0, True, training, tape)
+            self._conv_bn(units[u + "conv.double_conv.3"], (mid, 64, 0), B, H, nxt, 64, 0, True, training, tape)
+            low = ops.empty(B, H, H, dtype=torch.float32)
+            ops.head_fwd(nxt, 64, P[head_name + ".weight"], P[head_name + ".bias"], low, M)
+            full = ops.empty(B, 1, S, S, dtype=torch.float32)
+            ops.resample1_fwd(low, full, B, H, S, ResampleTables.get(H, S, False, float(scale), self.device))
+            outs[head_name] = full
+            if tape is not None:
+                tape["dec"][u] = dict(inp=cur, inp_ld=cur_ld, inp_h=cur_h, catb=catb, mid=mid, out=nxt, H=H,
+                                      head=head_name, scale=scale)
+            cur, cur_ld, cur_h = nxt, 64, H
+        return outs["head"], outs["side1"], outs["side2"]
+
+    # ----------------------------------------------------------------------------------------- backward
+
+    def backward(self, g_out, g_out1, g_out2, on_bucket=None):
+        """Gradients of (out, out1, out2) [B,1,S,S] fp32 -> accumulates into model.flat.grad; frees the tape.
+        `on_bucket(lo, hi)` is called as soon as the flat gradient range [lo, hi) is final (data-parallel overlap)."""
+        tape = self.tape
+        if tape is None:
+            raise RuntimeError("backward() without a saved forward")
+        if not tape["training"]:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not implemented")
+        self.tape = None
+        B, S = tape["B"], tape["S"]
+        nblocks = len(self.cfg.blocks)
+        buckets = self.model.flat.buckets if on_bucket is not None else []
+        d_feats = self._decoder_bwd(tape, {"head": g_out, "side1": g_out1, "side2": g_out2}, B, S)
+        for lo, hi, ready in buckets:
+            if ready == nblocks:
+                on_bucket(lo, hi)
+        # trunk: walk the blocks backwards; stage-end blocks receive the RFB's gradient of that feature map
+        dz = None
+        stage = len(d_feats) - 1
+        for i in range(nblocks - 1, -1, -1):
+            spec = self.cfg.blocks[i]
+            if spec.stage_end:
+                g = d_feats[stage]
+                stage -= 1
+                if dz is None:
+                    dz = g
+                else:
+                    self.ops.add(dz, g, dz)
+            dz = self._block_bwd(i, spec, tape["blocks"][i], dz, B)
+            tape["blocks"][i] = None
+            for lo, hi, ready in buckets:
+                if ready == i:
+                    on_bucket(lo, hi)
+
+    def _block_bwd(self, i, spec, tp, dz, B):
+        ops, fz, sh = self.ops, self._frozen, self._shadow
+        G = self.model.flat.grad_views
+        p = f"encoder.blocks.{i}.block."
+        a = f"encoder.blocks.{i}.prompt_learn."
+        C, C2, nh = spec.dim, spec.dim_out, spec.num_heads
+        hd = C2 // nh
+        H, W, Ho, Wo = tp["H"], tp["W"], tp["Ho"], tp["Wo"]
+        R, Ro = B * H * W, B * Ho * Wo
+        # z = y + fc2(gelu(fc1(LN2(y))))
+        dh = ops.empty(Ro, 4 * C2)
+        ops.gemm(dz, fz[p + "mlp.layers.1.wt"], dh, aux=tp["hid"], flags=DGELU)
+        dn2 = ops.empty(Ro, C2)
+        ops.gemm(dh, fz[p + "mlp.layers.0.wt"], dn2)
+        del dh
+        dy = ops.empty(Ro, C2)
+        ops.ln_bwd(dn2, tp["y"], fz[p + "norm2.g"], tp["mean2"], tp["rstd2"], dz, dy, Ro, C2)
+        # y = shortcut + proj(attn)
+        do = dn2                                        # reuse
+        ops.gemm(dy, fz[p + "attn.proj.wt"], do)
+        dqkv = ops.empty(R, 3 * C2)
+        ops.attn_bwd(tp["qkv"], fz[p + "attn.qkv.b"], tp["o"], tp["lse"], do, dqkv, B, H, W, nh, hd, spec.window,
+                     spec.q_pool)
+        dn1 = ops.empty(R, C)
+        ops.gemm(dqkv, fz[p + "attn.qkv.wt"], dn1)
+        del dqkv
+        dres = dy
+        if C != C2:
+            dpr = ops.empty(R, C2)
+            ops.maxpool_bwd(tp["pr"], dy, dpr, B, H, W, C2)
+            ops.gemm(dpr, fz[p + "proj.wt"], dn1, resid=dn1, flags=RESID)
+            dres = None
+        dxa = ops.empty(R, C)
+        ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C)
+        # adapter backward: xa = x + gelu(h2), h2 = u W2^T + b2, u = gelu(h1), h1 = x W1^T + b1
+        dh2 = dn1                                       # reuse [R, C]
+        ops.dgelu_mul(dxa, tp["h2"], dh2)
+        ops.wgrad(dh2, tp["u"], G[a + "2.weight"], ldg=32)              # [C, 32]
+        ops.colsum(dh2, G[a + "2.bias"])
+        dh1 = ops.empty(R, 32)
+        ops.gemm(dh2, sh[a + "2.wt"], dh1, aux=tp["h1"], flags=DGELU)   # (dh2 W2) * gelu'(h1)
+        ops.wgrad(dh1, tp["x"], G[a + "0.weight"], ldg=C)               # [32, C]
+        ops.colsum(dh1, G[a + "0.bias"])
+        dx = ops.empty(R, C)
+        ops.gemm(dh1, sh[a + "0.wt"], dx, resid=dxa, flags=RESID)
+        return dx
+
+    def _conv_bn_bwd(self, cs: _ConvSpec, tape, dy, ld_dy, dy_off, y, ld_y, y_off, dst, accumulate):
+        """Backward of one conv+BN unit.  dy / y: (tensor, pitch, channel offset) of the output gradient and, when
+        the unit ends in a ReLU, of its saved output.  dst = (tensor, ld, offset) receiving d(input)."""
+        ops, sh = self.ops, self._shadow
+        P, G = self.model.flat.views, self.model.flat.grad_views
+        tp = tape["convs"][cs.name]
+        B, H = tp["B"], tp["H"]
+        M = B * H * H
+        taps = cs.kh * cs.kw
+        ws = self._bn_workspace(cs.bn, 64)
+        draw = ops.empty(M, 64)
+        dyv = dy.view(-1)[dy_off:] if dy_off else dy
+        yv = None
+        if y is not None:
+            yv = y.view(-1)[y_off:] if y_off else y
+        ops.bn_bwd(dyv, ld_dy, yv, ld_y, tp["raw"], 64, tp["mean"], tp["rstd"], P[cs.bn + ".weight"], ws["sums"],
+                   G[cs.bn + ".weight"], G[cs.bn + ".bias"], ws["c1"], ws["c2"], draw, 64, M, 64)
+        col = tp["col"]
+        colv = col.view(-1)[tp["coff"]:] if tp["coff"] else col
+        ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin, lda=64, ldb=tp["ldcol"],
+                  ldg=taps * cs.cin, q_inner=cs.cin, q_taps=taps)
+        if dst is None:
+            return
+        dt, ld_d, d_off = dst
+        dv = dt.view(-1)[d_off:] if d_off else dt
+        if taps == 1:
+            A, lda = draw, 64
+        else:
+            A = ops.empty(M, taps * 64)
+            ph, pw = cs.dil * (cs.kh - 1) // 2, cs.dil * (cs.kw - 1) // 2
+            ops.im2col(draw, 64, A, B, H, H, 64, cs.kh, cs.kw, cs.dil, cs.dil, ph, pw)
+            lda = taps * 64
+        ops.gemm(A, sh[cs.name + ".wd"], dv, M=M, N=cs.cin, K=taps * 64, lda=lda, ldw=taps * 64, ldc=ld_d,
+                 resid=dv if accumulate else None, ld_res=ld_d, flags=RESID if accumulate else 0)
+
+    def _decoder_bwd(self, tape, g_heads, B, S):
+        ops = self.ops
+        units = {cs.name: cs for cs in self.model.conv_units}
+        P, G = self.model.flat.views, self.model.flat.grad_views
+        dec = tape["dec"]
+        # gradient w.r.t. each RFB output (the left half of the concat buffers) and rfb4's output
+        d_rfb: List[Optional[torch.Tensor]] = [None, None, None, None]
+        d_cur = None                                    # gradient of the current decoder feature map [M,64]
+        for stage in (2, 1, 0):                          # up3, up2, up1
+            u = f"up{stage + 1}."
+            tp = dec[u]
+            H, M = tp["H"], B * tp["H"] * tp["H"]
+            k = 2 - stage
+            # head on this level
+            tab = ResampleTables.get(H, S, False, float(tp["scale"]), self.device)
+            dlow = ops.empty(B, H, H, dtype=torch.float32)
+            ops.resample1_bwd(g_heads[tp["head"]].contiguous().float(), dlow, B, H, S, tab)
+            dfeat = ops.empty(M, 64) if d_cur is None else d_cur
+            ops.head_bwd(tp["out"], 64, P[tp["head"] + ".weight"], dlow, dfeat, 64, d_cur is not None,
+                         G[tp["head"] + ".weight"], G[tp["head"] + ".bias"], M)
+            # double conv backwards
+            dmid = ops.empty(M, 64)
+            self._conv_bn_bwd(units[u + "conv.double_conv.3"], tape, dfeat, 64, 0, tp["out"], 64, 0, (dmid, 64, 0),
+                              False)
+            dcat = ops.empty(M, 128)
+            self._conv_bn_bwd(units[u + "conv.double_conv.0"], tape, dmid, 64, 0, tp["mid"], 64, 0, (dcat, 128, 0),
+                              False)
+            d_rfb[k] = dcat                             # left half [:, :64] is d(rfb_k output), pitch 128
+            # right half -> transpose of the bilinear x2 upsample
+            h_in = tp["inp_h"]
+            dprev = ops.empty(B * h_in * h_in, 64)
+            ops.resample_bwd(dcat.data_ptr() + 64 * dcat.element_size(), 128, dprev, 64, B, h_in, H, 64,
+                             ResampleTables.get(h_in, H, True, None, self.device))
+            d_cur = dprev
+        d_feats = []
+        for k in range(4):
+            r = f"rfb{k + 1}."
+            tp = dec[r]
+            H, Cin = tp["H"], tp["Cin"]
+            M = B * H * H
+            if k < 3:
+                dy, ld_dy = d_rfb[k], 128
+            else:
+                dy, ld_dy = d_cur, 64
+            # out = relu(bn(conv_cat(cat)) + bn(conv_res(f))): g = dy * (out > 0) feeds both BN backwards
+            g = ops.empty(M, 64)
+            ops.relu_bwd(dy, ld_dy, tp["dst"], tp["ld_dst"], g, 64, M, 64)
+            df = ops.empty(M, Cin)
+            dcatb = ops.empty(M, 256)
+            self._conv_bn_bwd(units[r + "conv_cat.conv"], tape, g, 64, 0, None, 0, 0, (dcatb, 256, 0), False)
+            self._conv_bn_bwd(units[r + "conv_res.conv"], tape, g, 64, 0, None, 0, 0, (df, Cin, 0), False)
+            self._conv_bn_bwd(units[r + "branch0.0.conv"], tape, dcatb, 256, 0, None, 0, 0, (df, Cin, 0), True)
+            for bi in (1, 2, 3):
+                d2, d1, d0 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
+                self._conv_bn_bwd(units[r + f"branch{bi}.3.conv"], tape, dcatb, 256, 64 * bi, None, 0, 0, (d2, 64, 0),
+                                  False)
+                self._conv_bn_bwd(units[r + f"branch{bi}.2.conv"], tape, d2, 64, 0, None, 0, 0, (d1, 64, 0), False)
+                self._conv_bn_bwd(units[r + f"branch{bi}.1.conv"], tape, d1, 64, 0, None, 0, 0, (d0, 64, 0), False)
+                self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, (df, Cin, 0), True)
+            d_feats.append(df)
+        return d_feats

@@ -1,0 +1,175 @@
+"""Fused AdamW over the flat parameter buffer and the fused train step.
+
+Reference: torch.optim.AdamW(lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.999), eps=1e-8) over
+`model.parameters()` where frozen / unused parameters have `grad is None` and are skipped
+(/root/reference/train.py:48-52,74,83), CosineAnnealingLR stepped once per epoch (train.py:54,87).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .model import SAM2UNet
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.Optimizer-compatible (param_groups, LR schedulers, zero_grad) AdamW whose `step()` is ONE
+    kernel over the model's flat fp32 master buffer (28 B/parameter of HBM traffic)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, *, model: SAM2UNet,
+                 grad_scale: float = 1.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.model = model
+        self.grad_scale = grad_scale
+        self._t = 0
+        self._m = self._v = self._hyper = self._staged = None
+
+    def _ensure_state(self):
+        flat = self.model.flat
+        if flat is None:
+            raise RuntimeError("FusedAdamW.step() before the first forward: the flat parameter buffer does not exist")
+        if self._m is None or self._m.numel() != flat.n_active or self._m.device != flat.master.device:
+            dev = flat.master.device
+            self._m = torch.zeros(flat.n_active, dtype=torch.float32, device=dev)
+            self._v = torch.zeros(flat.n_active, dtype=torch.float32, device=dev)
+            self._hyper = torch.tensor([0.0, 1.0, 1.0, 1.0], dtype=torch.float32, device=dev)
+            self._staged = None
+        return flat
+
+    def set_hyper(self):
+        """Stage lr / gradient scale on the device when they changed (stream-ordered fills, no host buffer to race
+        with; the bias-correction products beta^t advance on the device inside s2u_adamw)."""
+        self._ensure_state()
+        lr = float(self.param_groups[0]["lr"])
+        if self._staged != (lr, self.grad_scale):
+            self._hyper[0:1].fill_(lr)
+            self._hyper[1:2].fill_(self.grad_scale)
+            self._staged = (lr, self.grad_scale)
+
+    def launch(self):
+        """Enqueue the update kernel (capturable); hyper-parameters must have been staged by set_hyper()."""
+        flat = self._ensure_state()
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        st = torch.cuda.current_stream(flat.master.device).cuda_stream
+        _lib.call("s2u_adamw", flat.master.data_ptr(), flat.grad.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                  flat.n_active, self._hyper.data_ptr(), b1, b2, g["eps"], g["weight_decay"], st)
+        flat.bump()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        flat = self._ensure_state()
+        active = [p for n, p in flat.params.items() if flat.offsets[n] < flat.n_active]
+        if all(p.grad is None for p in active):
+            return loss
+        for n, p in flat.params.items():                # gradients delivered by something else than our backward
+            if flat.offsets[n] < flat.n_active and p.grad is not None and \
+                    p.grad.data_ptr() != flat.grad_views[n].data_ptr():
+                flat.grad_views[n].copy_(p.grad)
+        self.set_hyper()
+        self.launch()
+        self._t += 1
+        return loss
+
+
+def cosine_lr(epoch: int, t_max: int, base_lr: float = 1e-3, eta_min: float = 1e-7) -> float:
+    """Closed form of CosineAnnealingLR(T_max, eta_min) after `epoch` scheduler steps (train.py:54,87)."""
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * epoch / t_max)) / 2
+
+
+class TrainStep:
+    """The whole step of train.py:66-86 — forward, three structure_loss terms, backward, (all-reduce,) AdamW —
+    as one launch sequence without autograd, optionally captured in a CUDA graph.
+
+        step = TrainStep(model, lr=1e-3, weight_decay=5e-4)
+        loss = step(x, mask)          # device tensor [3]; `.sum().item()` only when you want to look at it
+    """
+
+    def __init__(self, model: SAM2UNet, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.999), eps=1e-8,
+                 use_graph: bool = True, process_group=None):
+        self.model = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.optim = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=lr, betas=betas, eps=eps,
+                                weight_decay=weight_decay, model=model, grad_scale=1.0 / self.world)
+        self.use_graph = use_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._static = None
+        self._warm = 0
+
+    # the raw launch sequence (capturable: no host sync, no allocation outside torch's caching allocator)
+    def _run(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        model = self.model
+        eng = model._engine(x.device)
+        flat = model.flat
+        dev = x.device
+        B, S = x.shape[0], x.shape[-1]
+        out, out1, out2 = eng.forward(x, True, save=True)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        weit = torch.empty(B, S, S, dtype=torch.float32, device=dev)
+        sums = torch.empty(3 * B * 2 + 3, dtype=torch.float64, device=dev)
+        loss = torch.empty(3, dtype=torch.float32, device=dev)
+        _lib.call("s2u_structure_loss_fwd", out.data_ptr(), out1.data_ptr(), out2.data_ptr(), mask.data_ptr(),
+                  weit.data_ptr(), sums.data_ptr(), loss.data_ptr(), B, S, S, 3, st)
+        g = [torch.empty_like(out) for _ in range(3)]
+        _lib.call("s2u_structure_loss_bwd", out.data_ptr(), out1.data_ptr(), out2.data_ptr(), mask.data_ptr(),
+                  weit.data_ptr(), sums.data_ptr(), 0, g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), B, S, S, 3,
+                  st)
+        flat.grad.zero_()
+        works = []
+
+        def on_bucket(lo, hi):
+            if self.world > 1:
+                works.append(dist.all_reduce(flat.grad[lo:hi], group=self.pg, async_op=True))
+
+        eng.backward(g[0], g[1], g[2], on_bucket=on_bucket)
+        for w in works:
+            w.wait()
+        self.optim.launch()
+        return loss
+
+    def __call__(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        model = self.model
+        if not model.training:
+            model.train()
+        if x.device.type != "cuda":
+            raise _lib.KernelError("TrainStep expects CUDA tensors (copy the batch to the GPU first)")
+        x = x.contiguous().float()
+        mask = mask.contiguous().float()
+        self.optim.set_hyper()
+        if not self.use_graph:
+            loss = self._run(x, mask)
+        else:
+            key = (tuple(x.shape), x.device)
+            if self._static is None or self._static[0] != key:
+                self._static = (key, torch.empty_like(x), torch.empty_like(mask), None)
+                self._graph = None
+                self._warm = 0
+            _, sx, sm, sl = self._static
+            sx.copy_(x, non_blocking=True)
+            sm.copy_(mask, non_blocking=True)
+            if self._graph is None and self._warm < 2:
+                loss = self._run(sx, sm)                # eager warm-up: allocator pools, smem attributes, tensor maps
+                self._warm += 1
+            elif self._graph is None:
+                torch.cuda.synchronize(x.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    sl = self._run(sx, sm)
+                self._graph = graph
+                self._static = (key, sx, sm, sl)
+                graph.replay()
+                loss = sl
+            else:
+                self._graph.replay()
+                self.model.flat.bump()
+                loss = sl
+        self.optim._t += 1
+        for p in self.model.flat.params.values():       # this path bypasses autograd: keep .grad unset
+            p.grad = None
+        return loss

@@ -1,0 +1,395 @@
+"""Op-level parity of every CUDA kernel (through the C ABI) against a plain PyTorch fp32 expression of the same
+op on identical inputs.  fp32 mode: <= 1e-3 of the output scale (observed ~1e-6); bf16 mode: inputs are rounded
+to bf16 first and the tolerance scales with the bf16 output rounding (2^-8)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+def _ops(dtype, cuda, backend=0):
+    from sam2_unet_b200.engine import Ops
+    return Ops(DT[dtype], cuda, backend)
+
+
+def _close(got, ref, tol, what=""):
+    got, ref = got.float(), ref.float()
+    scale = ref.abs().max().clamp_min(1e-6)
+    err = (got - ref).abs().max() / scale
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    assert err.item() <= tol, f"{what}: max-normalised error {err.item():.3e} > {tol}"
+
+
+def _tol(dtype, fp32=1e-4, bf16=2e-2):
+    return fp32 if dtype == "fp32" else bf16
+
+
+def _rand(shape, dtype, cuda, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(cuda).to(DT[dtype])
+
+
+# --------------------------------------------------------------------------------------------------- GEMM
+
+GEMM_SHAPES = [(300, 96, 32), (1000, 432, 144), (484, 2304, 576), (777, 32, 144), (128, 64, 64), (130, 72, 40),
+               (5808, 576, 2304), (64, 256, 1152)]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+@pytest.mark.parametrize("flags", [0, 1, 4, 5, 2])
+def test_gemm_simt(cuda, dtype, shape, flags):
+    M, N, K = shape
+    ops = _ops(dtype, cuda, backend=1)
+    A, W = _rand((M, K), dtype, cuda, 1), _rand((N, K), dtype, cuda, 2, K ** -0.5)
+    bias = _rand((N,), "fp32", cuda, 3)
+    aux, resid = _rand((M, N), dtype, cuda, 4), _rand((M, N), dtype, cuda, 5)
+    C, pre = ops.empty(M, N), ops.empty(M, N)
+    ops.gemm(A, W, C, bias=bias, pre_out=pre, aux=aux if flags & 2 else None, resid=resid if flags & 4 else None,
+             flags=flags)
+    ref_pre = A.float() @ W.float().t() + bias
+    ref = ref_pre
+    if flags & 1:
+        ref = F.gelu(ref)
+    if flags & 2:
+        a = aux.float().requires_grad_(True)
+        (dg,) = torch.autograd.grad(F.gelu(a).sum(), a)
+        ref = ref * dg
+    if flags & 4:
+        ref = ref + resid.float()
+    _close(pre, ref_pre, _tol(dtype), "pre_out")
+    _close(C, ref, _tol(dtype), "C")
+
+
+@pytest.mark.parametrize("shape", GEMM_SHAPES + [(92928, 144, 144), (1452, 4608, 1152), (256, 1152, 4608)])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
+def test_gemm_umma(cuda, shape, bn):
+    """tcgen05 + TMA GEMM vs fp32 matmul of the same bf16 operands, all tile widths, with the full epilogue."""
+    M, N, K = shape
+    if K % 8 or N % 8:
+        pytest.skip("TMA path needs 16-byte row pitches (the engine routes such shapes to the SIMT kernel)")
+    ops = _ops("bf16", cuda)
+    A, W = _rand((M, K), "bf16", cuda, 1), _rand((N, K), "bf16", cuda, 2, K ** -0.5)
+    bias = _rand((N,), "fp32", cuda, 3)
+    resid = _rand((M, N), "bf16", cuda, 5)
+    C, pre = ops.empty(M, N), ops.empty(M, N)
+    backend = 2 if bn == 0 else 16 + bn
+    ops.gemm(A, W, C, bias=bias, pre_out=pre, resid=resid, flags=1 | 4, backend=backend)
+    ref_pre = A.float() @ W.float().t() + bias
+    ref = F.gelu(ref_pre) + resid.float()
+    _close(pre, ref_pre, 1e-2, "pre_out")
+    _close(C, ref, 1e-2, "C")
+    # plain (no epilogue) and DGELU variants
+    C2 = ops.empty(M, N)
+    ops.gemm(A, W, C2, backend=backend)
+    _close(C2, A.float() @ W.float().t(), 1e-2, "plain")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_wgrad_colsum(cuda, dtype):
+    ops = _ops(dtype, cuda)
+    M, P, Q = 3000, 64, 192
+    A, B = _rand((M, P), dtype, cuda, 1), _rand((M, Q), dtype, cuda, 2)
+    G = torch.zeros(P, Q, device=cuda)
+    ops.wgrad(A, B, G)
+    ops.wgrad(A, B, G)                                    # accumulates
+    _close(G, 2 * A.float().t() @ B.float(), 1e-4, "wgrad")
+    # conv-weight mapping: q = tap*Cin + ci -> [P][Cin][taps]
+    taps, cin = 3, 64
+    G2 = torch.zeros(P, cin, taps, device=cuda)
+    ops.wgrad(A, B, G2, ldg=Q, q_inner=cin, q_taps=taps)
+    ref = (A.float().t() @ B.float()).view(P, taps, cin).permute(0, 2, 1)
+    _close(G2, ref, 1e-4, "wgrad conv layout")
+    s = torch.zeros(Q, device=cuda)
+    ops.colsum(B, s)
+    _close(s, B.float().sum(0), 1e-4, "colsum")
+
+
+# ------------------------------------------------------------------------------------------ norm / pointwise
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("C", [32, 144, 1152])
+def test_layernorm(cuda, dtype, C):
+    ops = _ops(dtype, cuda)
+    R = 1001
+    x = _rand((R, C), dtype, cuda, 1) * 2 + 0.5
+    g, b = _rand((C,), "fp32", cuda, 2) * 0.1 + 1, _rand((C,), "fp32", cuda, 3) * 0.1
+    y, mean, rstd = ops.empty(R, C), ops.empty(R, dtype=torch.float32), ops.empty(R, dtype=torch.float32)
+    ops.ln_fwd(x, g, b, y, mean, rstd, R, C)
+    xr = x.float().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), g, b, 1e-6)
+    _close(y, ref, _tol(dtype), "ln fwd")
+    dy, dres = _rand((R, C), dtype, cuda, 4), _rand((R, C), dtype, cuda, 5)
+    dx = ops.empty(R, C)
+    ops.ln_bwd(dy, x, g, mean, rstd, dres, dx, R, C)
+    (gx,) = torch.autograd.grad(ref, xr, dy.float())
+    _close(dx, gx + dres.float(), _tol(dtype), "ln bwd")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_maxpool_dgelu(cuda, dtype):
+    ops = _ops(dtype, cuda)
+    B, H, W, C = 2, 10, 12, 64
+    x = _rand((B, H, W, C), dtype, cuda, 1)
+    out = ops.empty(B, H // 2, W // 2, C)
+    ops.maxpool_fwd(x, out, B, H, W, C)
+    xr = x.float().requires_grad_(True)
+    ref = F.max_pool2d(xr.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    _close(out, ref, 1e-6, "maxpool fwd")
+    dout = _rand(tuple(out.shape), dtype, cuda, 2)
+    dx = ops.empty(B, H, W, C)
+    ops.maxpool_bwd(x, dout, dx, B, H, W, C)
+    (gx,) = torch.autograd.grad(ref, xr, dout.float())
+    _close(dx, gx, 1e-6, "maxpool bwd")
+    pre, dy = _rand((64, 40), dtype, cuda, 3), _rand((64, 40), dtype, cuda, 4)
+    o = ops.empty(64, 40)
+    ops.dgelu_mul(dy, pre, o)
+    pr = pre.float().requires_grad_(True)
+    (gp,) = torch.autograd.grad(F.gelu(pr), pr, dy.float())
+    _close(o, gp, _tol(dtype, 1e-5), "dgelu")
+
+
+# ---------------------------------------------------------------------------------------------- attention
+
+def _attn_reference(qkv, bias, B, H, W, nh, hd, window, pool):
+    """hieradet.py:56-81 + utils.py:16-55 on an already-projected qkv map; padded tokens carry the bias."""
+    C = nh * hd
+    ws_h, ws_w = (window, window) if window > 0 else (H, W)
+    ph, pw = (ws_h - H % ws_h) % ws_h, (ws_w - W % ws_w) % ws_w
+    full = bias.view(1, 1, 1, -1).expand(B, H + ph, W + pw, 3 * C).clone()
+    full[:, :H, :W] = qkv
+    Hp, Wp = H + ph, W + pw
+    t = full.view(B, Hp // ws_h, ws_h, Wp // ws_w, ws_w, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws_h, ws_w, 3 * C)
+    q, k, v = t[..., :C], t[..., C:2 * C], t[..., 2 * C:]
+    qh, qw = ws_h, ws_w
+    if pool:
+        q = F.max_pool2d(q.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        qh, qw = ws_h // 2, ws_w // 2
+    nw = t.shape[0]
+    q = q.reshape(nw, qh * qw, nh, hd).transpose(1, 2)
+    k = k.reshape(nw, ws_h * ws_w, nh, hd).transpose(1, 2)
+    v = v.reshape(nw, ws_h * ws_w, nh, hd).transpose(1, 2)
+    o = ((q @ k.transpose(-1, -2)) / math.sqrt(hd)).softmax(-1) @ v
+    o = o.transpose(1, 2).reshape(nw, qh, qw, C)
+    o = o.view(B, Hp // ws_h, Wp // ws_w, qh, qw, C).permute(0, 1, 3, 2, 4, 5).reshape(B, (Hp // ws_h) * qh,
+                                                                                     (Wp // ws_w) * qw, C)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    return o[:, :Ho, :Wo]
+
+
+ATTN_CASES = [  # B, H, W, nh, hd, window, pool
+    (2, 16, 16, 2, 72, 8, False), (1, 22, 22, 2, 72, 16, False), (2, 11, 11, 4, 72, 8, False),
+    (1, 22, 22, 1, 96, 0, False), (2, 16, 16, 2, 72, 8, True), (1, 22, 22, 2, 72, 16, True),
+    (1, 12, 12, 2, 32, 4, True), (2, 10, 10, 1, 32, 6, True), (1, 5, 5, 2, 56, 3, False), (1, 22, 22, 2, 96, 14, False),
+]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_window_attention(cuda, dtype, case):
+    B, H, W, nh, hd, window, pool = case
+    ops = _ops(dtype, cuda)
+    C = nh * hd
+    qkv = _rand((B, H, W, 3 * C), dtype, cuda, 1)
+    bias = _rand((3 * C,), "fp32", cuda, 2)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out, lse = ops.empty(B, Ho, Wo, C), ops.empty(B, Ho, Wo, nh, dtype=torch.float32)
+    ops.attn_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, pool)
+    qr = qkv.float().requires_grad_(True)
+    b_eff = bias.to(DT[dtype]).float()
+    ref = _attn_reference(qr, b_eff, B, H, W, nh, hd, window, pool)
+    _close(out, ref, _tol(dtype, 1e-4, 2e-2), "attention fwd")
+    dout = _rand((B, Ho, Wo, C), dtype, cuda, 3)
+    dqkv = torch.full((B, H, W, 3 * C), float("nan"), device=cuda, dtype=DT[dtype])
+    ops.attn_bwd(qkv, bias, out, lse, dout, dqkv, B, H, W, nh, hd, window, pool)
+    (gq,) = torch.autograd.grad(ref, qr, dout.float())
+    _close(dqkv, gq, _tol(dtype, 2e-4, 3e-2), "attention bwd")
+
+
+# ----------------------------------------------------------------------------------------- stem and convs
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_patch_embed(cuda, dtype):
+    ops = _ops(dtype, cuda)
+    B, S, E = 2, 96, 144
+    x = _rand((B, 3, S, S), "fp32", cuda, 1)
+    w, b = _rand((E, 3, 7, 7), "fp32", cuda, 2, 0.1), _rand((E,), "fp32", cuda, 3)
+    pos = _rand((S // 4, S // 4, E), "fp32", cuda, 4)
+    out = ops.empty(B, S // 4, S // 4, E)
+    ops.patch_embed(x, w, b, pos, out, B, S, E)
+    ref = F.conv2d(x, w, b, stride=4, padding=3).permute(0, 2, 3, 1) + pos
+    _close(out, ref, _tol(dtype, 1e-5, 1e-2), "patch embed")
+
+
+CONVS = [(64, 1, 3, 1), (64, 3, 1, 1), (64, 1, 7, 1), (64, 7, 1, 1), (64, 3, 3, 3), (64, 3, 3, 7), (256, 3, 3, 1),
+         (128, 3, 3, 1)]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("conv", CONVS)
+def test_conv_im2col_gemm(cuda, dtype, conv):
+    """conv forward, input gradient and weight gradient through im2col + GEMM vs F.conv2d autograd."""
+    cin, kh, kw, dil = conv
+    ops = _ops(dtype, cuda)
+    B, H = 2, 11
+    M, taps = B * H * H, kh * kw
+    x = _rand((B, H, H, cin), dtype, cuda, 1)
+    w = _rand((64, cin, kh, kw), "fp32", cuda, 2, (cin * taps) ** -0.5)
+    wf, wd = ops.empty(64, taps * cin), ops.empty(cin, taps * 64)
+    ops.conv_weight_pack(w, wf, wd, 64, cin, kh, kw)
+    ph, pw = dil * (kh - 1) // 2, dil * (kw - 1) // 2
+    col = ops.empty(M, taps * cin)
+    ops.im2col(x, cin, col, B, H, H, cin, kh, kw, dil, dil, ph, pw)
+    y = ops.empty(M, 64)
+    ops.gemm(col, wf, y)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.to(DT[dtype]).float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, padding=(ph, pw), dilation=dil)
+    _close(y.view(B, H, H, 64), ref.permute(0, 2, 3, 1), _tol(dtype), "conv fwd")
+    dy = _rand((M, 64), dtype, cuda, 3)
+    gx, gw = torch.autograd.grad(ref, (xr, wr), dy.float().view(B, H, H, 64).permute(0, 3, 1, 2))
+    cold = ops.empty(M, taps * 64)
+    ops.im2col(dy, 64, cold, B, H, H, 64, kh, kw, dil, dil, ph, pw)
+    dx = ops.empty(M, cin)
+    ops.gemm(cold, wd, dx)
+    _close(dx.view(B, H, H, cin), gx.permute(0, 2, 3, 1), _tol(dtype), "conv dgrad")
+    G = torch.zeros(64, cin, kh, kw, device=cuda)
+    ops.wgrad(dy, col, G, ldg=taps * cin, q_inner=cin, q_taps=taps)
+    _close(G, gw, _tol(dtype, 1e-4, 1e-2), "conv wgrad")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("relu", [False, True])
+def test_batchnorm(cuda, dtype, relu):
+    ops = _ops(dtype, cuda)
+    M, C = 2 * 11 * 11, 64
+    x = _rand((M, C), dtype, cuda, 1) * 1.5 + 0.3
+    g, b = _rand((C,), "fp32", cuda, 2) * 0.1 + 1, _rand((C,), "fp32", cuda, 3) * 0.1
+    rm, rv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    nbt = torch.zeros((), dtype=torch.long, device=cuda)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=cuda)
+    scale, shift, mean, rstd = (torch.empty(C, device=cuda) for _ in range(4))
+    ops.bn_stats(x, C, sums, M, C)
+    ops.bn_finalize(sums, g, b, rm, rv, nbt, scale, shift, mean, rstd, M, C, True)
+    y = ops.empty(M, C)
+    ops.bn_apply(x, C, scale, shift, None, 0, y, C, M, C, relu)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    ref = F.batch_norm(xr.t().reshape(1, C, M), rm2, rv2, gr, br, True, 0.1, 1e-5).reshape(C, M).t()
+    if relu:
+        ref = F.relu(ref)
+    _close(y, ref, _tol(dtype, 1e-4, 2e-2), "bn fwd")
+    _close(rm, rm2, 1e-4, "running mean")
+    _close(rv, rv2, 1e-4, "running var")
+    assert int(nbt) == 1 and float(sums.abs().max()) == 0.0
+    dy = _rand((M, C), dtype, cuda, 4)
+    dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    c1, c2 = torch.empty(C, device=cuda), torch.empty(C, device=cuda)
+    dx = ops.empty(M, C)
+    ops.bn_bwd(dy, C, y if relu else None, C, x, C, mean, rstd, g, sums, dg, db, c1, c2, dx, C, M, C)
+    # the kernel masks with ITS OWN saved output; use the same mask in the reference to stay flip-free
+    yr = F.batch_norm(xr.t().reshape(1, C, M), None, None, gr, br, True, 0.1, 1e-5).reshape(C, M).t()
+    up = dy.float() * ((y.float() > 0).float() if relu else 1.0)
+    gx, gg, gb = torch.autograd.grad(yr, (xr, gr, br), up)
+    _close(dx, gx, _tol(dtype, 2e-4, 3e-2), "bn dx")
+    _close(dg, gg, _tol(dtype, 2e-4, 2e-2), "bn dgamma")
+    _close(db, gb, _tol(dtype, 2e-4, 2e-2), "bn dbeta")
+    # eval mode uses the running statistics
+    ops.bn_finalize(sums, g, b, rm, rv, nbt, scale, shift, None, None, M, C, False)
+    ops.bn_apply(x, C, scale, shift, None, 0, y, C, M, C, False)
+    ref = F.batch_norm(x.float().t().reshape(1, C, M), rm, rv, g, b, False, 0.1, 1e-5).reshape(C, M).t()
+    _close(y, ref, _tol(dtype, 1e-4, 2e-2), "bn eval")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_resample_and_heads(cuda, dtype):
+    from sam2_unet_b200.resample_tables import ResampleTables
+    ops = _ops(dtype, cuda)
+    B, h, C = 2, 11, 64
+    x = _rand((B, h, h, C), dtype, cuda, 1)
+    tab = ResampleTables.get(h, 2 * h, True, None, cuda)
+    out = ops.empty(B, 2 * h, 2 * h, 128)
+    out.zero_()
+    ops.resample_fwd(x, C, out.data_ptr() + 64 * out.element_size(), 128, B, h, 2 * h, C, tab)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)
+    _close(out[..., 64:], ref.permute(0, 2, 3, 1), _tol(dtype, 1e-5, 1e-2), "upsample fwd")
+    assert float(out[..., :64].abs().max()) == 0.0
+    dout = _rand((B, 2 * h, 2 * h, 128), dtype, cuda, 2)
+    dx = ops.empty(B, h, h, C)
+    ops.resample_bwd(dout.data_ptr() + 64 * dout.element_size(), 128, dx, C, B, h, 2 * h, C, tab)
+    (gx,) = torch.autograd.grad(ref, xr, dout[..., 64:].float().permute(0, 3, 1, 2))
+    _close(dx, gx.permute(0, 2, 3, 1), _tol(dtype, 1e-5, 1e-2), "upsample bwd")
+    # heads: 1x1 conv + x4/x8/x16 (align_corners=False)
+    for scale in (4, 8, 16):
+        M = B * h * h
+        feat = _rand((M, 64), dtype, cuda, 3)
+        w, b = _rand((1, 64, 1, 1), "fp32", cuda, 4, 0.2), _rand((1,), "fp32", cuda, 5)
+        low = torch.empty(B, h, h, device=cuda)
+        ops.head_fwd(feat, 64, w, b, low, M)
+        S = h * scale
+        t2 = ResampleTables.get(h, S, False, float(scale), cuda)
+        full = torch.empty(B, 1, S, S, device=cuda)
+        ops.resample1_fwd(low, full, B, h, S, t2)
+        fr = feat.float().view(B, h, h, 64).permute(0, 3, 1, 2).requires_grad_(True)
+        wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ref = F.interpolate(F.conv2d(fr, wr, br), scale_factor=scale, mode="bilinear")
+        _close(full, ref, 1e-5, f"head x{scale} fwd")
+        g = _rand((B, 1, S, S), "fp32", cuda, 6)
+        dlow = torch.empty(B, h, h, device=cuda)
+        ops.resample1_bwd(g, dlow, B, h, S, t2)
+        dfeat = ops.empty(M, 64)
+        dw, db = torch.zeros(64, device=cuda), torch.zeros(1, device=cuda)
+        ops.head_bwd(feat, 64, w, dlow, dfeat, 64, False, dw, db, M)
+        gf, gw, gb = torch.autograd.grad(ref, (fr, wr, br), g)
+        _close(dfeat.view(B, h, h, 64), gf.permute(0, 2, 3, 1), _tol(dtype, 1e-4, 1e-2), "head dfeat")
+        _close(dw, gw.view(-1), _tol(dtype, 1e-4, 1e-2), "head dw")
+        _close(db, gb, 1e-4, "head db")
+
+
+# ------------------------------------------------------------------------------------------ loss / optimizer
+
+@pytest.mark.parametrize("shape", [(2, 96), (3, 352), (1, 64)])
+def test_structure_loss(cuda, shape):
+    from oracle import port
+    from sam2_unet_b200.loss import structure_loss, structure_loss3
+    B, S = shape
+    _, mask = port.synthetic_batch(B, S, seed=3)
+    preds = [(torch.randn(B, 1, S, S, generator=torch.Generator().manual_seed(i)) * 2).to(cuda).requires_grad_(True)
+             for i in range(3)]
+    mask = mask.to(cuda)
+    ref = [port.structure_loss(p, mask) for p in preds]
+    gref = torch.autograd.grad(sum(r * (i + 1) for i, r in enumerate(ref)), preds)
+    l3 = structure_loss3(*preds, mask)
+    got = torch.autograd.grad((l3 * torch.tensor([1.0, 2.0, 3.0], device=cuda)).sum(), preds)
+    for i in range(3):
+        assert abs(l3[i].item() - ref[i].item()) <= 1e-5 * max(1.0, abs(ref[i].item()))
+        _close(got[i], gref[i], 1e-4, f"loss grad {i}")
+    one = structure_loss(preds[0], mask)
+    assert abs(one.item() - ref[0].item()) <= 1e-5 * max(1.0, abs(ref[0].item()))
+    (g1,) = torch.autograd.grad(one, preds[0])
+    _close(g1, gref[0], 1e-4, "single-head grad")
+
+
+def test_adamw_kernel(cuda):
+    from sam2_unet_b200 import _lib
+    n = 10007
+    p = torch.randn(n, device=cuda)
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, weight_decay=5e-4)
+    m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    hyper = torch.tensor([1e-3, 1.0, 1.0, 1.0], device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(5):
+        g = torch.randn(n, device=cuda, generator=torch.Generator(device="cuda").manual_seed(step))
+        ref_p.grad = g.clone()
+        opt.step()
+        _lib.call("s2u_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, hyper.data_ptr(), 0.9, 0.999,
+                  1e-8, 5e-4, st)
+    _close(p, ref_p.detach(), 1e-5, "adamw")
