@@ -58,11 +58,13 @@ int s2u_cast(const float* src, void* dst, int R, int C, int transpose, int dtype
 
 /* ---- windowed / global attention (hieradet.py:56-81,141-162; backbones/utils.py:16-55) ------------------ *
  * qkv [B,H,W,3*nh*hd]; window = 0 means global; pool = 1 applies the 2x2 q max-pool inside each window;
- * bias = the qkv bias (value of zero-padded tokens); out [B,Ho,Wo,nh*hd], lse [B,Ho,Wo,nh]. */
+ * bias = the qkv bias (value of zero-padded tokens); out [B,Ho,Wo,nh*hd], lse [B,Ho,Wo,nh];
+ * dws = fp32 workspace [B,Ho,Wo,nh] of the backward.  bf16 runs on tensor cores, fp32 on an exact FFMA kernel. */
 int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
                      int window, int pool, int dtype, void* stream);
 int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
-                     void* dqkv, int B, int H, int W, int nh, int hd, int window, int pool, int dtype, void* stream);
+                     void* dqkv, float* dws, int B, int H, int W, int nh, int hd, int window, int pool, int dtype,
+                     void* stream);
 
 /* ---- stem and convolutions -------------------------------------------------------------------------------- *
  * 7x7/s4/p3 conv 3->E + bias + position-embedding table (backbones/utils.py:80-88, hieradet.py:268-283). */

@@ -27,7 +27,7 @@ SIGNATURES = {
     "s2u_maxpool2_bwd": [P, P, P, I, I, I, I, I, P],
     "s2u_cast": [P, P, I, I, I, I, P],
     "s2u_win_attn_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P],
-    "s2u_win_attn_bwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
+    "s2u_win_attn_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     "s2u_patch_embed": [P, P, P, P, P, I, I, I, I, P],
     "s2u_im2col": [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "s2u_conv_weight_pack": [P, P, P, I, I, I, I, I, P],
@@ -82,13 +82,39 @@ def _describe(rc: int) -> str:
     return f"CUDA error {rc}"
 
 
+_profile = None      # when profiling: list of (name, start_event, end_event, args)
+
+
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point and raise on a non-zero status."""
     global _launches
-    rc = getattr(load(), name)(*args)
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        _profile.append((name, e0, e1, args))
+    else:
+        rc = getattr(load(), name)(*args)
     _launches += 1
     if rc != 0:
         raise KernelError(f"{name} failed: {_describe(rc)}")
+
+
+def profile_begin() -> None:
+    """Bracket every following C-ABI call with CUDA events on the current stream (eager runs only)."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """-> list of (name, milliseconds, args) for the calls made since profile_begin()."""
+    global _profile
+    import torch
+    torch.cuda.synchronize()
+    rec, _profile = _profile, None
+    return [(n, e0.elapsed_time(e1), a) for n, e0, e1, a in rec]
 
 
 def launch_count() -> int:

@@ -414,10 +414,21 @@ static int make_geom(AttnGeom& g, int B, int H, int W, int nh, int hd, int windo
   return 0;
 }
 
+// tensor-core variants (attention_mma.cu), bf16 only; return S2U_EUNSUPPORTED for shapes they do not cover
+int s2u_attn_mma_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
+                     int window, int pool, cudaStream_t st);
+int s2u_attn_mma_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
+                     void* dqkv, float* Dws, int B, int H, int W, int nh, int hd, int window, int pool,
+                     cudaStream_t st);
+
 extern "C" {
 
 int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
                      int window, int pool, int dtype, void* stream) {
+  if (dtype == S2U_BF16) {
+    const int rc2 = s2u_attn_mma_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, pool, (cudaStream_t)stream);
+    if (rc2 != S2U_EUNSUPPORTED) return rc2;
+  }
   AttnGeom g;
   int rc = make_geom(g, B, H, W, nh, hd, window, pool);
   if (rc) return rc;
@@ -431,9 +442,16 @@ int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, 
   return 0;
 }
 
-// dqkv must be fully overwritten: every real token receives dq (part 1) and dk, dv (part 2).
+// dqkv is fully overwritten: every real token receives dq (part 1) and dk, dv (part 2).
+// dws: fp32 workspace of B*Ho*Wo*nh entries (rowsum(dO o O) of the tensor-core path).
 int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
-                     void* dqkv, int B, int H, int W, int nh, int hd, int window, int pool, int dtype, void* stream) {
+                     void* dqkv, float* dws, int B, int H, int W, int nh, int hd, int window, int pool, int dtype,
+                     void* stream) {
+  if (dtype == S2U_BF16 && dws) {
+    const int rc2 = s2u_attn_mma_bwd(qkv, bias, out, lse, dout, dqkv, dws, B, H, W, nh, hd, window, pool,
+                                     (cudaStream_t)stream);
+    if (rc2 != S2U_EUNSUPPORTED) return rc2;
+  }
   AttnGeom g;
   int rc = make_geom(g, B, H, W, nh, hd, window, pool);
   if (rc) return rc;

@@ -1,0 +1,553 @@
+// Tensor-core (bf16 mma.sync m16n8k16, fp32 accumulate) flash-style windowed / global attention, forward and
+// backward, same semantics and layouts as attention.cu (window partition, zero-pad-as-bias tokens, q max-pool,
+// un-partition + crop all folded into the addressing; /root/reference/sam2/modeling/backbones/hieradet.py:56-81).
+//
+// One CTA = 4 warps = 64 query rows (forward, dQ) or 64 key rows (dK/dV) of one (window, head); the other
+// operand streams through shared memory in 64-row tiles.  Head dims are zero-padded to HDP in {32,64,80,96}
+// inside shared memory only (Hiera-L's 72 -> 80), so global memory keeps the reference layout.
+// S/P never leave registers: the QK^T accumulator fragments are re-packed as the A operand of the PV product.
+#include "common.cuh"
+
+namespace amma {
+
+struct Geom {
+  int B, H, W, nh, hd, wh, ww, nwy, nwx, pool, Ho, Wo, qh, qw;
+  float scale;
+};
+
+constexpr int BM = 64, BN = 64, NT = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 8 bf16 (16 B) of the qkv row at token (y, x), columns col..col+7; padded tokens hold the (bf16-rounded) bias
+__device__ __forceinline__ uint4 tok8(const bf16* __restrict__ qkv, const float* __restrict__ bias, const Geom& g,
+                                      int b, int y, int x, int col) {
+  if (y < g.H && x < g.W)
+    return *reinterpret_cast<const uint4*>(qkv + (((long long)b * g.H + y) * g.W + x) * (3LL * g.nh * g.hd) + col);
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(bias[col + 2 * i], bias[col + 2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+
+// rows = window positions r0..r0+63 (row-major in the window), `which` = 1 (k) or 2 (v); zero beyond the window / hd
+template <int HDP>
+__device__ __forceinline__ void load_kv(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, int b, int wy,
+                                        int wx, int head, int which, int r0) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  const int C = g.nh * g.hd;
+  for (int e = threadIdx.x; e < BN * CH; e += NT) {
+    const int r = e / CH, c = e - r * CH;
+    const int idx = r0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (idx < g.wh * g.ww && c * 8 < g.hd) {
+      const int ty = idx / g.ww, tx = idx - ty * g.ww;
+      v = tok8(qkv, bias, g, b, wy * g.wh + ty, wx * g.ww + tx, which * C + head * g.hd + c * 8);
+    }
+    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+  }
+}
+
+// rows = query positions r0..r0+63 of the window (pooled grid when g.pool)
+template <int HDP>
+__device__ __forceinline__ void load_q(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, int b, int wy,
+                                       int wx, int head, int r0) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  for (int e = threadIdx.x; e < BM * CH; e += NT) {
+    const int r = e / CH, c = e - r * CH;
+    const int idx = r0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (idx < g.qh * g.qw && c * 8 < g.hd) {
+      const int py = idx / g.qw, px = idx - py * g.qw;
+      const int col = head * g.hd + c * 8;
+      if (!g.pool) {
+        v = tok8(qkv, bias, g, b, wy * g.wh + py, wx * g.ww + px, col);
+      } else {
+        const int y = wy * g.wh + 2 * py, x = wx * g.ww + 2 * px;
+        v = max8(max8(tok8(qkv, bias, g, b, y, x, col), tok8(qkv, bias, g, b, y, x + 1, col)),
+                 max8(tok8(qkv, bias, g, b, y + 1, x, col), tok8(qkv, bias, g, b, y + 1, x + 1, col)));
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+  }
+}
+
+// rows = the output tokens of query positions r0..r0+63 (zero for cropped queries); src is [B,Ho,Wo,nh*hd]
+template <int HDP>
+__device__ __forceinline__ void load_o(bf16* dst, const bf16* src, const Geom& g, int b, int wy, int wx, int head,
+                                       int r0) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  for (int e = threadIdx.x; e < BM * CH; e += NT) {
+    const int r = e / CH, c = e - r * CH;
+    const int idx = r0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (idx < g.qh * g.qw && c * 8 < g.hd) {
+      const int py = idx / g.qw, px = idx - py * g.qw;
+      const int oy = wy * g.qh + py, ox = wx * g.qw + px;
+      if (oy < g.Ho && ox < g.Wo)
+        v = *reinterpret_cast<const uint4*>(src + (((long long)b * g.Ho + oy) * g.Wo + ox) * (g.nh * g.hd) +
+                                            head * g.hd + c * 8);
+    }
+    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+  }
+}
+
+__device__ __forceinline__ long long out_token(const Geom& g, int b, int wy, int wx, int idx) {
+  if (idx >= g.qh * g.qw) return -1;
+  const int py = idx / g.qw, px = idx - py * g.qw;
+  const int oy = wy * g.qh + py, ox = wx * g.qw + px;
+  if (oy >= g.Ho || ox >= g.Wo) return -1;
+  return ((long long)b * g.Ho + oy) * g.Wo + ox;
+}
+
+// acc[j][0..3] (j = 8-column tile) = A(16 x HDP, this warp's rows of `As`) . Bt(64 x HDP, rows of `Bs`)^T
+template <int HDP>
+__device__ __forceinline__ void mm_ab_t(float (*acc)[4], const bf16* As, const bf16* Bs, int warp, int lane) {
+  constexpr int LD = HDP + 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[j][t] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HDP / 16; ++kk) {
+    uint32_t a[4];
+    ldsm4(smem_u32(As + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm4(smem_u32(Bs + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * LD + kk * 16 + ((lane >> 3) & 1) * 8), b0, b1,
+            b2, b3);
+      mma16816(acc[2 * jp], a, b0, b1);
+      mma16816(acc[2 * jp + 1], a, b2, b3);
+    }
+  }
+}
+
+// out[j][0..3] (j over HDP/8 column tiles) += P(16 x 64, fragments re-packed from `p`) . Bs(64 x HDP)
+template <int HDP>
+__device__ __forceinline__ void mm_p_b(float (*out)[4], const float (*p)[4], const bf16* Bs, int lane) {
+  constexpr int LD = HDP + 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+    a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+    a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < HDP / 16; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm4t(smem_u32(Bs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + dp * 16 + (lane >> 4) * 8), b0, b1,
+             b2, b3);
+      mma16816(out[2 * dp], a, b0, b1);
+      mma16816(out[2 * dp + 1], a, b2, b3);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- forward
+template <int HDP>
+__global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                bf16* __restrict__ out, float* __restrict__ lse, Geom g) {
+  constexpr int LD = HDP + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + BM * LD;
+  bf16* Vs = Ks + BN * LD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.z, win = blockIdx.y;
+  const int b = win / (g.nwy * g.nwx), wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+  const int q0 = blockIdx.x * BM;
+  const int nk = g.wh * g.ww;
+  const float sl2 = g.scale * 1.4426950408889634f;
+
+  load_q<HDP>(Qs, qkv, bias, g, b, wy, wx, head, q0);
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[j][t] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows lane/4 and lane/4 + 8 of this warp's 16
+  for (int k0 = 0; k0 < nk; k0 += BN) {
+    __syncthreads();
+    load_kv<HDP>(Ks, qkv, bias, g, b, wy, wx, head, 1, k0);
+    load_kv<HDP>(Vs, qkv, bias, g, b, wy, wx, head, 2, k0);
+    __syncthreads();
+    float s[8][4];
+    mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
+    float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = k0 + j * 8 + 2 * (lane & 3);
+      if (c >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (c + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      t0 = fmaxf(t0, fmaxf(s[j][0], s[j][1]));
+      t1 = fmaxf(t1, fmaxf(s[j][2], s[j][3]));
+    }
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+    const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+    const float a0 = ex2((m0 - n0) * sl2), a1 = ex2((m1 - n1) * sl2);
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = ex2((s[j][0] - n0) * sl2);
+      s[j][1] = ex2((s[j][1] - n0) * sl2);
+      s[j][2] = ex2((s[j][2] - n1) * sl2);
+      s[j][3] = ex2((s[j][3] - n1) * sl2);
+      p0 += s[j][0] + s[j][1];
+      p1 += s[j][2] + s[j][3];
+    }
+    p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+    p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+    l0 = l0 * a0 + p0;
+    l1 = l1 * a1 + p1;
+    m0 = n0;
+    m1 = n1;
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j) {
+      o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1;
+    }
+    mm_p_b<HDP>(o, s, Vs, lane);
+  }
+  const int C = g.nh * g.hd;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int row = warp * 16 + (lane >> 2) + half * 8;
+    const long long tok = out_token(g, b, wy, wx, q0 + row);
+    if (tok < 0) continue;
+    const float inv = 1.f / (half ? l1 : l0);
+    bf16* orow = out + tok * C + head * g.hd;
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j) {
+      const int d = j * 8 + 2 * (lane & 3);
+      if (d < g.hd)
+        *reinterpret_cast<__nv_bfloat162*>(orow + d) =
+            __floats2bfloat162_rn(o[j][half * 2] * inv, o[j][half * 2 + 1] * inv);
+    }
+    if ((lane & 3) == 0) lse[tok * g.nh + head] = (half ? m1 : m0) * g.scale + __logf(half ? l1 : l0);
+  }
+}
+
+// D[token, head] = sum_d dO * O  (one warp per token)
+__global__ void bwd_prep_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ D,
+                                long long ntok, int nh, int hd) {
+  const long long tok = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= ntok) return;
+  const int C = nh * hd;
+  for (int h = 0; h < nh; ++h) {
+    float s = 0.f;
+    for (int d = lane * 2; d < hd; d += 64) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + tok * C + h * hd + d));
+      const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + tok * C + h * hd + d));
+      s += a.x * c.x + a.y * c.y;
+    }
+    s = warp_sum(s);
+    if (lane == 0) D[tok * nh + h] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- backward: dQ
+template <int HDP>
+__global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                   const float* __restrict__ lse, const float* __restrict__ Dv,
+                                                   const bf16* __restrict__ dout, bf16* __restrict__ dqkv, Geom g) {
+  constexpr int LD = HDP + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* dOs = Qs + BM * LD;
+  bf16* Ks = dOs + BM * LD;
+  bf16* Vs = Ks + BN * LD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.z, win = blockIdx.y;
+  const int b = win / (g.nwy * g.nwx), wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+  const int q0 = blockIdx.x * BM;
+  const int nk = g.wh * g.ww;
+  const float sl2 = g.scale * 1.4426950408889634f;
+
+  load_q<HDP>(Qs, qkv, bias, g, b, wy, wx, head, q0);
+  load_o<HDP>(dOs, dout, g, b, wy, wx, head, q0);
+  const int r0 = warp * 16 + (lane >> 2);
+  const long long tok0 = out_token(g, b, wy, wx, q0 + r0), tok1 = out_token(g, b, wy, wx, q0 + r0 + 8);
+  const float L0 = tok0 >= 0 ? lse[tok0 * g.nh + head] * 1.4426950408889634f : INFINITY;
+  const float L1 = tok1 >= 0 ? lse[tok1 * g.nh + head] * 1.4426950408889634f : INFINITY;
+  const float D0 = tok0 >= 0 ? Dv[tok0 * g.nh + head] : 0.f;
+  const float D1 = tok1 >= 0 ? Dv[tok1 * g.nh + head] : 0.f;
+  float dq[HDP / 8][4];
+#pragma unroll
+  for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dq[j][t] = 0.f;
+  for (int k0 = 0; k0 < nk; k0 += BN) {
+    __syncthreads();
+    load_kv<HDP>(Ks, qkv, bias, g, b, wy, wx, head, 1, k0);
+    load_kv<HDP>(Vs, qkv, bias, g, b, wy, wx, head, 2, k0);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
+    mm_ab_t<HDP>(dp, dOs, Vs, warp, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = k0 + j * 8 + 2 * (lane & 3);
+      const bool v0 = c < nk, v1 = c + 1 < nk;
+      const float p00 = v0 ? ex2(s[j][0] * sl2 - L0) : 0.f, p01 = v1 ? ex2(s[j][1] * sl2 - L0) : 0.f;
+      const float p10 = v0 ? ex2(s[j][2] * sl2 - L1) : 0.f, p11 = v1 ? ex2(s[j][3] * sl2 - L1) : 0.f;
+      s[j][0] = p00 * (dp[j][0] - D0) * g.scale;
+      s[j][1] = p01 * (dp[j][1] - D0) * g.scale;
+      s[j][2] = p10 * (dp[j][2] - D1) * g.scale;
+      s[j][3] = p11 * (dp[j][3] - D1) * g.scale;
+    }
+    mm_p_b<HDP>(dq, s, Ks, lane);
+  }
+  // scatter into the q third of dqkv (argmax routing through the q max-pool)
+  const int C = g.nh * g.hd;
+  const long long row3 = 3LL * C;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int idx = q0 + r0 + half * 8;
+    if (idx >= g.qh * g.qw) continue;
+    const int py = idx / g.qw, px = idx - py * g.qw;
+    if (!g.pool) {
+      const int y = wy * g.wh + py, x = wx * g.ww + px;
+      if (y >= g.H || x >= g.W) continue;
+      bf16* dst = dqkv + (((long long)b * g.H + y) * g.W + x) * row3 + head * g.hd;
+#pragma unroll
+      for (int j = 0; j < HDP / 8; ++j) {
+        const int d = j * 8 + 2 * (lane & 3);
+        if (d < g.hd)
+          *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(dq[j][half * 2], dq[j][half * 2 + 1]);
+      }
+    } else {
+      const int y = wy * g.wh + 2 * py, x = wx * g.ww + 2 * px;
+#pragma unroll
+      for (int j = 0; j < HDP / 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int d = j * 8 + 2 * (lane & 3) + e;
+          if (d >= g.hd) continue;
+          const int col = head * g.hd + d;
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int yy = y + (k >> 1), xx = x + (k & 1);
+            v[k] = (yy < g.H && xx < g.W) ? __bfloat162float(qkv[(((long long)b * g.H + yy) * g.W + xx) * row3 + col])
+                                          : __bfloat162float(__float2bfloat16(bias[col]));
+          }
+          int best = 0;
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (v[k] > v[best]) best = k;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int yy = y + (k >> 1), xx = x + (k & 1);
+            if (yy < g.H && xx < g.W)
+              dqkv[(((long long)b * g.H + yy) * g.W + xx) * row3 + col] =
+                  __float2bfloat16(k == best ? dq[j][half * 2 + e] : 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------- backward: dK, dV
+template <int HDP>
+__global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                    const float* __restrict__ lse, const float* __restrict__ Dv,
+                                                    const bf16* __restrict__ dout, bf16* __restrict__ dqkv, Geom g) {
+  constexpr int LD = HDP + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* Ks = reinterpret_cast<bf16*>(smraw);
+  bf16* Vs = Ks + BN * LD;
+  bf16* Qs = Vs + BN * LD;
+  bf16* dOs = Qs + BM * LD;
+  float* Ls = reinterpret_cast<float*>(dOs + BM * LD);     // [64] lse * log2(e)  (+inf for cropped queries)
+  float* Ds = Ls + BM;                                     // [64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.z, win = blockIdx.y;
+  const int b = win / (g.nwy * g.nwx), wy = (win / g.nwx) % g.nwy, wx = win % g.nwx;
+  const int k0 = blockIdx.x * BN;
+  const int nk = g.wh * g.ww, nq = g.qh * g.qw;
+  const float sl2 = g.scale * 1.4426950408889634f;
+
+  load_kv<HDP>(Ks, qkv, bias, g, b, wy, wx, head, 1, k0);
+  load_kv<HDP>(Vs, qkv, bias, g, b, wy, wx, head, 2, k0);
+  float dk[HDP / 8][4], dv[HDP / 8][4];
+#pragma unroll
+  for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { dk[j][t] = 0.f; dv[j][t] = 0.f; }
+  const int kr0 = k0 + warp * 16 + (lane >> 2);            // this thread's key rows: kr0, kr0 + 8
+  for (int q0 = 0; q0 < nq; q0 += BM) {
+    __syncthreads();
+    load_q<HDP>(Qs, qkv, bias, g, b, wy, wx, head, q0);
+    load_o<HDP>(dOs, dout, g, b, wy, wx, head, q0);
+    if (threadIdx.x < BM) {
+      const long long tok = out_token(g, b, wy, wx, q0 + threadIdx.x);
+      Ls[threadIdx.x] = tok >= 0 ? lse[tok * g.nh + head] * 1.4426950408889634f : INFINITY;
+      Ds[threadIdx.x] = tok >= 0 ? Dv[tok * g.nh + head] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dpt[8][4];                              // [16 keys x 64 queries]
+    mm_ab_t<HDP>(st, Ks, Qs, warp, lane);
+    mm_ab_t<HDP>(dpt, Vs, dOs, warp, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                            // st <- P^T
+      const int c = j * 8 + 2 * (lane & 3);                  // query column inside the tile
+      const float La = Ls[c], Lb = Ls[c + 1];
+      const bool ka = kr0 < nk, kb = kr0 + 8 < nk;
+      st[j][0] = ka ? ex2(st[j][0] * sl2 - La) : 0.f;
+      st[j][1] = ka ? ex2(st[j][1] * sl2 - Lb) : 0.f;
+      st[j][2] = kb ? ex2(st[j][2] * sl2 - La) : 0.f;
+      st[j][3] = kb ? ex2(st[j][3] * sl2 - Lb) : 0.f;
+    }
+    mm_p_b<HDP>(dv, st, dOs, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                            // st <- dS^T = P^T o (dP^T - D) * scale
+      const int c = j * 8 + 2 * (lane & 3);
+      const float Da = Ds[c], Db = Ds[c + 1];
+      st[j][0] *= (dpt[j][0] - Da) * g.scale;
+      st[j][1] *= (dpt[j][1] - Db) * g.scale;
+      st[j][2] *= (dpt[j][2] - Da) * g.scale;
+      st[j][3] *= (dpt[j][3] - Db) * g.scale;
+    }
+    mm_p_b<HDP>(dk, st, Qs, lane);
+  }
+  const int C = g.nh * g.hd;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int idx = kr0 + half * 8;
+    if (idx >= nk) continue;
+    const int ty = idx / g.ww, tx = idx - ty * g.ww;
+    const int y = wy * g.wh + ty, x = wx * g.ww + tx;
+    if (y >= g.H || x >= g.W) continue;                      // padded key: frozen bias, no gradient
+    bf16* dst = dqkv + (((long long)b * g.H + y) * g.W + x) * (3LL * C) + head * g.hd;
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j) {
+      const int d = j * 8 + 2 * (lane & 3);
+      if (d < g.hd) {
+        *reinterpret_cast<__nv_bfloat162*>(dst + C + d) = __floats2bfloat162_rn(dk[j][half * 2], dk[j][half * 2 + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(dst + 2 * C + d) = __floats2bfloat162_rn(dv[j][half * 2], dv[j][half * 2 + 1]);
+      }
+    }
+  }
+}
+
+static int make_geom(Geom& g, int B, int H, int W, int nh, int hd, int window, int pool) {
+  if (B <= 0 || H <= 0 || W <= 0 || nh <= 0 || hd <= 0) return S2U_EINVAL;
+  if ((hd & 7) || hd > 96) return S2U_EUNSUPPORTED;
+  g.B = B; g.H = H; g.W = W; g.nh = nh; g.hd = hd;
+  g.wh = window > 0 ? window : H;
+  g.ww = window > 0 ? window : W;
+  g.nwy = (H + g.wh - 1) / g.wh;
+  g.nwx = (W + g.ww - 1) / g.ww;
+  g.pool = pool ? 1 : 0;
+  if (pool && ((g.wh & 1) || (g.ww & 1) || (H & 1) || (W & 1))) return S2U_EUNSUPPORTED;
+  g.Ho = pool ? H / 2 : H;
+  g.Wo = pool ? W / 2 : W;
+  g.qh = pool ? g.wh / 2 : g.wh;
+  g.qw = pool ? g.ww / 2 : g.ww;
+  g.scale = 1.0f / sqrtf((float)hd);
+  return 0;
+}
+
+template <int HDP>
+static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse, const Geom& g, cudaStream_t st) {
+  dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
+  const size_t smem = (size_t)(BM + 2 * BN) * (HDP + 8) * sizeof(bf16);
+  S2U_ALLOW_SMEM(fwd_kernel<HDP>);
+  fwd_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, out, lse, g);
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int HDP>
+static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const float* lse, const bf16* dout,
+                      bf16* dqkv, float* Dws, const Geom& g, cudaStream_t st) {
+  const long long ntok = (long long)g.B * g.Ho * g.Wo;
+  bwd_prep_kernel<<<ceil_div(ntok * 32, 256), 256, 0, st>>>(out, dout, Dws, ntok, g.nh, g.hd);
+  S2U_LAUNCH_CHECK();
+  {
+    dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
+    const size_t smem = (size_t)(2 * BM + 2 * BN) * (HDP + 8) * sizeof(bf16);
+    S2U_ALLOW_SMEM(bwd_dq_kernel<HDP>);
+    bwd_dq_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, lse, Dws, dout, dqkv, g);
+    S2U_LAUNCH_CHECK();
+  }
+  {
+    dim3 grid(ceil_div(g.wh * g.ww, BN), g.B * g.nwy * g.nwx, g.nh);
+    const size_t smem = (size_t)(2 * BM + 2 * BN) * (HDP + 8) * sizeof(bf16) + 2 * BM * sizeof(float);
+    S2U_ALLOW_SMEM(bwd_dkv_kernel<HDP>);
+    bwd_dkv_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, lse, Dws, dout, dqkv, g);
+    S2U_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace amma
+
+// entry points used by attention.cu's dispatch (bf16 only)
+int s2u_attn_mma_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
+                     int window, int pool, cudaStream_t st) {
+  amma::Geom g;
+  int rc = amma::make_geom(g, B, H, W, nh, hd, window, pool);
+  if (rc) return rc;
+  const bf16* q = (const bf16*)qkv;
+  bf16* o = (bf16*)out;
+  if (hd <= 32) return amma::launch_fwd<32>(q, bias, o, lse, g, st);
+  if (hd <= 64) return amma::launch_fwd<64>(q, bias, o, lse, g, st);
+  if (hd <= 80) return amma::launch_fwd<80>(q, bias, o, lse, g, st);
+  return amma::launch_fwd<96>(q, bias, o, lse, g, st);
+}
+
+int s2u_attn_mma_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
+                     void* dqkv, float* Dws, int B, int H, int W, int nh, int hd, int window, int pool,
+                     cudaStream_t st) {
+  amma::Geom g;
+  int rc = amma::make_geom(g, B, H, W, nh, hd, window, pool);
+  if (rc) return rc;
+  const bf16 *q = (const bf16*)qkv, *o = (const bf16*)out, *d = (const bf16*)dout;
+  bf16* dq = (bf16*)dqkv;
+  if (hd <= 32) return amma::launch_bwd<32>(q, bias, o, lse, d, dq, Dws, g, st);
+  if (hd <= 64) return amma::launch_bwd<64>(q, bias, o, lse, d, dq, Dws, g, st);
+  if (hd <= 80) return amma::launch_bwd<80>(q, bias, o, lse, d, dq, Dws, g, st);
+  return amma::launch_bwd<96>(q, bias, o, lse, d, dq, Dws, g, st);
+}

@@ -104,8 +104,10 @@ class Ops:
                   hd, window, 1 if pool else 0, self.dt, self.stream)
 
     def attn_bwd(self, qkv, bias, out, lse, dout, dqkv, B, H, W, nh, hd, window, pool):
+        dws = torch.empty_like(lse)
         _lib.call("s2u_win_attn_bwd", qkv.data_ptr(), bias.data_ptr(), out.data_ptr(), lse.data_ptr(),
-                  dout.data_ptr(), dqkv.data_ptr(), B, H, W, nh, hd, window, 1 if pool else 0, self.dt, self.stream)
+                  dout.data_ptr(), dqkv.data_ptr(), dws.data_ptr(), B, H, W, nh, hd, window, 1 if pool else 0,
+                  self.dt, self.stream)
 
     def patch_embed(self, x, w, bias, pos, out, B, S, E):
         _lib.call("s2u_patch_embed", x.data_ptr(), w.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(), B,

@@ -137,17 +137,20 @@ class TrainStep:
         model = self.model
         if not model.training:
             model.train()
-        if x.device.type != "cuda":
-            raise _lib.KernelError("TrainStep expects CUDA tensors (copy the batch to the GPU first)")
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.KernelError("TrainStep needs the model on a CUDA device (no CPU fallback)")
         x = x.contiguous().float()
         mask = mask.contiguous().float()
+        model._engine(dev)
         self.optim.set_hyper()
         if not self.use_graph:
-            loss = self._run(x, mask)
+            # host batches (pinned or pageable) are copied to the device here: this is the H2D leg of the step
+            loss = self._run(x.to(dev, non_blocking=True), mask.to(dev, non_blocking=True))
         else:
-            key = (tuple(x.shape), x.device)
+            key = (tuple(x.shape), dev)
             if self._static is None or self._static[0] != key:
-                self._static = (key, torch.empty_like(x), torch.empty_like(mask), None)
+                self._static = (key, torch.empty_like(x, device=dev), torch.empty_like(mask, device=dev), None)
                 self._graph = None
                 self._warm = 0
             _, sx, sm, sl = self._static
@@ -157,7 +160,7 @@ class TrainStep:
                 loss = self._run(sx, sm)                # eager warm-up: allocator pools, smem attributes, tensor maps
                 self._warm += 1
             elif self._graph is None:
-                torch.cuda.synchronize(x.device)
+                torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     sl = self._run(sx, sm)

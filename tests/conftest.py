@@ -18,4 +18,7 @@ def cuda():
 
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # the PyTorch side of every comparison must be genuine fp32 (cuDNN / cuBLAS default to TF32 for convs)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")

@@ -1,0 +1,279 @@
+"""CPU-side tests (`-m "not gpu"`): the oracle against the committed golden vectors (which the reference itself
+produced, oracle/make_golden.py), the host logic (trunk tables, state-dict layout, flat parameter buffer,
+gradient buckets, resampling tables), and that the C-ABI library loads and exports every declared symbol.
+No kernel is launched here."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------ oracle vs golden vectors
+
+def _sd(cfg):
+    from sam2_unet_b200 import SAM2UNet
+    from sam2_unet_b200.params import fill_deterministic_
+    m = SAM2UNet(model_cfg=cfg, dtype="fp32")
+    fill_deterministic_(m, 0)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def _proj(n, k=4):
+    g = torch.Generator().manual_seed(n % 1000003)
+    return torch.randn(k, n, generator=g, dtype=torch.float64) / n ** 0.5
+
+
+def test_pin_report_is_green():
+    rep = json.load(open(os.path.join(GOLD, "pin_report.json")))
+    for case in ("tiny_160_b2", "hiera_l_352"):
+        r = rep[case]
+        assert max(r["eval_logits_maxnorm"]) < 1e-4 and max(r["train_logits_maxnorm"]) < 1e-4
+        assert r["loss_rel"] < 1e-5 and r["grad_global_rel_l2"] < 5e-3
+
+
+def test_oracle_tiny_against_reference_vectors():
+    from oracle import port
+    sd = _sd("tiny_test.yaml")
+    x, mask = port.synthetic_batch(2, 160, seed=2)
+    gold_t, gold_e = np.load(os.path.join(GOLD, "tiny_train.npz")), np.load(os.path.join(GOLD, "tiny_eval.npz"))
+    with torch.no_grad():
+        ev = port.forward(sd, port.TRUNKS["test"], x, False)
+    for o, nm in zip(ev, ("out", "out1", "out2")):
+        assert np.abs(o.numpy() - gold_e[nm]).max() <= 1e-4 * np.abs(gold_e[nm]).max()
+    loss, outs, grads = port.loss_and_grads(sd, port.TRUNKS["test"], x, mask, True, port.BNState())
+    assert abs(loss.item() - float(gold_t["loss"])) <= 1e-5 * abs(float(gold_t["loss"]))
+    for o, nm in zip(outs, ("out", "out1", "out2")):
+        assert np.abs(o.numpy() - gold_t[nm]).max() <= 1e-4 * np.abs(gold_t[nm]).max()
+    num = den = 0.0
+    for k, g in grads.items():
+        if g is None:
+            assert "gnorm/" + k not in gold_t.files and k.startswith("up4.")
+            continue
+        v = g.double().reshape(-1)
+        ref_proj = gold_t["gproj/" + k]
+        num += float(((_proj(v.numel()) @ v).numpy() - ref_proj).__pow__(2).sum())
+        den += float((ref_proj ** 2).sum())
+        assert abs(v.norm().item() - float(gold_t["gnorm/" + k])) <= 2e-2 * float(gold_t["gnorm/" + k]) + 1e-9, k
+    assert (num / den) ** 0.5 <= 1e-3
+
+
+def test_oracle_config1_hiera_l_forward():
+    """BASELINE.json config 1 (Hiera-L 352^2, batch 1, fp32 forward) — the oracle reproduces the reference's output."""
+    from oracle import port
+    sd = _sd("sam2_hiera_l.yaml")
+    x, _ = port.synthetic_batch(1, 352, seed=0)
+    gold = np.load(os.path.join(GOLD, "hiera_l_352_fwd.npz"))
+    with torch.no_grad():
+        outs = port.forward(sd, port.TRUNKS["l"], x, False)
+    for o, nm in zip(outs, ("out", "out1", "out2")):
+        assert np.abs(o[0, 0, ::3, ::3].numpy() - gold[nm]).max() <= 1e-4 * np.abs(gold[nm]).max()
+
+
+def test_structure_loss_oracle_and_closed_form():
+    from oracle import port
+    gold = np.load(os.path.join(GOLD, "structure_loss.npz"))
+    for i, (B, S) in enumerate(((2, 96), (3, 352), (1, 64))):
+        _, mask = port.synthetic_batch(B, S, seed=3)
+        pred = (torch.randn(B, 1, S, S, generator=torch.Generator().manual_seed(i)) * 2).requires_grad_(True)
+        loss = port.structure_loss(pred, mask)
+        (g,) = torch.autograd.grad(loss, pred)
+        assert abs(loss.item() - float(gold[f"loss_{i}"])) <= 1e-6
+        assert np.abs(g[:, 0, ::7, ::5].numpy() - gold[f"grad_{i}"]).max() <= 1e-4 * np.abs(gold[f"grad_{i}"]).max()
+        cf_loss, cf_grad = port.structure_loss_closed_form(pred.detach().double(), mask.double())
+        assert abs(cf_loss.item() - loss.item()) <= 1e-6
+        assert (cf_grad.float() - g).abs().max() <= 1e-4 * g.abs().max()
+
+
+def test_oracle_against_live_reference_when_present():
+    from oracle import port, ref_shim
+    if not ref_shim.available():
+        pytest.skip("/root/reference is not present on this machine")
+    from sam2_unet_b200.params import fill_deterministic_
+    ref = ref_shim.build_reference("t")
+    fill_deterministic_(ref, 1)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    x, _ = port.synthetic_batch(1, 96, seed=9)
+    ref.eval()
+    with torch.no_grad():
+        a = ref(x)
+        b = port.forward(sd, port.TRUNKS["t"], x, False)
+    for u, v in zip(a, b):
+        assert (u - v).abs().max() <= 1e-4 * u.abs().max()
+
+
+def test_adamw_and_cosine_schedule_match_torch():
+    from oracle import port
+    from sam2_unet_b200 import cosine_lr
+    p = torch.randn(1000)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([{"params": [ref], "initial_lr": 1e-3}], lr=1e-3, weight_decay=5e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, 20, eta_min=1e-7)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for t in range(1, 6):
+        g = torch.randn(1000, generator=torch.Generator().manual_seed(t))
+        ref.grad = g.clone()
+        lr = opt.param_groups[0]["lr"]
+        assert abs(lr - cosine_lr(t - 1, 20)) < 1e-12 and abs(lr - port.cosine_lr(t - 1, 20)) < 1e-12
+        opt.step()
+        port.adamw_step(p, g, m, v, t, lr=lr)
+        sched.step()
+    assert (p - ref.detach()).abs().max() < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- host logic
+
+def test_trunk_tables_match_the_reference_variants():
+    from oracle import port
+    from sam2_unet_b200 import trunk_config
+    want = {"t": (12, [1, 3, 10], [5, 7, 9]), "s": (16, [1, 3, 14], [7, 10, 13]), "b+": (24, [2, 5, 21], [12, 16, 20]),
+            "l": (48, [2, 8, 44], [23, 33, 43])}
+    for name, (depth, pools, globs) in want.items():
+        cfg = trunk_config(name)
+        assert len(cfg.blocks) == depth
+        assert [b.index for b in cfg.blocks if b.q_pool] == pools
+        assert [b.index for b in cfg.blocks if b.window == 0] == globs
+        table = port.block_table(port.TRUNKS[name])
+        for b, t in zip(cfg.blocks, table):
+            assert (b.dim, b.dim_out, b.num_heads, b.window, b.q_pool, b.stage_end) == \
+                   (t["dim"], t["dim_out"], t["heads"], t["window"], t["pool"], t["end"])
+    lcfg = trunk_config("l")
+    assert lcfg.stage_dims == [144, 288, 576, 1152] and lcfg.blocks[44].window == 16 and lcfg.blocks[45].window == 8
+    assert all(b.dim_out // b.num_heads == 72 for b in lcfg.blocks)
+    with pytest.raises(ValueError):
+        trunk_config("nope.yaml")
+
+
+def test_state_dict_layout_and_requires_grad_pattern():
+    from sam2_unet_b200 import SAM2UNet
+    m = SAM2UNet(model_cfg="sam2_hiera_l.yaml")
+    sd = m.state_dict()
+    assert len(sd) == 1192                                           # SURVEY.md section 8b, measured on the reference
+    assert sum(p.numel() for p in m.parameters()) == 216529891
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 4380595
+    for key in ("encoder.pos_embed", "encoder.pos_embed_window", "encoder.patch_embed.proj.weight",
+                "encoder.blocks.2.block.proj.weight", "encoder.blocks.0.block.attn.qkv.bias",
+                "encoder.blocks.47.block.mlp.layers.1.weight", "encoder.blocks.5.prompt_learn.2.bias",
+                "rfb3.branch2.3.bn.running_var", "rfb1.conv_cat.conv.weight", "up4.conv.double_conv.4.num_batches_tracked",
+                "side2.bias", "head.weight"):
+        assert key in sd, key
+    assert sd["rfb2.branch3.3.conv.weight"].shape == (64, 64, 3, 3) and sd["up1.conv.double_conv.0.weight"].shape == (64, 128, 3, 3)
+    for n, p in m.named_parameters():
+        frozen = n.startswith("encoder.") and ".prompt_learn." not in n
+        assert p.requires_grad == (not frozen), n
+    s = SAM2UNet()                                                   # the fork's default trunk is Hiera-S
+    assert s.cfg.name == "sam2_hiera_s.yaml" and s.rfb1.conv_res.conv.weight.shape[1] == 96
+    with pytest.raises(Exception):
+        s(torch.randn(1, 3, 64, 64))                                  # CPU tensor: the product path has no fallback
+
+
+def test_state_dict_matches_live_reference_keys():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("/root/reference is not present on this machine")
+    from sam2_unet_b200 import SAM2UNet
+    ref = ref_shim.build_reference("s")
+    mine = SAM2UNet()
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys()) or set(rs) == set(ms)
+    for k in rs:
+        assert rs[k].shape == ms[k].shape, k
+    mine.load_state_dict(rs, strict=True)
+    ref.load_state_dict(mine.state_dict(), strict=True)
+    assert {n for n, p in ref.named_parameters() if p.requires_grad} == {n for n, p in mine.named_parameters() if p.requires_grad}
+
+
+def test_flat_parameters_alias_and_buckets():
+    from sam2_unet_b200 import SAM2UNet
+    from sam2_unet_b200.model import FlatParams
+    m = SAM2UNet(model_cfg="tiny_test.yaml")
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = FlatParams(m, torch.device("cpu"))
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    p = dict(m.named_parameters())["side1.weight"]
+    assert p.data_ptr() == flat.views["side1.weight"].data_ptr()
+    with torch.no_grad():
+        p.add_(1.0)
+    off = flat.offsets["side1.weight"]
+    assert torch.equal(flat.master[off:off + 64].view_as(p), p)
+    assert all(flat.offsets[n] >= flat.n_active for n in flat.offsets if n.startswith("up4."))
+    assert all(flat.offsets[n] < flat.n_active for n in flat.offsets if not n.startswith("up4."))
+    lo_prev = 0
+    for lo, hi, ready in flat.buckets:                               # contiguous cover of the active range
+        assert lo == lo_prev and hi > lo
+        lo_prev = hi
+    assert lo_prev == flat.n_active and flat.buckets[0][2] == len(m.cfg.blocks) and flat.buckets[-1][2] == 0
+    for n, o in flat.offsets.items():                                # an adapter's bucket is ready only after its block
+        if n.startswith("encoder.blocks."):
+            blk = int(n.split(".")[2])
+            ready = next(r for lo, hi, r in flat.buckets if lo <= o < hi)
+            assert ready <= blk
+
+
+def test_resample_tables_match_aten():
+    from sam2_unet_b200.resample_tables import axis_backward, axis_forward
+    for n_in, n_out, ac, sc in ((11, 22, True, None), (44, 88, True, None), (22, 352, False, 16.0), (88, 352, False, 4.0)):
+        f = axis_forward(n_in, n_out, ac, sc)
+        x = torch.randn(1, 1, n_in, n_in, requires_grad=True)
+        ref = F.interpolate(x, scale_factor=2 if ac else sc, mode="bilinear", align_corners=ac if ac else None)
+        i0, i1, w0, w1 = (torch.from_numpy(a) for a in f)
+        xv = x.detach()[0, 0]
+        rows = w0[:, None] * xv[i0.long()] + w1[:, None] * xv[i1.long()]
+        out = w0[None, :] * rows[:, i0.long()] + w1[None, :] * rows[:, i1.long()]
+        assert (out - ref[0, 0]).abs().max() < 1e-5
+        bi, bw, taps = axis_backward(n_in, n_out, f)
+        g = torch.randn_like(ref)
+        (gx,) = torch.autograd.grad(ref, x, g)
+        bi_t, bw_t = torch.from_numpy(bi).long(), torch.from_numpy(bw)
+        tmp = (bw_t[:, :, None] * g[0, 0][bi_t]).sum(1)
+        dx = (bw_t[None, :, :] * tmp[:, bi_t]).sum(2)
+        assert (dx - gx[0, 0]).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+
+def _header_decls():
+    src = open(os.path.join(ROOT, "include", "sam2unet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"int\s+(s2u_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+
+
+def test_library_exports_every_declared_symbol():
+    from sam2_unet_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from sam2_unet_b200 import build
+        build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    decls = _header_decls()
+    assert len(decls) >= 29
+    for name, _ in decls:
+        assert hasattr(lib, name), name
+    assert {n for n, _ in decls} == set(_lib.SIGNATURES)
+
+
+def test_ctypes_signatures_match_the_header():
+    from sam2_unet_b200 import _lib
+    kinds = {"P": ctypes.c_void_p, "I": ctypes.c_int, "L": ctypes.c_longlong, "F": ctypes.c_float}
+
+    def kind(arg):
+        return "P" if "*" in arg else "L" if "long long" in arg else "F" if "float" in arg else "I"
+
+    for name, args in _header_decls():
+        want = [kinds[kind(a.strip())] for a in args.split(",")]
+        assert want == _lib.SIGNATURES[name], name
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from sam2_unet_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsam2unet_b200.so")
+    with pytest.raises(_lib.KernelError):
+        _lib.call("s2u_add", 0, 0, 0, 8, 0, 0)
