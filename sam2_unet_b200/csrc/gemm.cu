@@ -386,6 +386,416 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised variant (the product path): one CTA per SM loops over output tiles;
+//   warp 0      TMA producer (one elected lane) — fills the STAGES-deep smem ring across tile boundaries
+//   warp 1      MMA issuer  (one elected lane) — tcgen05.mma into one of TWO TMEM accumulators (2 x BN columns)
+//   warps 2..5  epilogue — drain the other accumulator (tcgen05.ld), apply bias / GELU / GELU' / residual, and
+//               move data between registers and global memory through a per-warp swizzled smem staging tile so
+//               every global access is a full 128-byte row segment
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+// ------------------------------------------------------------------------------------------------------------
+
+// exact-erf GELU for the bf16 epilogue without the SFU: odd minimax polynomial of erf on |z| <= 3.3 (|err| < 7e-5,
+// two orders below bf16 resolution), clamped outside.  fp32 mode never runs this (SIMT kernel, erff).
+__device__ __forceinline__ float erf_poly(float z) {
+  z = fminf(fmaxf(z, -3.3f), 3.3f);
+  const float u = z * z;
+  float p = 2.0112330506e-08f;
+  p = fmaf(p, u, -1.1352825549e-06f);
+  p = fmaf(p, u, 2.7990254297e-05f);
+  p = fmaf(p, u, -3.9921021419e-04f);
+  p = fmaf(p, u, 3.6915675290e-03f);
+  p = fmaf(p, u, -2.3606465426e-02f);
+  p = fmaf(p, u, 1.0890402398e-01f);
+  p = fmaf(p, u, -3.7390216815e-01f);
+  p = fmaf(p, u, 1.1280026288e+00f);
+  return z * p;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, erf_poly(x * 0.70710678118654752f), h);
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  const float cdf = fmaf(0.5f, erf_poly(x * 0.70710678118654752f), 0.5f);
+  return fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf);
+}
+
+constexpr int WS_EPI_WARPS = 8;
+constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
+constexpr int EPI_TILE_BYTES = 32 * 64;        // per epilogue warp: 32 rows x 32 bf16, 16-byte chunks XOR-swizzled
+
+template <int BN, int STAGES>
+struct CfgWS {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + WS_EPI_WARPS * EPI_TILE_BYTES + 1024;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(BM >> 4) << 24);
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// staging tile: row r (0..31), 16-byte chunk c (0..3) at r*64 + ((c ^ ((r >> 1) & 3)) << 4): conflict-free both for
+// "thread = row" accesses and for "4 lanes = one 64-byte row" accesses
+__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int r, int c) {
+  return base + (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// global [32 rows x 32 cols] (row pitch ld) <-> staging tile; 4 lanes move one 64-byte row segment
+__device__ __forceinline__ void g2s_tile(uint32_t stg, const bf16* __restrict__ src, long long ld, int rows_ok,
+                                         int cols_ok, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), c = lane & 3;
+    if (r < rows_ok && c * 8 < cols_ok)
+      sts16(stg_addr(stg, r, c), *reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8));
+  }
+}
+__device__ __forceinline__ void s2g_tile(uint32_t stg, bf16* __restrict__ dst, long long ld, int rows_ok, int cols_ok,
+                                         int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), c = lane & 3;
+    if (r < rows_ok && c * 8 < cols_ok)
+      *reinterpret_cast<uint4*>(dst + (long long)r * ld + c * 8) = lds16(stg_addr(stg, r, c));
+  }
+}
+// this thread's row of the staging tile <-> 32 floats
+__device__ __forceinline__ void regs_to_stage(uint32_t stg, int lane, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+    sts16(stg_addr(stg, lane, j), u);
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                   const __grid_constant__ CUtensorMap tma_b,
+                                                                   bf16* __restrict__ C, int ldc, int M, int N, int K,
+                                                                   EpiView<bf16> epi) {
+  using cfg = CfgWS<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base + ((WS_EPI_WARPS * EPI_TILE_BYTES + 1023) & ~1023);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), WS_EPI_WARPS);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), (uint32_t)cfg::STAGE_BYTES);
+          const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tma_a, full_bar(s), kb * BK, m0);
+          tma_load_2d(sa + cfg::A_BYTES, &tma_b, full_bar(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), ((lt >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * cfg::ACC_COLS);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sa);
+          const uint64_t bdesc = smem_desc_sw128(sa + cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), cfg::IDESC,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ---- 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware restriction of tcgen05.ld); the two warps of a
+    //      quarter take alternate 32-column chunks
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t stg = smem_base + (uint32_t)((warp - 2) * EPI_TILE_BYTES);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      const int acc = lt & 1;
+      mbar_wait(tfull_bar(acc), (lt >> 1) & 1u);
+      tc_fence_after();
+      const long long row0 = (long long)m0 + q * 32;
+      const int rows_ok = (int)min((long long)32, (long long)M - row0);     // may be <= 0
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        const int col0 = n0 + c0;
+        const int cols_ok = min(32, N - col0);                              // may be <= 0
+        if (rows_ok <= 0 || cols_ok <= 0) continue;                         // warp-uniform
+        float v[32];
+        {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * cfg::ACC_COLS + c0), r);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (epi.bias) {
+          if (cols_ok == 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
+          }
+        }
+        if (epi.pre_out) {
+          regs_to_stage(stg, lane, v);
+          __syncwarp();
+          s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
+          __syncwarp();
+        }
+        if (epi.flags & GEMM_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (epi.flags & GEMM_DGELU) {
+          g2s_tile(stg, epi.aux + row0 * epi.ld_aux + col0, epi.ld_aux, rows_ok, cols_ok, lane);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = lds16(stg_addr(stg, lane, j));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h[e]);
+              v[j * 8 + 2 * e] *= dgelu_fast(f.x);
+              v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
+            }
+          }
+          __syncwarp();
+        }
+        if (epi.flags & GEMM_RESID) {
+          g2s_tile(stg, epi.resid + row0 * epi.ld_res + col0, epi.ld_res, rows_ok, cols_ok, lane);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = lds16(stg_addr(stg, lane, j));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h[e]);
+              v[j * 8 + 2 * e] += f.x;
+              v[j * 8 + 2 * e + 1] += f.y;
+            }
+          }
+          __syncwarp();
+        }
+        regs_to_stage(stg, lane, v);
+        __syncwarp();
+        s2g_tile(stg, C + row0 * ldc + col0, ldc, rows_ok, cols_ok, lane);
+        __syncwarp();
+      }
+      // hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM on tcgen05:  D[x, y] = sum_m X[m, x] * Y[m, y]   (x tiled by 128 = UMMA M, y <= 64 = UMMA N)
+// Both operands are "MN-major" for the tensor core (the reduction index m is the slow one in memory), which UMMA
+// reads directly from 128-byte-swizzled TMA tiles of [64 rows(m) x 64 columns]: canonical layout
+// ((8,8,n),(8,k)) : ((1,8,LBO),(64,SBO)) in elements, LBO = distance between 64-column chunks, SBO = 1024 B between
+// groups of 8 rows.  The row range is split over blockIdx.z; partial tiles are reduced with fp32 atomics.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int WG_STAGES = 4;
+constexpr int WG_X_BYTES = 2 * 64 * 128;      // two [64 x 64] bf16 boxes (x chunk 0, x chunk 1)
+constexpr int WG_Y_BYTES = 64 * 128;
+constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_Y_BYTES;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024;
+// D=f32, A=B=bf16, both MN-major (bits 15, 16), N = 64, M = 128
+constexpr uint32_t WG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                              ((uint32_t)(128 >> 4) << 24);
+
+__global__ void __launch_bounds__(128) wgrad_umma_kernel(const __grid_constant__ CUtensorMap tma_x,
+                                                        const __grid_constant__ CUtensorMap tma_y,
+                                                        float* __restrict__ G, int ldg, int M, int X, int Y, int swap,
+                                                        int q_inner, int q_taps, int kb_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
+  __shared__ uint32_t tmem_holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (WG_STAGES + s); };
+  const uint32_t tfull = bar0 + 8u * (2 * WG_STAGES);
+  const int x0 = blockIdx.x * 128;
+  const int total_kb = (M + 63) / 64;
+  const int kb_beg = blockIdx.z * kb_per_split;
+  const int kb_end = min(total_kb, kb_beg + kb_per_split);
+  const int num_kb = kb_end - kb_beg;                     // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_x);
+    tma_prefetch_desc(&tma_y);
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"(64u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % WG_STAGES;
+      const uint32_t ph = (uint32_t)(i / WG_STAGES) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      mbar_expect_tx(full_bar(s), (uint32_t)WG_STAGE_BYTES);
+      const uint32_t sa = smem_base + (uint32_t)s * WG_STAGE_BYTES;
+      const int m0 = (kb_beg + i) * 64;
+      tma_load_2d(sa, &tma_x, full_bar(s), x0, m0);
+      tma_load_2d(sa + 8192, &tma_x, full_bar(s), x0 + 64, m0);
+      tma_load_2d(sa + WG_X_BYTES, &tma_y, full_bar(s), 0, m0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % WG_STAGES;
+      const uint32_t ph = (uint32_t)(i / WG_STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t sa = smem_base + (uint32_t)s * WG_STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                        // 16 rows (two 8-row groups = 2048 B) per instruction
+        const uint64_t adesc = smem_desc_mn_sw128(sa + (uint32_t)k * 2048u, 8192u);
+        const uint64_t bdesc = smem_desc_mn_sw128(sa + WG_X_BYTES + (uint32_t)k * 2048u, 8192u);
+        tc_mma_bf16(tmem_base, adesc, bdesc, WG_IDESC, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      tc_commit(empty_bar(s));
+    }
+    tc_commit(tfull);
+  }
+  __syncwarp();
+  mbar_wait(tfull, 0);
+  tc_fence_after();
+  const int x = x0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
+    tc_wait_ld();
+    if (x >= X) continue;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int y = c * 32 + j;
+      if (y >= Y) continue;
+      const int p = swap ? y : x, q = swap ? x : y;
+      atomicAdd(G + (long long)p * ldg + (long long)(q % q_inner) * q_taps + q / q_inner, __uint_as_float(r[j]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+  }
+}
+
 // ---- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -471,6 +881,40 @@ static int launch(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int l
   return 0;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
+                     const GemmEpi& e, cudaStream_t st) {
+  using cfg = CfgWS<BN, STAGES>;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, W, N, K, ldw, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_ws_kernel<BN, STAGES>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_umma_ws_kernel<BN, STAGES><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
+                                                                          EpiView<bf16>(e));
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // can the TMA/UMMA path describe this problem?
@@ -484,6 +928,53 @@ static bool supported(const void* A, int lda, const void* W, int ldw, const void
   return true;
 }
 
+
+// [rows, cols] bf16 row-major, box = 64 rows x 64 columns (128 B), 128-byte swizzle (operands of the wgrad kernel)
+static int make_map_mn(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return S2U_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -100 - (int)r;
+}
+
+// G[P,Q] += A^T B on tcgen05; returns S2U_EUNSUPPORTED when the operands do not fit the kernel's assumptions
+static int launch_wgrad(const bf16* A, int lda, const bf16* B, int ldb, float* G, int ldg, long long M, int P, int Q,
+                        int q_inner, int q_taps, cudaStream_t st) {
+  if (!aligned16(A) || !aligned16(B) || (lda % 8) || (ldb % 8) || M > 0x7fffffffLL) return S2U_EUNSUPPORTED;
+  const int swap = Q > P;                         // the larger side is tiled by 128 (UMMA M), the smaller is UMMA N
+  const int X = swap ? Q : P, Y = swap ? P : Q;
+  if (Y > 64) return S2U_EUNSUPPORTED;
+  CUtensorMap mx, my;
+  int rc = make_map_mn(&mx, swap ? (const void*)B : (const void*)A, M, X, swap ? ldb : lda);
+  if (rc) return rc;
+  rc = make_map_mn(&my, swap ? (const void*)A : (const void*)B, M, Y, swap ? lda : ldb);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          WG_SMEM_BYTES);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  const int x_tiles = ceil_div(X, 128);
+  const int total_kb = (int)((M + 63) / 64);
+  int splits = (2 * num_sms() + x_tiles - 1) / x_tiles;
+  if (splits > total_kb / 4) splits = total_kb / 4;        // at least 4 k-blocks per CTA
+  if (splits < 1) splits = 1;
+  const int kb_per = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kb_per - 1) / kb_per;
+  dim3 grid(x_tiles, 1, splits);
+  wgrad_umma_kernel<<<grid, 128, WG_SMEM_BYTES, st>>>(mx, my, G, ldg, (int)M, X, Y, swap, q_inner, q_taps, kb_per);
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace umma
 
 // ------------------------------------------------------------------------------------------- C ABI
@@ -491,7 +982,8 @@ static bool supported(const void* A, int lda, const void* W, int ldw, const void
 extern "C" {
 
 // backend: 0 = auto (tcgen05 for bf16 when describable, else SIMT), 1 = force SIMT, 2 = force tcgen05,
-//          16+bn = force tcgen05 with tile width bn (32/64/128/256; tuning and tests)
+//          16+bn = force tcgen05 with tile width bn (32/64/128/256; tuning and tests),
+//          512+bn = the earlier one-tile-per-CTA tcgen05 kernel (A/B measurements only)
 int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const float* bias,
              void* pre_out, int ld_pre, const void* aux, int ld_aux, const void* resid, int ld_res, int flags,
              int dtype, int backend, void* stream) {
@@ -502,23 +994,30 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
   GemmEpi e{bias, pre_out, aux, resid, ld_pre, ld_aux, ld_res, flags};
   const bool want_umma = dtype == S2U_BF16 && backend != 1;
   if (want_umma && umma::supported(A, lda, W, ldw, C, ldc, N, K, e)) {
-    int bn = backend >= 16 ? backend - 16 : 0;
+    const bool legacy = backend >= 512;          // 512+bn: one-tile-per-CTA kernel (kept for A/B measurements)
+    int bn = legacy ? backend - 512 : (backend >= 16 ? backend - 16 : 0);
     if (bn == 0) {
       if (N <= 32) bn = 32;
       else if (N <= 64) bn = 64;
-      else {
-        // wide tiles amortise the A read; narrow ones fill the 148 SMs when the grid is small
-        const long long t256 = (long long)ceil_div(M, 128) * ceil_div(N, 256);
-        bn = (t256 >= 148 && N >= 256) ? 256 : 128;
-      }
+      else if (N <= 128) bn = 128;
+      else bn = 256;   // 128x256 tiles: fewest operand bytes per FLOP from L2 (measured best on every model shape)
     }
     const bf16 *a = (const bf16*)A, *w = (const bf16*)W;
     bf16* c = (bf16*)C;
+    if (legacy) {
+      switch (bn) {
+        case 32: return umma::launch<32, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 64: return umma::launch<64, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 128: return umma::launch<128, 3>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 256: return umma::launch<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        default: return S2U_EINVAL;
+      }
+    }
     switch (bn) {
-      case 32: return umma::launch<32, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 64: return umma::launch<64, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 128: return umma::launch<128, 3>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 256: return umma::launch<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 32: return umma::launch_ws<32, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 64: return umma::launch_ws<64, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 128: return umma::launch_ws<128, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 256: return umma::launch_ws<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
       default: return S2U_EINVAL;
     }
   }
@@ -536,6 +1035,11 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
                    int q_inner, int q_taps, int dtype, void* stream) {
   if (M <= 0 || P <= 0 || Q <= 0) return S2U_EINVAL;
   if (q_inner <= 0) { q_inner = Q; q_taps = 1; }
+  if (dtype == S2U_BF16) {
+    const int rc = umma::launch_wgrad((const bf16*)A, lda, (const bf16*)B, ldb, G, ldg, M, P, Q, q_inner, q_taps,
+                                      (cudaStream_t)stream);
+    if (rc != S2U_EUNSUPPORTED) return rc;
+  }
   const int tiles = ceil_div(P, 64) * ceil_div(Q, 64);
   int splits = (int)((M + 255) / 256);
   const int want = (4 * 148 + tiles - 1) / tiles;

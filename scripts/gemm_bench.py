@@ -1,0 +1,55 @@
+"""GPU-box micro-benchmark of the GEMM kernel on the model's dominant shapes (CUDA events, back-to-back launches)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sam2_unet_b200.engine import Ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+ops = Ops(torch.bfloat16, dev)
+shapes = [(5808, 2304, 576), (5808, 576, 2304), (5808, 1728, 576), (5808, 576, 576), (92928, 576, 144),
+          (92928, 144, 576), (23232, 1152, 288), (23232, 288, 1152), (1452, 4608, 1152), (1452, 1152, 4608),
+          (92928, 64, 576), (92928, 32, 144), (8192, 8192, 8192)]
+variants = [("ws128", 16 + 128), ("ws256", 16 + 256), ("old128", 512 + 128), ("old256", 512 + 256)]
+flagsets = [("plain", 0, False), ("gelu+pre", 1, True), ("dgelu", 2, False), ("resid", 4, False)]
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+
+def timeit(fn, iters=20):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+for (M, N, K) in shapes:
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=dev)
+    aux = torch.randn(M, N, device=dev).bfloat16()
+    C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    fl = 2.0 * M * N * K
+    t_ref = timeit(lambda: torch.matmul(A, W.t(), out=C))
+    line = f"{str((M, N, K)):22s} cublas {t_ref:7.1f}us {fl / t_ref / 1e6:6.0f}TF |"
+    for fname, fl_, use_pre in flagsets:
+        if fname != "plain" and (M, N, K) not in ((5808, 2304, 576), (5808, 576, 2304), (92928, 576, 144)):
+            continue
+        for vname, be in variants:
+            if N <= 64 and "256" in vname:
+                continue
+            try:
+                t = timeit(lambda: ops.gemm(A, W, C, bias=bias, pre_out=pre if use_pre else None,
+                                            aux=aux if fl_ & 2 else None, resid=aux if fl_ & 4 else None, flags=fl_,
+                                            backend=be))
+                line += f" {fname}/{vname} {t:6.1f}us {fl / t / 1e6:5.0f}TF |"
+            except Exception as e:  # noqa: BLE001
+                line += f" {fname}/{vname} ERR |"
+    print(line, flush=True)

@@ -90,6 +90,18 @@ def test_gemm_umma(cuda, shape, bn):
     _close(C2, A.float() @ W.float().t(), 1e-2, "plain")
 
 
+@pytest.mark.parametrize("shape", [(3000, 32, 144), (5808, 576, 32), (777, 64, 64), (92928, 64, 576), (100, 64, 2304),
+                                   (1452, 1152, 32), (4096, 64, 136)])
+def test_wgrad_tcgen05_shapes(cuda, shape):
+    """bf16 weight-gradient GEMM (MN-major tcgen05 path) on the adapter / conv shapes, ragged row counts included."""
+    M, P, Q = shape
+    ops = _ops("bf16", cuda)
+    A, B = _rand((M, P), "bf16", cuda, 1), _rand((M, Q), "bf16", cuda, 2)
+    G = torch.zeros(P, Q, device=cuda)
+    ops.wgrad(A, B, G)
+    _close(G, A.float().t() @ B.float(), 2e-3, "wgrad")
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_wgrad_colsum(cuda, dtype):
     ops = _ops(dtype, cuda)
