@@ -120,8 +120,11 @@ def test_fused_train_step_matches_autograd_path(cuda):
     for losses, sd in results[1:]:
         assert np.allclose(losses, base_losses, rtol=2e-4), (losses, base_losses)
         for k in base_sd:
+            # Adam normalises every element's update to ~lr, so an element whose gradient is at the level of the
+            # (atomic-order) summation noise may move differently in two runs: compare tensors in rel-L2
             if base_sd[k].dtype.is_floating_point:
-                assert _maxnorm(sd[k], base_sd[k]) <= 2e-3, k
+                d = (sd[k].double() - base_sd[k].double()).norm() / base_sd[k].double().norm().clamp_min(1e-12)
+                assert d <= 5e-3, (k, float(d))
     assert base_losses[-1] < base_losses[0]
 
 
