@@ -13,6 +13,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .ddp import GradSync
 from .model import SAM2UNet
 
 
@@ -121,15 +122,9 @@ class TrainStep:
                   weit.data_ptr(), sums.data_ptr(), 0, g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), B, S, S, 3,
                   st)
         flat.grad.zero_()
-        works = []
-
-        def on_bucket(lo, hi):
-            if self.world > 1:
-                works.append(dist.all_reduce(flat.grad[lo:hi], group=self.pg, async_op=True))
-
-        eng.backward(g[0], g[1], g[2], on_bucket=on_bucket)
-        for w in works:
-            w.wait()
+        sync = GradSync(flat.grad, self.pg)
+        eng.backward(g[0], g[1], g[2], on_bucket=sync.on_bucket if self.world > 1 else None)
+        sync.finish()
         self.optim.launch()
         return loss
 

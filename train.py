@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""train.py — drop-in for the reference's training entry point (/root/reference/train.py:32-208).
+
+Same flags, same per-epoch flow (train -> CosineAnnealingLR step -> evaluate -> best / latest checkpoint with the
+reference's file names, train.py:127-149), same state-dict files.  The step itself (train.py:66-86) runs as
+`sam2_unet_b200.TrainStep`: forward, the three structure_loss terms, backward and AdamW on the sm_100a kernels,
+captured in one CUDA graph, with the loss read back only when it is printed (the reference syncs every step at
+train.py:81).  Under torchrun the batch is sharded over ranks and gradients are all-reduced over NCCL.
+
+Data: the reference's own `dataset.py` / `eval.py` (CPU image I/O, augmentation and metrics: out of scope of this
+package) are used unchanged when they are importable; otherwise a minimal folder loader and an on-device IoU stand
+in, and `--synthetic N` trains on N seeded synthetic images without any files.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from sam2_unet_b200 import SAM2UNet, TrainStep, cosine_lr
+
+
+def structure_loss(pred, mask):
+    """train.py:21-29 — kept importable from this module like in the reference."""
+    from sam2_unet_b200 import structure_loss as _sl
+    return _sl(pred, mask)
+
+
+class _FolderData(torch.utils.data.Dataset):
+    """Longest-side resize + zero pad to `size`, ImageNet normalisation (dataset.py:34-143 without augmentation)."""
+
+    def __init__(self, image_root, gt_root, size):
+        from PIL import Image  # noqa: F401
+        self.images = sorted(os.path.join(image_root, f) for f in os.listdir(image_root) if f.endswith((".jpg", ".png")))
+        self.gts = sorted(os.path.join(gt_root, f) for f in os.listdir(gt_root) if f.endswith(".png"))
+        self.size = size
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        import numpy as np
+        from PIL import Image
+        img = torch.from_numpy(np.asarray(Image.open(self.images[i]).convert("RGB"), dtype=np.float32) / 255).permute(2, 0, 1)
+        gt = torch.from_numpy(np.asarray(Image.open(self.gts[i]).convert("L"), dtype=np.float32) / 255)[None]
+        s = self.size / max(img.shape[1:])
+        hw = (max(1, round(img.shape[1] * s)), max(1, round(img.shape[2] * s)))
+        img = F.interpolate(img[None], size=hw, mode="bilinear", align_corners=False)[0]
+        gt = (F.interpolate(gt[None], size=hw, mode="nearest")[0] > 0.5).float()
+        pad = (0, self.size - hw[1], 0, self.size - hw[0])
+        mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+        return {"image": F.pad((img - mean) / std, pad), "label": F.pad(gt, pad)}
+
+
+class _Synthetic(torch.utils.data.Dataset):
+    def __init__(self, n, size):
+        g = torch.Generator().manual_seed(0)
+        yy, xx = torch.meshgrid(torch.arange(size, dtype=torch.float32), torch.arange(size, dtype=torch.float32), indexing="ij")
+        self.items = []
+        for _ in range(n):
+            m = torch.zeros(size, size)
+            for _ in range(3):
+                cy, cx = (torch.rand(2, generator=g) * size).tolist()
+                r = (0.08 + 0.2 * torch.rand(1, generator=g).item()) * size
+                m = torch.maximum(m, ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r).float())
+            x = 0.5 * torch.randn(3, size, size, generator=g) + 2 * m - 0.5
+            self.items.append({"image": x, "label": m[None]})
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+
+def _datasets(args):
+    if args.synthetic > 0:
+        ds = _Synthetic(args.synthetic, args.size)
+        return ds, ds
+    try:                                             # the reference's own pipeline, unchanged, when it is on the path
+        from dataset import FullDataset
+        return (FullDataset(args.train_image_path, args.train_mask_path, args.size, mode="train"),
+                FullDataset(args.test_image_path, args.test_gt_path, args.size, mode="test"))
+    except ImportError:
+        return (_FolderData(args.train_image_path, args.train_mask_path, args.size),
+                _FolderData(args.test_image_path, args.test_gt_path, args.size))
+
+
+@torch.no_grad()
+def evaluate(model, dataset, device, batch_size):
+    """Mean IoU of sigmoid(out) > 0.5 against the mask (stand-in for eval.py's semantic IoU, eval.py:55-90)."""
+    model.eval()
+    inter = union = 0.0
+    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
+    ious = []
+    for batch in loader:
+        res, _, _ = model(batch["image"].to(device))
+        pred = res.sigmoid() > 0.5
+        gt = batch["label"].to(device) > 0.5
+        inter = (pred & gt).flatten(1).sum(1).float()
+        union = (pred | gt).flatten(1).sum(1).float()
+        ious.append(((inter + 1e-6) / (union + 1e-6)).cpu())
+    return torch.cat(ious).mean().item() if ious else 0.0
+
+
+def main(args):
+    ddp = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ddp:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank() if ddp else 0
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    train_ds, test_ds = _datasets(args)
+    sampler = torch.utils.data.distributed.DistributedSampler(train_ds, shuffle=True) if ddp else None
+    loader = torch.utils.data.DataLoader(train_ds, batch_size=args.batch_size, shuffle=sampler is None, sampler=sampler,
+                                         num_workers=0 if args.synthetic else 8, drop_last=True, pin_memory=True)
+    model = SAM2UNet(checkpoint_path=args.hiera_path if os.path.exists(args.hiera_path) else "",
+                     model_cfg=args.model_cfg, dtype=args.dtype).to(device)
+    if len(args.checkpoint) > 0:
+        model.load_state_dict(torch.load(args.checkpoint, map_location=device), strict=True)
+    step = TrainStep(model, lr=args.lr, weight_decay=args.weight_decay, use_graph=not args.no_graph)
+    os.makedirs(args.save_path, exist_ok=True)
+    log_path = os.path.join(args.save_path, "log.txt")
+    base_mean_iou = args.base_mean_iou
+    for epoch in range(args.epoch):
+        if rank == 0:
+            print("Training:")
+        model.train()
+        if sampler is not None:
+            sampler.set_epoch(epoch)
+        step.optim.param_groups[0]["lr"] = cosine_lr(epoch, args.epoch, args.lr)      # train.py:54,87
+        t0, seen, loss = time.time(), 0, None
+        for i, batch in enumerate(loader):
+            loss = step(batch["image"], batch["label"])
+            seen += batch["image"].shape[0]
+            if i % 10 == 0 and rank == 0:
+                print("epoch-{}-{}: loss:{}".format(epoch + 1, i + 1, loss.sum().item()))
+        torch.cuda.synchronize(device)
+        epoch_loss = loss.sum().item() if loss is not None else float("nan")
+        if rank == 0:
+            print(f"epoch {epoch + 1}: {seen / max(time.time() - t0, 1e-9):.1f} img/s/rank")
+            print("Evaluating", end="")
+            mean_iou = evaluate(model, test_ds, device, args.batch_size)
+            epoch_name = f"epoch-{epoch + 1}_loss-{epoch_loss:.3f}"
+            line = f"{epoch_name}: mIoU {mean_iou:.4f}"
+            print("\n" + line)
+            with open(log_path, "a") as f:
+                f.write(line + "\n")
+            if mean_iou > base_mean_iou:                                              # train.py:133-143
+                base_mean_iou = mean_iou
+                path = os.path.join(args.save_path, f"SAM2-UNet_{epoch_name}_iou-{mean_iou:.3f}.pth")
+                torch.save(model.state_dict(), path)
+                print("Saving Snapshot best:", path)
+            elif (epoch + 1) % args.save_interval == 0 or (epoch + 1) == args.epoch:  # train.py:144-149
+                path = os.path.join(args.save_path, "SAM2-UNet_epoch-latest.pth")
+                torch.save(model.state_dict(), path)
+                print("Saving Snapshot:", path)
+        if ddp:
+            dist.barrier()
+    if ddp:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser("SAM2-UNet")
+    parser.add_argument("--save_path", type=str, required=True, help="path to store the checkpoint")
+    parser.add_argument("--hiera_path", type=str, default="../sam2_hiera_small.pt", help="path to the sam2 pretrained hiera")
+    parser.add_argument("--checkpoint", type=str, default="", help="path to the checkpoint of sam2-unet")
+    parser.add_argument("--train_image_path", type=str, default="data_train/images/")
+    parser.add_argument("--train_mask_path", type=str, default="data_train/masks/")
+    parser.add_argument("--test_image_path", type=str, default="data_test/images/")
+    parser.add_argument("--test_gt_path", type=str, default="data_test/masks/")
+    parser.add_argument("--epoch", type=int, default=500, help="training epochs")
+    parser.add_argument("--lr", type=float, default=0.001, help="learning rate")
+    parser.add_argument("--batch_size", default=16, type=int)
+    parser.add_argument("--size", default=960, type=int)
+    parser.add_argument("--weight_decay", default=5e-4, type=float)
+    parser.add_argument("--save_interval", default=20, type=int)
+    parser.add_argument("--base_mean_iou", default=0.83, type=float)
+    # extras of this implementation
+    parser.add_argument("--model_cfg", default="sam2_hiera_s.yaml", help="trunk yaml: sam2_hiera_{t,s,b+,l}.yaml")
+    parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    parser.add_argument("--synthetic", type=int, default=0, help="train on N seeded synthetic images (no files needed)")
+    main(parser.parse_args())
