@@ -283,7 +283,7 @@ def run_b200(args):
     if rank == 0:
         pk = peaks()
         if args.mode == "train":
-            eager = TrainStep(model, lr=1e-3, weight_decay=5e-4, use_graph=False)
+            eager = TrainStep(model, lr=1e-3, weight_decay=5e-4, use_graph=False, sync_grads=False)
             eager.optim = step.optim
             fn = lambda: eager(xd, md)                          # noqa: E731
         else:
@@ -326,7 +326,12 @@ def run_b200(args):
                 "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroying a communicator whose collectives were captured in a live CUDA
+        # graph can block; everything has been reported and synchronised at this point
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -92,10 +92,12 @@ class TrainStep:
     """
 
     def __init__(self, model: SAM2UNet, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.999), eps=1e-8,
-                 use_graph: bool = True, process_group=None):
+                 use_graph: bool = True, process_group=None, sync_grads: bool = True):
         self.model = model
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        # sync_grads=False: a rank-local step without the all-reduce (profiling one rank must not issue collectives)
+        self.world = (dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1) \
+            if sync_grads else 1
         self.optim = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=lr, betas=betas, eps=eps,
                                 weight_decay=weight_decay, model=model, grad_scale=1.0 / self.world)
         self.use_graph = use_graph
