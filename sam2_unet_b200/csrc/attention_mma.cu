@@ -53,6 +53,23 @@ __device__ __forceinline__ uint4 tok8(const bf16* __restrict__ qkv, const float*
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(bias[col + 2 * i], bias[col + 2 * i + 1]);
   return u;
 }
+__device__ __forceinline__ void cp_async16(bf16* dst, const bf16* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous variant: real tokens are copied global -> shared by cp.async (no registers, no stall), padded tokens
+// are written directly
+__device__ __forceinline__ void tok8_async(bf16* dst, const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                           const Geom& g, int b, int y, int x, int col) {
+  if (y < g.H && x < g.W) {
+    cp_async16(dst, qkv + (((long long)b * g.H + y) * g.W + x) * (3LL * g.nh * g.hd) + col);
+  } else {
+    *reinterpret_cast<uint4*>(dst) = tok8(qkv, bias, g, b, y, x, col);
+  }
+}
 __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
   uint4 r;
   const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
@@ -100,17 +117,18 @@ __device__ __forceinline__ void load_kv(bf16* dst, const bf16* qkv, const float*
   for (int e = threadIdx.x; e < BN * CH; e += NT) {
     const int r = e / CH, c = e - r * CH;
     const int idx = r0 + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
+    bf16* d = dst + r * LD + c * 8;
     if (idx < w.nk && c * 8 < g.hd) {
       const int col = which * C + head * g.hd + c * 8;
       if (idx < w.n_real) {
         const int ty = idx / w.rw, tx = idx - ty * w.rw;
-        v = tok8(qkv, bias, g, w.b, w.wy * g.wh + ty, w.wx * g.ww + tx, col);
+        tok8_async(d, qkv, bias, g, w.b, w.wy * g.wh + ty, w.wx * g.ww + tx, col);
       } else {
-        v = tok8(qkv, bias, g, w.b, g.H, g.W, col);           // the virtual pad key: bias
+        *reinterpret_cast<uint4*>(d) = tok8(qkv, bias, g, w.b, g.H, g.W, col);   // the virtual pad key: bias
       }
+    } else {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
   }
 }
 
@@ -122,19 +140,21 @@ __device__ __forceinline__ void load_q(bf16* dst, const bf16* qkv, const float* 
   for (int e = threadIdx.x; e < BM * CH; e += NT) {
     const int r = e / CH, c = e - r * CH;
     const int idx = r0 + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
+    bf16* d = dst + r * LD + c * 8;
     if (idx < w.nq && c * 8 < g.hd) {
       const int py = idx / w.qrw, px = idx - py * w.qrw;
       const int col = head * g.hd + c * 8;
       if (!g.pool) {
-        v = tok8(qkv, bias, g, w.b, w.wy * g.wh + py, w.wx * g.ww + px, col);
+        tok8_async(d, qkv, bias, g, w.b, w.wy * g.wh + py, w.wx * g.ww + px, col);
       } else {
         const int y = w.wy * g.wh + 2 * py, x = w.wx * g.ww + 2 * px;
-        v = max8(max8(tok8(qkv, bias, g, w.b, y, x, col), tok8(qkv, bias, g, w.b, y, x + 1, col)),
+        *reinterpret_cast<uint4*>(d) =
+            max8(max8(tok8(qkv, bias, g, w.b, y, x, col), tok8(qkv, bias, g, w.b, y, x + 1, col)),
                  max8(tok8(qkv, bias, g, w.b, y + 1, x, col), tok8(qkv, bias, g, w.b, y + 1, x + 1, col)));
       }
+    } else {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
   }
 }
 
@@ -152,10 +172,11 @@ __device__ __forceinline__ void load_o(bf16* dst, const bf16* src, const Geom& g
   for (int e = threadIdx.x; e < BM * CH; e += NT) {
     const int r = e / CH, c = e - r * CH;
     const long long tok = out_token(g, w, r0 + r);
-    uint4 v = make_uint4(0, 0, 0, 0);
+    bf16* d = dst + r * LD + c * 8;
     if (tok >= 0 && c * 8 < g.hd)
-      v = *reinterpret_cast<const uint4*>(src + tok * (g.nh * g.hd) + head * g.hd + c * 8);
-    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+      cp_async16(d, src + tok * (g.nh * g.hd) + head * g.hd + c * 8);
+    else
+      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -211,8 +232,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
   constexpr int LD = HDP + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
-  bf16* Ks = Qs + BM * LD;
-  bf16* Vs = Ks + BN * LD;
+  bf16* KV = Qs + BM * LD;                                      // [2 buffers][K | V]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.z;
   const Win w = make_win(g, blockIdx.y);
@@ -222,16 +242,25 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
   const float sl2 = g.scale * 1.4426950408889634f;
 
   load_q<HDP>(Qs, qkv, bias, g, w, head, q0);
+  load_kv<HDP>(KV, qkv, bias, g, w, head, 1, 0);
+  load_kv<HDP>(KV + BN * LD, qkv, bias, g, w, head, 2, 0);
+  cp_async_commit();
   float o[HDP / 8][4];
 #pragma unroll
   for (int j = 0; j < HDP / 8; ++j)
 #pragma unroll
     for (int t = 0; t < 4; ++t) o[j][t] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows lane/4 and lane/4 + 8 of this warp's 16
-  for (int k0 = 0; k0 < nk; k0 += BN) {
-    __syncthreads();
-    load_kv<HDP>(Ks, qkv, bias, g, w, head, 1, k0);
-    load_kv<HDP>(Vs, qkv, bias, g, w, head, 2, k0);
+  for (int k0 = 0, it = 0; k0 < nk; k0 += BN, ++it) {
+    const bf16* Ks = KV + (it & 1) * 2 * BN * LD;
+    const bf16* Vs = Ks + BN * LD;
+    if (k0 + BN < nk) {                                         // prefetch the next key tile into the other buffer
+      bf16* nxt = KV + ((it + 1) & 1) * 2 * BN * LD;
+      load_kv<HDP>(nxt, qkv, bias, g, w, head, 1, k0 + BN);
+      load_kv<HDP>(nxt + BN * LD, qkv, bias, g, w, head, 2, k0 + BN);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
     float s[8][4];
     mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
@@ -275,6 +304,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
       o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1;
     }
     mm_p_b<HDP>(o, s, Vs, lane);
+    __syncthreads();                                            // buffer (it & 1) is refilled two iterations later
   }
   const int C = g.nh * g.hd;
 #pragma unroll
@@ -323,8 +353,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* dOs = Qs + BM * LD;
-  bf16* Ks = dOs + BM * LD;
-  bf16* Vs = Ks + BN * LD;
+  bf16* KV = dOs + BM * LD;                                     // [2 buffers][K | V]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.z;
   const Win w = make_win(g, blockIdx.y);
@@ -336,6 +365,9 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
 
   load_q<HDP>(Qs, qkv, bias, g, w, head, q0);
   load_o<HDP>(dOs, dout, g, w, head, q0);
+  load_kv<HDP>(KV, qkv, bias, g, w, head, 1, 0);
+  load_kv<HDP>(KV + BN * LD, qkv, bias, g, w, head, 2, 0);
+  cp_async_commit();
   const int r0 = warp * 16 + (lane >> 2);
   const long long tok0 = out_token(g, w, q0 + r0), tok1 = out_token(g, w, q0 + r0 + 8);
   const float L0 = tok0 >= 0 ? lse[tok0 * g.nh + head] * 1.4426950408889634f : INFINITY;
@@ -347,10 +379,16 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
   for (int j = 0; j < HDP / 8; ++j)
 #pragma unroll
     for (int t = 0; t < 4; ++t) dq[j][t] = 0.f;
-  for (int k0 = 0; k0 < nk; k0 += BN) {
-    __syncthreads();
-    load_kv<HDP>(Ks, qkv, bias, g, w, head, 1, k0);
-    load_kv<HDP>(Vs, qkv, bias, g, w, head, 2, k0);
+  for (int k0 = 0, it = 0; k0 < nk; k0 += BN, ++it) {
+    const bf16* Ks = KV + (it & 1) * 2 * BN * LD;
+    const bf16* Vs = Ks + BN * LD;
+    if (k0 + BN < nk) {
+      bf16* nxt = KV + ((it + 1) & 1) * 2 * BN * LD;
+      load_kv<HDP>(nxt, qkv, bias, g, w, head, 1, k0 + BN);
+      load_kv<HDP>(nxt + BN * LD, qkv, bias, g, w, head, 2, k0 + BN);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
     float s[8][4], dp[8][4];
     mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
@@ -369,6 +407,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
       s[j][3] = p11 * (dp[j][3] - D1) * g.scale;
     }
     mm_p_b<HDP>(dq, s, Ks, lane);
+    __syncthreads();
   }
   // scatter into the q third of dqkv (argmax routing through the q max-pool)
   const int C = g.nh * g.hd;
@@ -429,10 +468,8 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qk
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Ks = reinterpret_cast<bf16*>(smraw);
   bf16* Vs = Ks + BN * LD;
-  bf16* Qs = Vs + BN * LD;
-  bf16* dOs = Qs + BM * LD;
-  float* Ls = reinterpret_cast<float*>(dOs + BM * LD);     // [64] lse * log2(e)  (+inf for cropped queries)
-  float* Ds = Ls + BM;                                     // [64]
+  bf16* QO = Vs + BN * LD;                                 // [2 buffers][Q | dO]
+  float* LD2 = reinterpret_cast<float*>(QO + 4 * BM * LD); // [2 buffers][lse*log2e (64) | D (64)]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.z;
   const Win w = make_win(g, blockIdx.y);
@@ -442,23 +479,34 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qk
   const int nk = w.n_real, nq = w.nq;
   const float sl2 = g.scale * 1.4426950408889634f;
 
+  auto stage_q = [&](int buf, int q0) {                     // Q, dO, lse, D of one query tile -> buffer `buf`
+    bf16* qs = QO + buf * 2 * BM * LD;
+    load_q<HDP>(qs, qkv, bias, g, w, head, q0);
+    load_o<HDP>(qs + BM * LD, dout, g, w, head, q0);
+    if (threadIdx.x < BM) {
+      const long long tok = out_token(g, w, q0 + threadIdx.x);
+      LD2[buf * 2 * BM + threadIdx.x] = tok >= 0 ? lse[tok * g.nh + head] * 1.4426950408889634f : INFINITY;
+      LD2[buf * 2 * BM + BM + threadIdx.x] = tok >= 0 ? Dv[tok * g.nh + head] : 0.f;
+    }
+  };
   load_kv<HDP>(Ks, qkv, bias, g, w, head, 1, k0);
   load_kv<HDP>(Vs, qkv, bias, g, w, head, 2, k0);
+  stage_q(0, 0);
+  cp_async_commit();
   float dk[HDP / 8][4], dv[HDP / 8][4];
 #pragma unroll
   for (int j = 0; j < HDP / 8; ++j)
 #pragma unroll
     for (int t = 0; t < 4; ++t) { dk[j][t] = 0.f; dv[j][t] = 0.f; }
   const int kr0 = k0 + warp * 16 + (lane >> 2);            // this thread's key rows: kr0, kr0 + 8
-  for (int q0 = 0; q0 < nq; q0 += BM) {
-    __syncthreads();
-    load_q<HDP>(Qs, qkv, bias, g, w, head, q0);
-    load_o<HDP>(dOs, dout, g, w, head, q0);
-    if (threadIdx.x < BM) {
-      const long long tok = out_token(g, w, q0 + threadIdx.x);
-      Ls[threadIdx.x] = tok >= 0 ? lse[tok * g.nh + head] * 1.4426950408889634f : INFINITY;
-      Ds[threadIdx.x] = tok >= 0 ? Dv[tok * g.nh + head] : 0.f;
-    }
+  for (int q0 = 0, it = 0; q0 < nq; q0 += BM, ++it) {
+    const bf16* Qs = QO + (it & 1) * 2 * BM * LD;
+    const bf16* dOs = Qs + BM * LD;
+    const float* Ls = LD2 + (it & 1) * 2 * BM;
+    const float* Ds = Ls + BM;
+    if (q0 + BM < nq) stage_q((it + 1) & 1, q0 + BM);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
     float st[8][4], dpt[8][4];                              // [16 keys x 64 queries]
     mm_ab_t<HDP>(st, Ks, Qs, warp, lane);
@@ -484,6 +532,7 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qk
       st[j][3] *= (dpt[j][3] - Db) * g.scale;
     }
     mm_p_b<HDP>(dk, st, Qs, lane);
+    __syncthreads();
   }
   const int C = g.nh * g.hd;
 #pragma unroll
@@ -525,7 +574,7 @@ static int make_geom(Geom& g, int B, int H, int W, int nh, int hd, int window, i
 template <int HDP>
 static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse, const Geom& g, cudaStream_t st) {
   dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
-  const size_t smem = (size_t)(BM + 2 * BN) * (HDP + 8) * sizeof(bf16);
+  const size_t smem = (size_t)(BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
   S2U_ALLOW_SMEM(fwd_kernel<HDP>);
   fwd_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, out, lse, g);
   S2U_LAUNCH_CHECK();
@@ -540,14 +589,14 @@ static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const
   S2U_LAUNCH_CHECK();
   {
     dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
-    const size_t smem = (size_t)(2 * BM + 2 * BN) * (HDP + 8) * sizeof(bf16);
+    const size_t smem = (size_t)(2 * BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
     S2U_ALLOW_SMEM(bwd_dq_kernel<HDP>);
     bwd_dq_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, lse, Dws, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
   }
   {
     dim3 grid(ceil_div(g.wh * g.ww, BN), g.B * g.nwy * g.nwx, g.nh);
-    const size_t smem = (size_t)(2 * BM + 2 * BN) * (HDP + 8) * sizeof(bf16) + 2 * BM * sizeof(float);
+    const size_t smem = (size_t)(4 * BM + 2 * BN) * (HDP + 8) * sizeof(bf16) + 4 * BM * sizeof(float);
     S2U_ALLOW_SMEM(bwd_dkv_kernel<HDP>);
     bwd_dkv_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, lse, Dws, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
