@@ -32,6 +32,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# (M, N, K) -> DRAM bytes of one launch measured by ncu --set full (see profiles/); filled per round
+NCU_TRAFFIC = {(5808, 2304, 576): 18.95e6}   # r1: 9.41 MB read + 9.54 MB written (L2 absorbs the rest)
+
 METRIC = {"train": "train img/s, SAM2-UNet Hiera-L 352x352 (fwd + 3x structure_loss + bwd + AdamW)",
           "infer": "infer img/s, SAM2-UNet Hiera-L 352x352 forward"}
 
@@ -51,6 +54,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--profile-out", default="", help="write the per-op CUDA-event breakdown of one eager step here")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     return ap.parse_args()
 
 
@@ -183,15 +188,21 @@ def workload_name(args):
 # --------------------------------------------------------------------------------------------------- B200 arm
 
 def gemm_flops(rec):
-    """Algorithmic FLOPs and time of the GEMM-family calls of one instrumented step."""
+    """Algorithmic FLOPs and time of the GEMM-family calls of one instrumented step, and the same for the single
+    (M, N, K) shape that takes the most time (the stage-3 MLP GEMM of Hiera-L)."""
     fl = ms = 0.0
     n = 0
+    shapes = {}
     for name, t, a in rec:
         if name == "s2u_gemm":
             fl += 2.0 * a[6] * a[7] * a[8]
             ms += t
             n += 1
-    return fl, ms, n
+            s = shapes.setdefault((a[6], a[7], a[8]), [0, 0.0])
+            s[0] += 1
+            s[1] += t
+    top = max(shapes.items(), key=lambda kv: kv[1][1]) if shapes else None
+    return fl, ms, n, top
 
 
 def run_b200(args):
@@ -240,16 +251,12 @@ def run_b200(args):
         run_e2e = lambda: step(xh, mh).cpu()                    # noqa: E731  H2D batch + D2H loss every step
         d2h = 12
     else:
+        from sam2_unet_b200 import Predictor
         model.eval()
-
-        def run_dev():
-            with torch.no_grad():
-                return model(xd)
-
-        def run_e2e():
-            with torch.no_grad():
-                return model(xh.to(dev, non_blocking=True))[0].mean().cpu()
-        d2h = 4
+        pred = Predictor(model, use_graph=not args.no_graph)
+        run_dev = lambda: pred(xd)                              # noqa: E731
+        run_e2e = lambda: pred(xh)[0].cpu()                     # noqa: E731  H2D batch + D2H of the main logits map
+        d2h = B * S * S * 4
     h2d = xh.numel() * 4 + (mh.numel() * 4 if args.mode == "train" else 0)
 
     def timed(fn, steps, warmup):
@@ -272,6 +279,16 @@ def run_b200(args):
         return ms, clk.summary(), _lib.launch_count() - l0
 
     warm = max(args.warmup, 3)
+    if args.ncu_range:
+        for _ in range(warm + 3):
+            run_dev()
+        torch.cuda.synchronize(dev)
+        torch.cuda.cudart().cudaProfilerStart()
+        run_dev()
+        torch.cuda.synchronize(dev)
+        torch.cuda.cudart().cudaProfilerStop()
+        print("ncu range done", flush=True)
+        return
     ms, clocks, _ = timed(run_dev, args.steps, warm + 3)        # +3: two eager warm-ups and the graph capture
     value = B * world * args.steps / (ms / 1e3)
     ms_e2e, _, _ = timed(run_e2e, args.steps, 2)
@@ -287,20 +304,32 @@ def run_b200(args):
             eager.optim = step.optim
             fn = lambda: eager(xd, md)                          # noqa: E731
         else:
-            fn = run_dev
+            def fn():
+                with torch.no_grad():
+                    return model(xd)
         fn()
         torch.cuda.synchronize(dev)
         _lib.profile_begin()
         fn()
         rec = _lib.profile_end()
         launches_per_step = len(rec)
-        fl, gms, ng = gemm_flops(rec)
+        fl, gms, ng, top = gemm_flops(rec)
         total_ms = sum(t for _, t, _ in rec)
-        achieved = fl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        (tm, tn, tk), (tcalls, tms) = top
+        tfl = 2.0 * tm * tn * tk
+        achieved = tfl * tcalls / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
+        all_tf = fl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the committed
+        # `ncu --set full` capture (profiles/r1_gemm_ws256_full.md); None when the shape differs from the captured one
+        traffic = NCU_TRAFFIC.get((tm, tn, tk))
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": None,
-                "kernel": "gemm_umma_kernel (tcgen05 + TMA; all GEMM-family launches of one step)",
-                "launches": ng, "gemm_ms_per_step": gms, "gemm_share_of_step": gms / total_ms if total_ms else None,
+                "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+                "kernel": f"gemm_umma_ws_kernel (persistent tcgen05 + TMA GEMM), dominant shape M={tm} N={tn} K={tk}",
+                "algorithmic_flop_per_launch": tfl, "launches_of_shape_per_step": tcalls,
+                "us_per_launch": tms / tcalls * 1e3,
+                "all_gemm_launches": ng, "all_gemm_tflops": all_tf, "gemm_ms_per_step": gms,
+                "gemm_share_of_step": gms / total_ms if total_ms else None,
+                "timing": "CUDA events around each launch of one eager step (includes ~5 us launch latency per call)",
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"}
         if args.profile_out:
             by = {}

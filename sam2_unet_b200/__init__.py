@@ -9,6 +9,7 @@ from . import _lib  # noqa: F401
 from .config import trunk_config  # noqa: F401
 from .loss import structure_loss, structure_loss3  # noqa: F401
 from .model import SAM2UNet  # noqa: F401
-from .optim import FusedAdamW, TrainStep, cosine_lr  # noqa: F401
+from .optim import FusedAdamW, Predictor, TrainStep, cosine_lr  # noqa: F401
 
-__all__ = ["SAM2UNet", "structure_loss", "structure_loss3", "FusedAdamW", "TrainStep", "cosine_lr", "trunk_config"]
+__all__ = ["SAM2UNet", "structure_loss", "structure_loss3", "FusedAdamW", "TrainStep", "Predictor", "cosine_lr",
+           "trunk_config"]

@@ -575,10 +575,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     }
   } else {
     // ---- 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware restriction of tcgen05.ld); the two warps of a
-    //      quarter take alternate 32-column chunks
+    //      quarter take alternate 32-column chunks.  The side input of the epilogue (GELU' argument or residual) is
+    //      prefetched one chunk ahead into registers so its global-load latency hides behind the math and the stores.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t stg = smem_base + (uint32_t)((warp - 2) * EPI_TILE_BYTES);
+    const bf16* side = (epi.flags & GEMM_DGELU) ? epi.aux : ((epi.flags & GEMM_RESID) ? epi.resid : nullptr);
+    const long long ld_side = (epi.flags & GEMM_DGELU) ? epi.ld_aux : epi.ld_res;
+    const bool second_resid = (epi.flags & GEMM_DGELU) && (epi.flags & GEMM_RESID);
+    uint4 pf[4];
+    auto prefetch = [&](int tile, int c0) {                    // chunk (tile, c0) of the side input -> pf
+      const long long r0 = (long long)(tile % m_tiles) * BM + q * 32;
+      const int cc = (tile / m_tiles) * BN + c0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + i * 8 + (lane >> 2);
+        const int c = cc + (lane & 3) * 8;
+        pf[i] = (r < M && c < N) ? __ldg(reinterpret_cast<const uint4*>(side + r * ld_side + c)) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    if (side && (int)blockIdx.x < num_tiles && half * 32 < BN) prefetch(blockIdx.x, half * 32);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
@@ -591,55 +607,68 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         const int col0 = n0 + c0;
         const int cols_ok = min(32, N - col0);                              // may be <= 0
-        if (rows_ok <= 0 || cols_ok <= 0) continue;                         // warp-uniform
+        const bool live = rows_ok > 0 && cols_ok > 0;                       // warp-uniform
         float v[32];
-        {
+        if (live) {
           uint32_t r[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * cfg::ACC_COLS + c0), r);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        }
-        if (epi.bias) {
-          if (cols_ok == 32) {
+          if (epi.bias) {
+            if (cols_ok == 32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          } else {
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
-          }
-        }
-        if (epi.pre_out) {
-          regs_to_stage(stg, lane, v);
-          __syncwarp();
-          s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
-          __syncwarp();
-        }
-        if (epi.flags & GEMM_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-        }
-        if (epi.flags & GEMM_DGELU) {
-          g2s_tile(stg, epi.aux + row0 * epi.ld_aux + col0, epi.ld_aux, rows_ok, cols_ok, lane);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = lds16(stg_addr(stg, lane, j));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              v[j * 8 + 2 * e] *= dgelu_fast(f.x);
-              v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
+              for (int j = 0; j < 32; ++j)
+                if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
             }
           }
-          __syncwarp();
+          if (epi.pre_out) {
+            regs_to_stage(stg, lane, v);
+            __syncwarp();
+            s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
+            __syncwarp();
+          }
+          if (epi.flags & GEMM_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          }
         }
-        if (epi.flags & GEMM_RESID) {
+        if (side) {
+          // the prefetched chunk is exactly this one (chunks are visited in prefetch order)
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sts16(stg_addr(stg, i * 8 + (lane >> 2), lane & 3), pf[i]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = lds16(stg_addr(stg, lane, j));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                if (epi.flags & GEMM_DGELU) {
+                  v[j * 8 + 2 * e] *= dgelu_fast(f.x);
+                  v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
+                } else {
+                  v[j * 8 + 2 * e] += f.x;
+                  v[j * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            }
+            __syncwarp();
+          }
+          // next chunk of this warp: same tile, or the first chunk of its next tile
+          if (c0 + 64 < BN) prefetch(tile, c0 + 64);
+          else if (tile + (int)gridDim.x < num_tiles) prefetch(tile + gridDim.x, half * 32);
+        }
+        if (!live) continue;
+        if (second_resid) {
           g2s_tile(stg, epi.resid + row0 * epi.ld_res + col0, epi.ld_res, rows_ok, cols_ok, lane);
           __syncwarp();
 #pragma unroll

@@ -173,3 +173,47 @@ class TrainStep:
         for p in self.model.flat.params.values():       # this path bypasses autograd: keep .grad unset
             p.grad = None
         return loss
+
+
+class Predictor:
+    """Inference forward (test.py:61, train.py:101) replayed from a CUDA graph: `out, out1, out2 = Predictor(model)(x)`.
+
+    The eager `model(x)` call issues ~700 launches from Python per Hiera-L forward; at small batch that launch stream,
+    not the GPU, is the bottleneck.  The graph is re-captured when the input shape or the weights change."""
+
+    def __init__(self, model: SAM2UNet, use_graph: bool = True):
+        self.model = model
+        self.use_graph = use_graph
+        self._key = None
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._sx = self._outs = None
+        self._warm = 0
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor):
+        model = self.model
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.KernelError("Predictor needs the model on a CUDA device (no CPU fallback)")
+        if model.training:
+            model.eval()
+        eng = model._engine(dev)
+        x = x.contiguous().float()
+        if not self.use_graph:
+            return eng.forward(x.to(dev, non_blocking=True), False, save=False)
+        key = (tuple(x.shape), dev, model.flat.version)
+        if key != self._key:
+            self._key, self._graph, self._warm = key, None, 0
+            self._sx = torch.empty_like(x, device=dev)
+        self._sx.copy_(x, non_blocking=True)
+        if self._graph is None and self._warm < 2:
+            self._warm += 1
+            return eng.forward(self._sx, False, save=False)
+        if self._graph is None:
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._outs = eng.forward(self._sx, False, save=False)
+            self._graph = graph
+        self._graph.replay()
+        return self._outs
