@@ -108,53 +108,37 @@ __device__ __forceinline__ Win make_win(const Geom& g, int win) {
   return w;
 }
 
-// rows = key indices r0..r0+63, `which` = 1 (k) or 2 (v); zero beyond nk / hd
-template <int HDP>
-__device__ __forceinline__ void load_kv(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
-                                        int head, int which, int r0) {
-  constexpr int LD = HDP + 8, CH = HDP / 8;
-  const int C = g.nh * g.hd;
-  for (int e = threadIdx.x; e < BN * CH; e += NT) {
-    const int r = e / CH, c = e - r * CH;
-    const int idx = r0 + r;
-    bf16* d = dst + r * LD + c * 8;
-    if (idx < w.nk && c * 8 < g.hd) {
-      const int col = which * C + head * g.hd + c * 8;
-      if (idx < w.n_real) {
-        const int ty = idx / w.rw, tx = idx - ty * w.rw;
-        tok8_async(d, qkv, bias, g, w.b, w.wy * g.wh + ty, w.wx * g.ww + tx, col);
-      } else {
-        *reinterpret_cast<uint4*>(d) = tok8(qkv, bias, g, w.b, g.H, g.W, col);   // the virtual pad key: bias
-      }
+// one 16-byte chunk (8 head-dim columns starting at c*8) of key `idx` of window w; `which` = 1 (k) or 2 (v)
+__device__ __forceinline__ void put_kv(bf16* d, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
+                                       int head, int which, int idx, int c) {
+  if (idx < w.nk && c * 8 < g.hd) {
+    const int col = which * g.nh * g.hd + head * g.hd + c * 8;
+    if (idx < w.n_real) {
+      const int ty = idx / w.rw, tx = idx - ty * w.rw;
+      tok8_async(d, qkv, bias, g, w.b, w.wy * g.wh + ty, w.wx * g.ww + tx, col);
     } else {
-      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(d) = tok8(qkv, bias, g, w.b, g.H, g.W, col);   // the virtual pad key: bias
     }
+  } else {
+    *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
   }
 }
-
-// rows = real query indices r0..r0+63 of the window (pooled grid when g.pool)
-template <int HDP>
-__device__ __forceinline__ void load_q(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
-                                       int head, int r0) {
-  constexpr int LD = HDP + 8, CH = HDP / 8;
-  for (int e = threadIdx.x; e < BM * CH; e += NT) {
-    const int r = e / CH, c = e - r * CH;
-    const int idx = r0 + r;
-    bf16* d = dst + r * LD + c * 8;
-    if (idx < w.nq && c * 8 < g.hd) {
-      const int py = idx / w.qrw, px = idx - py * w.qrw;
-      const int col = head * g.hd + c * 8;
-      if (!g.pool) {
-        tok8_async(d, qkv, bias, g, w.b, w.wy * g.wh + py, w.wx * g.ww + px, col);
-      } else {
-        const int y = w.wy * g.wh + 2 * py, x = w.wx * g.ww + 2 * px;
-        *reinterpret_cast<uint4*>(d) =
-            max8(max8(tok8(qkv, bias, g, w.b, y, x, col), tok8(qkv, bias, g, w.b, y, x + 1, col)),
-                 max8(tok8(qkv, bias, g, w.b, y + 1, x, col), tok8(qkv, bias, g, w.b, y + 1, x + 1, col)));
-      }
+// chunk c of real query `idx` (2x2 max-pooled when g.pool)
+__device__ __forceinline__ void put_q(bf16* d, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
+                                      int head, int idx, int c) {
+  if (idx < w.nq && c * 8 < g.hd) {
+    const int py = idx / w.qrw, px = idx - py * w.qrw;
+    const int col = head * g.hd + c * 8;
+    if (!g.pool) {
+      tok8_async(d, qkv, bias, g, w.b, w.wy * g.wh + py, w.wx * g.ww + px, col);
     } else {
-      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      const int y = w.wy * g.wh + 2 * py, x = w.wx * g.ww + 2 * px;
+      *reinterpret_cast<uint4*>(d) =
+          max8(max8(tok8(qkv, bias, g, w.b, y, x, col), tok8(qkv, bias, g, w.b, y, x + 1, col)),
+               max8(tok8(qkv, bias, g, w.b, y + 1, x, col), tok8(qkv, bias, g, w.b, y + 1, x + 1, col)));
     }
+  } else {
+    *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -164,19 +148,92 @@ __device__ __forceinline__ long long out_token(const Geom& g, const Win& w, int 
   const int py = idx / w.qrw, px = idx - py * w.qrw;
   return ((long long)w.b * g.Ho + (w.wy * g.qh + py)) * g.Wo + (w.wx * g.qw + px);
 }
+// chunk c of the [B,Ho,Wo,nh*hd] tensor `src` at the output token of query idx (zero beyond nq)
+__device__ __forceinline__ void put_o(bf16* d, const bf16* src, const Geom& g, const Win& w, int head, int idx,
+                                      int c) {
+  const long long tok = out_token(g, w, idx);
+  if (tok >= 0 && c * 8 < g.hd)
+    cp_async16(d, src + tok * (g.nh * g.hd) + head * g.hd + c * 8);
+  else
+    *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+}
 
-// rows = the output tokens of queries r0..r0+63 (zero beyond nq); src is [B,Ho,Wo,nh*hd]
+// 64-row tiles: rows = key / query indices r0..r0+63 of ONE window
+template <int HDP>
+__device__ __forceinline__ void load_kv(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
+                                        int head, int which, int r0) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  for (int e = threadIdx.x; e < BN * CH; e += NT) {
+    const int r = e / CH, c = e - r * CH;
+    put_kv(dst + r * LD + c * 8, qkv, bias, g, w, head, which, r0 + r, c);
+  }
+}
+template <int HDP>
+__device__ __forceinline__ void load_q(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
+                                       int head, int r0) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  for (int e = threadIdx.x; e < BM * CH; e += NT) {
+    const int r = e / CH, c = e - r * CH;
+    put_q(dst + r * LD + c * 8, qkv, bias, g, w, head, r0 + r, c);
+  }
+}
 template <int HDP>
 __device__ __forceinline__ void load_o(bf16* dst, const bf16* src, const Geom& g, const Win& w, int head, int r0) {
   constexpr int LD = HDP + 8, CH = HDP / 8;
   for (int e = threadIdx.x; e < BM * CH; e += NT) {
     const int r = e / CH, c = e - r * CH;
-    const long long tok = out_token(g, w, r0 + r);
-    bf16* d = dst + r * LD + c * 8;
-    if (tok >= 0 && c * 8 < g.hd)
-      cp_async16(d, src + tok * (g.nh * g.hd) + head * g.hd + c * 8);
-    else
-      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+    put_o(dst + r * LD + c * 8, src, g, w, head, r0 + r, c);
+  }
+}
+
+// write this thread's dq fragment rows (query idx, 2 adjacent head-dim columns per 8-column tile j) into the q third
+// of dqkv, routing through the arg-max of the 2x2 q max-pool when g.pool (first maximum in scan order, like ATen)
+template <int NJ>
+__device__ __forceinline__ void scatter_dq(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv,
+                                           const float* __restrict__ bias, const Geom& g, const Win& w, int head,
+                                           int idx, const float (*dq)[4], int half, int lane) {
+  if (idx >= w.nq) return;
+  const int C = g.nh * g.hd;
+  const long long row3 = 3LL * C;
+  const int py = idx / w.qrw, px = idx - py * w.qrw;
+  if (!g.pool) {
+    const int y = w.wy * g.wh + py, x = w.wx * g.ww + px;
+    bf16* dst = dqkv + (((long long)w.b * g.H + y) * g.W + x) * row3 + head * g.hd;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int d = j * 8 + 2 * (lane & 3);
+      if (d < g.hd)
+        *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(dq[j][half * 2], dq[j][half * 2 + 1]);
+    }
+    return;
+  }
+  const int y = w.wy * g.wh + 2 * py, x = w.wx * g.ww + 2 * px;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int d = j * 8 + 2 * (lane & 3) + e;
+      if (d >= g.hd) continue;
+      const int col = head * g.hd + d;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = y + (k >> 1), xx = x + (k & 1);
+        v[k] = (yy < g.H && xx < g.W) ? __bfloat162float(qkv[(((long long)w.b * g.H + yy) * g.W + xx) * row3 + col])
+                                      : __bfloat162float(__float2bfloat16(bias[col]));
+      }
+      int best = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k] > v[best]) best = k;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = y + (k >> 1), xx = x + (k & 1);
+        if (yy < g.H && xx < g.W)
+          dqkv[(((long long)w.b * g.H + yy) * g.W + xx) * row3 + col] =
+              __float2bfloat16(k == best ? dq[j][half * 2 + e] : 0.f);
+      }
+    }
   }
 }
 
@@ -410,53 +467,8 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
     __syncthreads();
   }
   // scatter into the q third of dqkv (argmax routing through the q max-pool)
-  const int C = g.nh * g.hd;
-  const long long row3 = 3LL * C;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int idx = q0 + r0 + half * 8;
-    if (idx >= w.nq) continue;
-    const int py = idx / w.qrw, px = idx - py * w.qrw;
-    if (!g.pool) {
-      const int y = wy * g.wh + py, x = wx * g.ww + px;
-      bf16* dst = dqkv + (((long long)b * g.H + y) * g.W + x) * row3 + head * g.hd;
-#pragma unroll
-      for (int j = 0; j < HDP / 8; ++j) {
-        const int d = j * 8 + 2 * (lane & 3);
-        if (d < g.hd)
-          *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(dq[j][half * 2], dq[j][half * 2 + 1]);
-      }
-    } else {
-      const int y = wy * g.wh + 2 * py, x = wx * g.ww + 2 * px;
-#pragma unroll
-      for (int j = 0; j < HDP / 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int d = j * 8 + 2 * (lane & 3) + e;
-          if (d >= g.hd) continue;
-          const int col = head * g.hd + d;
-          float v[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int yy = y + (k >> 1), xx = x + (k & 1);
-            v[k] = (yy < g.H && xx < g.W) ? __bfloat162float(qkv[(((long long)b * g.H + yy) * g.W + xx) * row3 + col])
-                                          : __bfloat162float(__float2bfloat16(bias[col]));
-          }
-          int best = 0;
-#pragma unroll
-          for (int k = 1; k < 4; ++k)
-            if (v[k] > v[best]) best = k;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int yy = y + (k >> 1), xx = x + (k & 1);
-            if (yy < g.H && xx < g.W)
-              dqkv[(((long long)b * g.H + yy) * g.W + xx) * row3 + col] =
-                  __float2bfloat16(k == best ? dq[j][half * 2 + e] : 0.f);
-          }
-        }
-      }
-    }
-  }
+  scatter_dq<HDP / 8>(dqkv, qkv, bias, g, w, head, q0 + r0, dq, 0, lane);
+  scatter_dq<HDP / 8>(dqkv, qkv, bias, g, w, head, q0 + r0 + 8, dq, 1, lane);
 }
 
 // --------------------------------------------------------------------------------------- backward: dK, dV
@@ -553,6 +565,263 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qk
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Packed variant for tiny windows (window area <= 16 tokens: Hiera stage 2 and its transition block): one CTA serves
+// FOUR windows of one head, warp w <-> window w (a warp's 16 MMA rows are exactly one window's query slot), so the
+// score tile of a window is a single 16x16 MMA block and nothing is wasted on cross-window pairs.  The backward is ONE
+// kernel: with a single key tile the softmax is recomputed from scratch (no lse / D workspace; D_r = sum_j P_rj dP_rj)
+// and P^T / dS^T reach the tensor core through a 16x16 shared-memory transpose per warp.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SLOT = 16, PACK = BM / SLOT;
+
+__device__ __forceinline__ void packed_wins(Win* wins, const Geom& g) {
+  if (threadIdx.x < PACK) {
+    const int id = blockIdx.y * PACK + threadIdx.x;
+    if (id < g.B * g.nwy * g.nwx) {
+      wins[threadIdx.x] = make_win(g, id);
+    } else {
+      Win z;
+      z.b = z.wy = z.wx = 0; z.rh = z.rw = 1; z.n_real = z.n_pad = z.nk = 0; z.qrh = z.qrw = 1; z.nq = 0; z.bonus = 0.f;
+      wins[threadIdx.x] = z;
+    }
+  }
+}
+// kind 0: q, 1: k, 2: v, 3: tensor `src` at the output tokens (dO)
+template <int HDP>
+__device__ __forceinline__ void load_packed(bf16* dst, int kind, const bf16* qkv, const float* bias, const bf16* src,
+                                            const Geom& g, const Win* wins, int head) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  for (int e = threadIdx.x; e < BM * CH; e += NT) {
+    const int r = e / CH, c = e - r * CH;
+    const Win& w = wins[r / SLOT];
+    const int idx = r % SLOT;
+    bf16* d = dst + r * LD + c * 8;
+    if (kind == 0) put_q(d, qkv, bias, g, w, head, idx, c);
+    else if (kind == 3) put_o(d, src, g, w, head, idx, c);
+    else put_kv(d, qkv, bias, g, w, head, kind, idx, c);
+  }
+}
+// acc[2][4] = A(rows 16w..16w+15 of As) . B(rows 16w..16w+15 of Bs)^T       (one 16x16 block)
+template <int HDP>
+__device__ __forceinline__ void mm_16x16(float (*acc)[4], const bf16* As, const bf16* Bs, int warp, int lane) {
+  constexpr int LD = HDP + 8;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[j][t] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HDP / 16; ++kk) {
+    uint32_t a[4], b0, b1, b2, b3;
+    ldsm4(smem_u32(As + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+    ldsm4(smem_u32(Bs + (warp * 16 + (lane & 7) + (lane >> 4) * 8) * LD + kk * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2,
+          b3);
+    mma16816(acc[0], a, b0, b1);
+    mma16816(acc[1], a, b2, b3);
+  }
+}
+// out[j][4] (j over HDP/8) += A(16x16 fragment a[4]) . B(rows 16w..16w+15 of Bs, [16 x HDP])
+template <int HDP>
+__device__ __forceinline__ void mm_16xd(float (*out)[4], const uint32_t* a, const bf16* Bs, int warp, int lane) {
+  constexpr int LD = HDP + 8;
+#pragma unroll
+  for (int dp = 0; dp < HDP / 16; ++dp) {
+    uint32_t b0, b1, b2, b3;
+    ldsm4t(smem_u32(Bs + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + dp * 16 + (lane >> 4) * 8), b0, b1, b2,
+           b3);
+    mma16816(out[2 * dp], a, b0, b1);
+    mma16816(out[2 * dp + 1], a, b2, b3);
+  }
+}
+// masked softmax of a warp's 16x16 score block (raw dot products in s); rows lane/4 and lane/4+8; returns P in s and
+// the per-row (max * scale, sum) needed for the lse
+__device__ __forceinline__ void softmax16(float (*s)[4], const Win& w, float sl2, int lane, float* mx, float* sum) {
+  float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = j * 8 + 2 * (lane & 3) + e;
+      if (c == w.n_real) { s[j][e] += w.bonus; s[j][2 + e] += w.bonus; }
+      if (c >= w.nk) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+    }
+    t0 = fmaxf(t0, fmaxf(s[j][0], s[j][1]));
+    t1 = fmaxf(t1, fmaxf(s[j][2], s[j][3]));
+  }
+  t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+  t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+  t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+  t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+  if (w.nk == 0) { t0 = 0.f; t1 = 0.f; }                     // dead window slot: keep everything finite (p = 0)
+  float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    s[j][0] = ex2((s[j][0] - t0) * sl2);
+    s[j][1] = ex2((s[j][1] - t0) * sl2);
+    s[j][2] = ex2((s[j][2] - t1) * sl2);
+    s[j][3] = ex2((s[j][3] - t1) * sl2);
+    p0 += s[j][0] + s[j][1];
+    p1 += s[j][2] + s[j][3];
+  }
+  p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+  p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+  p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+  p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+  mx[0] = t0; mx[1] = t1; sum[0] = p0; sum[1] = p1;
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(NT) fwd_packed_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                       bf16* __restrict__ out, float* __restrict__ lse, Geom g) {
+  constexpr int LD = HDP + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __shared__ Win wins[PACK];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + BM * LD;
+  bf16* Vs = Ks + BM * LD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, head = blockIdx.z;
+  packed_wins(wins, g);
+  __syncthreads();
+  load_packed<HDP>(Qs, 0, qkv, bias, nullptr, g, wins, head);
+  load_packed<HDP>(Ks, 1, qkv, bias, nullptr, g, wins, head);
+  load_packed<HDP>(Vs, 2, qkv, bias, nullptr, g, wins, head);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const Win w = wins[warp];
+  const float sl2 = g.scale * 1.4426950408889634f;
+  float s[2][4], mx[2], sum[2];
+  mm_16x16<HDP>(s, Qs, Ks, warp, lane);
+  softmax16(s, w, sl2, lane, mx, sum);
+  uint32_t a[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
+                   pack_bf16(s[1][2], s[1][3])};
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[j][t] = 0.f;
+  mm_16xd<HDP>(o, a, Vs, warp, lane);
+  const int C = g.nh * g.hd;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const long long tok = out_token(g, w, (lane >> 2) + half * 8);
+    if (tok < 0) continue;
+    const float inv = 1.f / sum[half];
+    bf16* orow = out + tok * C + head * g.hd;
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j) {
+      const int d = j * 8 + 2 * (lane & 3);
+      if (d < g.hd)
+        *reinterpret_cast<__nv_bfloat162*>(orow + d) =
+            __floats2bfloat162_rn(o[j][half * 2] * inv, o[j][half * 2 + 1] * inv);
+    }
+    if ((lane & 3) == 0) lse[tok * g.nh + head] = mx[half] * g.scale + __logf(sum[half]);
+  }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(NT) bwd_packed_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                       const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+                                                       Geom g) {
+  constexpr int LD = HDP + 8, TP = 24;                         // TP: pitch of the 16x16 transpose tiles (48 B rows)
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __shared__ Win wins[PACK];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + BM * LD;
+  bf16* Vs = Ks + BM * LD;
+  bf16* dOs = Vs + BM * LD;
+  bf16* Ts = dOs + BM * LD;                                    // [4 warps][2 tiles (P, dS)][16][TP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, head = blockIdx.z;
+  packed_wins(wins, g);
+  __syncthreads();
+  load_packed<HDP>(Qs, 0, qkv, bias, nullptr, g, wins, head);
+  load_packed<HDP>(Ks, 1, qkv, bias, nullptr, g, wins, head);
+  load_packed<HDP>(Vs, 2, qkv, bias, nullptr, g, wins, head);
+  load_packed<HDP>(dOs, 3, qkv, bias, dout, g, wins, head);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const Win w = wins[warp];
+  const float sl2 = g.scale * 1.4426950408889634f;
+  float s[2][4], dp[2][4], mx[2], sum[2];
+  mm_16x16<HDP>(s, Qs, Ks, warp, lane);
+  mm_16x16<HDP>(dp, dOs, Vs, warp, lane);
+  softmax16(s, w, sl2, lane, mx, sum);
+  const bool q0ok = (lane >> 2) < w.nq, q1ok = (lane >> 2) + 8 < w.nq;
+  const float i0 = q0ok ? 1.f / sum[0] : 0.f, i1 = q1ok ? 1.f / sum[1] : 0.f;   // cropped queries: P = 0
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    s[j][0] *= i0; s[j][1] *= i0; s[j][2] *= i1; s[j][3] *= i1;
+    d0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
+    d1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
+  }
+  d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+  d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+  d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+  d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+  // P and dS = P o (dP - D) * scale -> bf16 into the per-warp transpose tiles, rows = query, columns = key
+  bf16* Pt = Ts + warp * 2 * 16 * TP;
+  bf16* St = Pt + 16 * TP;
+  float ds[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    ds[j][0] = s[j][0] * (dp[j][0] - d0) * g.scale;
+    ds[j][1] = s[j][1] * (dp[j][1] - d0) * g.scale;
+    ds[j][2] = s[j][2] * (dp[j][2] - d1) * g.scale;
+    ds[j][3] = s[j][3] * (dp[j][3] - d1) * g.scale;
+    const int c = j * 8 + 2 * (lane & 3), r = lane >> 2;
+    *reinterpret_cast<__nv_bfloat162*>(Pt + r * TP + c) = __floats2bfloat162_rn(s[j][0], s[j][1]);
+    *reinterpret_cast<__nv_bfloat162*>(Pt + (r + 8) * TP + c) = __floats2bfloat162_rn(s[j][2], s[j][3]);
+    *reinterpret_cast<__nv_bfloat162*>(St + r * TP + c) = __floats2bfloat162_rn(ds[j][0], ds[j][1]);
+    *reinterpret_cast<__nv_bfloat162*>(St + (r + 8) * TP + c) = __floats2bfloat162_rn(ds[j][2], ds[j][3]);
+  }
+  __syncwarp();
+  // dQ = dS . K
+  {
+    float dq[HDP / 8][4];
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dq[j][t] = 0.f;
+    uint32_t a[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
+                     pack_bf16(ds[1][2], ds[1][3])};
+    mm_16xd<HDP>(dq, a, Ks, warp, lane);
+    scatter_dq<HDP / 8>(dqkv, qkv, bias, g, w, head, lane >> 2, dq, 0, lane);
+    scatter_dq<HDP / 8>(dqkv, qkv, bias, g, w, head, (lane >> 2) + 8, dq, 1, lane);
+  }
+  // dV = P^T . dO, dK = dS^T . Q : A fragments = transposed 16x16 tiles (ldmatrix.trans)
+  float dk[HDP / 8][4], dv[HDP / 8][4];
+#pragma unroll
+  for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { dk[j][t] = 0.f; dv[j][t] = 0.f; }
+  {
+    uint32_t a[4];
+    const int trow = (lane & 7) + (lane >> 4) * 8, tcol = ((lane >> 3) & 1) * 8;
+    ldsm4t(smem_u32(Pt + trow * TP + tcol), a[0], a[1], a[2], a[3]);
+    mm_16xd<HDP>(dv, a, dOs, warp, lane);
+    ldsm4t(smem_u32(St + trow * TP + tcol), a[0], a[1], a[2], a[3]);
+    mm_16xd<HDP>(dk, a, Qs, warp, lane);
+  }
+  const int C = g.nh * g.hd;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int idx = (lane >> 2) + half * 8;
+    if (idx >= w.n_real) continue;                             // only real keys receive gradients
+    const int ty = idx / w.rw, tx = idx - ty * w.rw;
+    bf16* dst = dqkv + (((long long)w.b * g.H + w.wy * g.wh + ty) * g.W + w.wx * g.ww + tx) * (3LL * C) + head * g.hd;
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j) {
+      const int d = j * 8 + 2 * (lane & 3);
+      if (d < g.hd) {
+        *reinterpret_cast<__nv_bfloat162*>(dst + C + d) = __floats2bfloat162_rn(dk[j][half * 2], dk[j][half * 2 + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(dst + 2 * C + d) = __floats2bfloat162_rn(dv[j][half * 2], dv[j][half * 2 + 1]);
+      }
+    }
+  }
+}
+
 static int make_geom(Geom& g, int B, int H, int W, int nh, int hd, int window, int pool) {
   if (B <= 0 || H <= 0 || W <= 0 || nh <= 0 || hd <= 0) return S2U_EINVAL;
   if ((hd & 7) || hd > 96) return S2U_EUNSUPPORTED;
@@ -573,6 +842,14 @@ static int make_geom(Geom& g, int B, int H, int W, int nh, int hd, int window, i
 
 template <int HDP>
 static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse, const Geom& g, cudaStream_t st) {
+  if (g.wh * g.ww <= SLOT) {                                   // tiny windows: 4 per CTA
+    dim3 pgrid(1, ceil_div(g.B * g.nwy * g.nwx, PACK), g.nh);
+    const size_t psmem = (size_t)3 * BM * (HDP + 8) * sizeof(bf16);
+    S2U_ALLOW_SMEM(fwd_packed_kernel<HDP>);
+    fwd_packed_kernel<HDP><<<pgrid, NT, psmem, st>>>(qkv, bias, out, lse, g);
+    S2U_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
   const size_t smem = (size_t)(BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
   S2U_ALLOW_SMEM(fwd_kernel<HDP>);
@@ -584,6 +861,14 @@ static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse,
 template <int HDP>
 static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const float* lse, const bf16* dout,
                       bf16* dqkv, float* Dws, const Geom& g, cudaStream_t st) {
+  if (g.wh * g.ww <= SLOT) {
+    dim3 pgrid(1, ceil_div(g.B * g.nwy * g.nwx, PACK), g.nh);
+    const size_t psmem = (size_t)(4 * BM * (HDP + 8) + 4 * 2 * 16 * 24) * sizeof(bf16);
+    S2U_ALLOW_SMEM(bwd_packed_kernel<HDP>);
+    bwd_packed_kernel<HDP><<<pgrid, NT, psmem, st>>>(qkv, bias, dout, dqkv, g);
+    S2U_LAUNCH_CHECK();
+    return 0;
+  }
   const long long ntok = (long long)g.B * g.Ho * g.Wo;
   bwd_prep_kernel<<<ceil_div(ntok * 32, 256), 256, 0, st>>>(out, dout, Dws, ntok, g.nh, g.hd);
   S2U_LAUNCH_CHECK();

@@ -66,31 +66,38 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
 }
 
 // out[m, (ky*KW+kx)*Cin + ci] = x[b, y + ky*dh - ph, x + kx*dw - pw, ci]  (0 outside the map)
+// One thread = one (pixel, 8-channel group); it walks the taps, so the pixel decomposition is done once and a warp
+// writes full 16-byte-per-lane rows of the output matrix for every tap.
 template <typename T>
-__global__ void im2col_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int B, int H, int W, int Cin,
-                              int KH, int KW, int dh, int dw, int ph, int pw) {
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int B,
+                                                    int H, int W, int Cin, int KH, int KW, int dh, int dw, int ph,
+                                                    int pw) {
   const int C8 = Cin >> 3;
   const int taps = KH * KW;
-  const long long total = (long long)B * H * W * taps * C8;
+  const long long total = (long long)B * H * W * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8);
-    long long t = i / C8;
-    const int tap = (int)(t % taps);
-    const long long m = t / taps;
+    const long long m = i / C8;
     const int xx = (int)(m % W);
     const int yy = (int)((m / W) % H);
-    const int b = (int)(m / ((long long)W * H));
-    const int ky = tap / KW, kx = tap - ky * KW;
-    const int sy = yy + ky * dh - ph, sx = xx + kx * dw - pw;
-    F8 v;
-    if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-      v = ld8(x + (((long long)b * H + sy) * W + sx) * ldx + c * 8);
-    } else {
+    const long long img = (m / ((long long)W * H)) * H;
+    T* orow = out + m * taps * Cin + c * 8;
+    for (int ky = 0; ky < KH; ++ky) {
+      const int sy = yy + ky * dh - ph;
+      const bool yok = sy >= 0 && sy < H;
+      for (int kx = 0; kx < KW; ++kx) {
+        const int sx = xx + kx * dw - pw;
+        F8 v;
+        if (yok && sx >= 0 && sx < W) {
+          v = ld8(x + ((img + sy) * W + sx) * ldx + c * 8);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v.v[j] = 0.f;
+          for (int j = 0; j < 8; ++j) v.v[j] = 0.f;
+        }
+        st8(orow + (ky * KW + kx) * Cin, v);
+      }
     }
-    st8(out + (m * taps + tap) * Cin + c * 8, v);
   }
 }
 
@@ -137,7 +144,7 @@ int s2u_patch_embed(const float* x, const float* w, const float* bias, const flo
 int s2u_im2col(const void* x, int ldx, void* out, int B, int H, int W, int Cin, int KH, int KW, int dil_h, int dil_w,
                int pad_h, int pad_w, int dtype, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin & 7) || (ldx & 7)) return S2U_EINVAL;
-  const long long total = (long long)B * H * W * KH * KW * (Cin / 8);
+  const long long total = (long long)B * H * W * (Cin / 8);
   S2U_DISPATCH_T(dtype, {
     im2col_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, B, H, W, Cin,
                                                                           KH, KW, dil_h, dil_w, pad_h, pad_w);

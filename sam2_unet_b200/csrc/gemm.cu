@@ -1089,8 +1089,8 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
 // out[P] (fp32, accumulated) += column sums of A[M,P]
 int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype, void* stream) {
   if (M <= 0 || P <= 0) return S2U_EINVAL;
-  int blocks_y = (int)((M + 511) / 512);
-  if (blocks_y > 256) blocks_y = 256;
+  int blocks_y = (int)((M + 127) / 128);              // >= 2 waves of small blocks: the pass is pure HBM streaming
+  if (blocks_y > 4096) blocks_y = 4096;
   const int rows = (int)((M + blocks_y - 1) / blocks_y);
   dim3 grid(ceil_div(P, 64), blocks_y);
   S2U_DISPATCH_T(dtype, {

@@ -198,6 +198,8 @@ ATTN_CASES = [  # B, H, W, nh, hd, window, pool
     (2, 16, 16, 2, 72, 8, False), (1, 22, 22, 2, 72, 16, False), (2, 11, 11, 4, 72, 8, False),
     (1, 22, 22, 1, 96, 0, False), (2, 16, 16, 2, 72, 8, True), (1, 22, 22, 2, 72, 16, True),
     (1, 12, 12, 2, 32, 4, True), (2, 10, 10, 1, 32, 6, True), (1, 5, 5, 2, 56, 3, False), (1, 22, 22, 2, 96, 14, False),
+    # tiny windows (packed 4-per-CTA kernels): Hiera-L stage 2, its q-pool transition, ragged window counts
+    (2, 44, 44, 4, 72, 4, False), (1, 44, 44, 8, 72, 4, True), (3, 12, 12, 2, 96, 4, False), (1, 6, 10, 1, 32, 4, False),
 ]
 
 
