@@ -42,9 +42,11 @@ int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype
 /* ---- LayerNorm (hieradet.py:99-100,104,120,134,166; eps 1e-6) ------------------------------------------- */
 int s2u_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                       long long R, int C, float eps, int dtype, void* stream);
-/* dx = LN'(dy) + dres (dres may be NULL); the affine parameters are frozen (SAM2UNet.py:146-147). */
+/* dx = LN'(dy) + dres (dres may be NULL); the affine parameters are frozen (SAM2UNet.py:146-147).
+ * Optional fused adapter tail: dx2 = dx * gelu'(pre), colsum[C] += column sums of dx2 (NULL to skip). */
 int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      const void* dres, void* dx, long long R, int C, int dtype, void* stream);
+                      const void* dres, void* dx, const void* pre, void* dx2, float* colsum, long long R, int C,
+                      int dtype, void* stream);
 
 /* ---- element-wise helpers --------------------------------------------------------------------------------- */
 int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int dtype, void* stream);
@@ -55,6 +57,10 @@ int s2u_maxpool2_bwd(const void* x, const void* dout, void* dx, int B, int H, in
                      void* stream);
 /* fp32 master -> compute-dtype shadow of a [R,C] parameter, optionally transposed. */
 int s2u_cast(const float* src, void* dst, int R, int C, int transpose, int dtype, void* stream);
+/* all shadows in one launch: `entries` = device array of {u64 src, u64 dst0, u64 dst1, i32 kind, i32 d0..d3, i32 pad}
+ * (kind 0: [d0,d1] matrix -> dst0 as is + dst1 transposed; kind 1: conv weight [d0,d1,d2,d3] -> dst0 [Cout][tap][Cin],
+ * dst1 [Cin][flipped tap][Cout]); `blocks` = device array of int2 (entry, 1024-element chunk), one per CUDA block. */
+int s2u_refresh_shadows(const void* entries, const void* blocks, int nblocks, int dtype, void* stream);
 
 /* ---- windowed / global attention (hieradet.py:56-81,141-162; backbones/utils.py:16-55) ------------------ *
  * qkv [B,H,W,3*nh*hd]; window = 0 means global; pool = 1 applies the 2x2 q max-pool inside each window;
@@ -77,7 +83,13 @@ int s2u_conv_weight_pack(const float* w, void* wf, void* wd, int Cout, int Cin, 
                          void* stream);
 
 /* ---- BatchNorm2d, eps 1e-5, momentum 0.1 (SAM2UNet.py:80,85,18,21) ---------------------------------------- */
+/* `sums`: fp64 workspace of 2C accumulators + 1 ticket word, zero on entry, left zero by the finalising kernel.
+ * s2u_bn_stats_finalize = training-mode statistics + finalisation in ONE launch (the last block finalises). */
 int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream);
+int s2u_bn_stats_finalize(const void* x, int ldx, double* sums, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches, float* scale, float* shift,
+                          float* save_mean, float* save_rstd, long long M, int C, float eps, float momentum, int dtype,
+                          void* stream);
 int s2u_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                     long long* num_batches, float* scale, float* shift, float* save_mean, float* save_rstd,
                     long long M, int C, float eps, float momentum, int training, void* stream);

@@ -4,28 +4,87 @@
 // Training mode normalises with the biased batch variance and updates the running statistics with the
 // unbiased one; eval mode uses the running statistics.  Per-channel sums are accumulated in fp64 so the
 // E[x^2]-E[x]^2 form loses nothing against ATen's Welford pass.
+//
+// Launch count matters here (66 layers, most of them tiny): the per-channel finalisation runs inside the reduction
+// kernel, in whichever block finishes last ("threadfence reduction"), so training forward is 2 launches per layer
+// (statistics+finalize, apply) and backward is 2 (reduce+finalize, apply).  The fp64 workspace `sums` holds 2C
+// accumulators followed by one ticket word; it is left zeroed for the next use.
 #include "common.cuh"
 
 constexpr int BN_ROWS = 64;   // rows per block in the reduction kernels
 
-// sums[0..C) += sum x, sums[C..2C) += sum x^2
-template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int ldx, double* __restrict__ sums,
-                                                      long long M, int C) {
-  extern __shared__ float red[];              // [256/cg][2][cg*8]... laid out as [sub][2*C]
-  const int cg = C >> 3;                      // 8-channel groups
-  const int nsub = 256 / cg;                  // row lanes per block
-  const int g = threadIdx.x % cg, sub = threadIdx.x / cg;
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  const long long r0 = (long long)blockIdx.x * BN_ROWS;
-  if (sub < nsub) {
-    for (long long r = r0 + sub; r < min(M, r0 + BN_ROWS); r += nsub) {
-      const F8 v = ld8(x + r * ldx + g * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
+struct BnFin {
+  const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches;
+  float* scale; float* shift; float* save_mean; float* save_rstd; float eps, momentum;
+};
+
+// batch statistics -> (scale, shift) for the apply pass, saved (mean, rstd) for backward, running-stat update;
+// clears the accumulators.  Executed by ONE block (the standalone kernel or the last block of the statistics pass).
+__device__ __forceinline__ void bn_finalize_block(volatile double* sums, const BnFin& f, long long M, int C,
+                                                  int training) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    if (training) {
+      const double m = sums[c] / (double)M;
+      double var = sums[C + c] / (double)M - m * m;
+      if (var < 0) var = 0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)f.eps));
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+      sums[c] = 0.0;
+      sums[C + c] = 0.0;
+    } else {
+      mean = f.running_mean[c];
+      rstd = rsqrtf(f.running_var[c] + f.eps);
     }
+    const float sc = f.gamma[c] * rstd;
+    f.scale[c] = sc;
+    f.shift[c] = f.beta[c] - mean * sc;
+    if (f.save_mean) f.save_mean[c] = mean;
+    if (f.save_rstd) f.save_rstd[c] = rstd;
+  }
+  if (training && f.num_batches && threadIdx.x == 0) *f.num_batches += 1;
+}
+
+__global__ void bn_finalize_kernel(double* __restrict__ sums, BnFin f, long long M, int C, int training) {
+  bn_finalize_block(sums, f, M, C, training);
+}
+
+// dgamma/dbeta accumulate into the parameter gradients; per-channel coefficients for the backward apply pass
+__device__ __forceinline__ void bn_bwd_finalize_block(volatile double* sums, float* dgamma, float* dbeta, float* c1,
+                                                      float* c2, long long M, int C) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sb = sums[c], sg = sums[C + c];
+    dbeta[c] += (float)sb;
+    dgamma[c] += (float)sg;
+    c1[c] = (float)(sb / (double)M);
+    c2[c] = (float)(sg / (double)M);
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
+  }
+}
+
+// "last block done": true in exactly one block of the grid, after every block's atomics are visible to it.
+__device__ __forceinline__ bool last_block(unsigned int* ticket) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
+}
+
+// block-level column reduction of per-thread partials (s, q) into the fp64 accumulators
+__device__ __forceinline__ void reduce_to_sums(float* red, const float* s, const float* q, double* sums, int C,
+                                               int g, int sub, int nsub) {
+  if (sub < nsub) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       red[sub * 2 * C + g * 8 + j] = s[j];
@@ -40,38 +99,27 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
-// one block: batch statistics -> (scale, shift) for the apply pass, saved (mean, rstd) for backward,
-// running-stat update; clears the accumulators for the next use.
-__global__ void bn_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ num_batches,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
-                                   float* __restrict__ save_rstd, long long M, int C, float eps, float momentum,
-                                   int training) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mean, rstd;
-    if (training) {
-      const double m = sums[c] / (double)M;
-      double var = sums[C + c] / (double)M - m * m;
-      if (var < 0) var = 0;
-      mean = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)eps));
-      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-      sums[c] = 0.0;
-      sums[C + c] = 0.0;
-    } else {
-      mean = running_mean[c];
-      rstd = rsqrtf(running_var[c] + eps);
+// sums[0..C) += sum x, sums[C..2C) += sum x^2 ; optionally finalises in the last block
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int ldx, double* __restrict__ sums,
+                                                      long long M, int C, int fuse_finalize, BnFin fin) {
+  extern __shared__ float red[];              // [row lanes][2*C]
+  const int cg = C >> 3;                      // 8-channel groups
+  const int nsub = 256 / cg;                  // row lanes per block
+  const int g = threadIdx.x % cg, sub = threadIdx.x / cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const long long r0 = (long long)blockIdx.x * BN_ROWS;
+  if (sub < nsub) {
+    for (long long r = r0 + sub; r < min(M, r0 + BN_ROWS); r += nsub) {
+      const F8 v = ld8(x + r * ldx + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
     }
-    const float sc = gamma[c] * rstd;
-    scale[c] = sc;
-    shift[c] = beta[c] - mean * sc;
-    if (save_mean) save_mean[c] = mean;
-    if (save_rstd) save_rstd[c] = rstd;
   }
-  if (training && num_batches && threadIdx.x == 0) *num_batches += 1;
+  reduce_to_sums(red, s, q, sums, C, g, sub, nsub);
+  if (fuse_finalize && last_block(reinterpret_cast<unsigned int*>(sums + 2 * C))) bn_finalize_block(sums, fin, M, C, 1);
 }
 
 // out = act(x * scale + shift (+ resid)); out may be a channel slice of a wider (concat) buffer via ld_out
@@ -120,14 +168,16 @@ __global__ void relu_bwd_kernel(const T* __restrict__ dy, int ld_dy, const T* __
   }
 }
 
-// sums[0..C) += sum g, sums[C..2C) += sum g * xhat, with g = dy * (y > 0 if y given)
+// sums[0..C) += sum g, sums[C..2C) += sum g * xhat, with g = dy * (y > 0 if y given); finalises in the last block
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ dy, int ld_dy,
                                                            const T* __restrict__ y, int ld_y,
                                                            const T* __restrict__ x, int ldx,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ rstd,
-                                                           double* __restrict__ sums, long long M, int C) {
+                                                           double* __restrict__ sums, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, float* __restrict__ c1,
+                                                           float* __restrict__ c2, long long M, int C) {
   extern __shared__ float red[];
   const int cg = C >> 3;
   const int nsub = 256 / cg;
@@ -152,33 +202,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
         q[j] = fmaf(d.v[j], (v.v[j] - mu.v[j]) * rs.v[j], q[j]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      red[sub * 2 * C + g * 8 + j] = s[j];
-      red[sub * 2 * C + C + g * 8 + j] = q[j];
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += 256) {
-    float t = 0.f;
-    for (int k = 0; k < nsub; ++k) t += red[k * 2 * C + i];
-    atomicAdd(sums + i, (double)t);
-  }
-}
-
-// one block: dgamma/dbeta accumulate into the parameter gradients; per-channel coefficients for the apply pass
-__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2,
-                                       long long M, int C) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double sb = sums[c], sg = sums[C + c];
-    dbeta[c] += (float)sb;
-    dgamma[c] += (float)sg;
-    c1[c] = (float)(sb / (double)M);
-    c2[c] = (float)(sg / (double)M);
-    sums[c] = 0.0;
-    sums[C + c] = 0.0;
-  }
+  reduce_to_sums(red, s, q, sums, C, g, sub, nsub);
+  if (last_block(reinterpret_cast<unsigned int*>(sums + 2 * C))) bn_bwd_finalize_block(sums, dgamma, dbeta, c1, c2, M, C);
 }
 
 // dx = gamma * rstd * (g - c1 - xhat * c2)
@@ -223,13 +249,33 @@ static inline bool bn_c_ok(int C) { return C >= 8 && (C & 7) == 0 && (C >> 3) <=
 
 extern "C" {
 
+// statistics only (the caller finalises with s2u_bn_finalize)
 int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream) {
   if (M <= 0 || !bn_c_ok(C) || (ldx & 7)) return S2U_EINVAL;
   const int nsub = 256 / (C >> 3);
   const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
+  BnFin none{};
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_stats_kernel<T>);
-    bn_stats_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C);
+    bn_stats_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 0, none);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+// training forward in ONE launch: statistics + (last block) scale/shift, saved mean/rstd, running-stat update.
+// `sums` must hold 2C+1 doubles (accumulators + ticket), zero on entry; it is zero again on exit.
+int s2u_bn_stats_finalize(const void* x, int ldx, double* sums, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches, float* scale, float* shift,
+                          float* save_mean, float* save_rstd, long long M, int C, float eps, float momentum, int dtype,
+                          void* stream) {
+  if (M <= 0 || !bn_c_ok(C) || (ldx & 7)) return S2U_EINVAL;
+  const int nsub = 256 / (C >> 3);
+  const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
+  BnFin f{gamma, beta, running_mean, running_var, num_batches, scale, shift, save_mean, save_rstd, eps, momentum};
+  S2U_DISPATCH_T(dtype, {
+    S2U_ALLOW_SMEM(bn_stats_kernel<T>);
+    bn_stats_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 1, f);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -239,9 +285,8 @@ int s2u_bn_finalize(double* sums, const float* gamma, const float* beta, float* 
                     long long* num_batches, float* scale, float* shift, float* save_mean, float* save_rstd,
                     long long M, int C, float eps, float momentum, int training, void* stream) {
   if (C <= 0) return S2U_EINVAL;
-  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, gamma, beta, running_mean, running_var, num_batches,
-                                                         scale, shift, save_mean, save_rstd, M, C, eps, momentum,
-                                                         training);
+  BnFin f{gamma, beta, running_mean, running_var, num_batches, scale, shift, save_mean, save_rstd, eps, momentum};
+  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, f, M, C, training);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -268,7 +313,8 @@ int s2u_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, void* g, in
   return 0;
 }
 
-// y == null: plain BN backward; y given: backward through relu(bn(x)) using the saved output for the mask
+// y == null: plain BN backward; y given: backward through relu(bn(x)) using the saved output for the mask.
+// `sums`: 2C+1 doubles, zero on entry and on exit.
 int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x, int ldx, const float* mean,
                const float* rstd, const float* gamma, double* sums, float* dgamma, float* dbeta, float* c1, float* c2,
                void* dx, int ld_dx, long long M, int C, int dtype, void* stream) {
@@ -279,10 +325,9 @@ int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_bwd_reduce_kernel<T>);
     bn_bwd_reduce_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
-                                                                    (const T*)x, ldx, mean, rstd, sums, M, C);
+                                                                    (const T*)x, ldx, mean, rstd, sums, dgamma, dbeta,
+                                                                    c1, c2, M, C);
   })
-  S2U_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<1, 256, 0, st>>>(sums, dgamma, dbeta, c1, c2, M, C);
   S2U_LAUNCH_CHECK();
   S2U_DISPATCH_T(dtype, {
     bn_bwd_apply_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,

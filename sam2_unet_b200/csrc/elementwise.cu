@@ -109,6 +109,48 @@ __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, 
   }
 }
 
+// One launch refreshes every low-precision operand of the trainable weights from the fp32 masters (192 adapter
+// casts/transposes + 66 conv re-layouts per step otherwise).  `blocks[b]` = (entry, chunk): block b converts elements
+// [chunk*1024, chunk*1024+1024) of entry `entry`.
+struct S2uRefreshEntry {
+  unsigned long long src, dst0, dst1;   // fp32 master; compute-dtype outputs (0 = skip)
+  int kind;                             // 0: [d0, d1] matrix -> dst0 (same layout) and dst1 (transposed)
+  int d0, d1, d2, d3;                   // 1: conv weight [Cout=d0][Cin=d1][KH=d2][KW=d3] -> dst0 [Cout][tap][Cin],
+  int pad;                              //    dst1 [Cin][flipped tap][Cout]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) refresh_kernel(const S2uRefreshEntry* __restrict__ entries,
+                                                     const int2* __restrict__ blocks) {
+  const int2 bk = blocks[blockIdx.x];
+  const S2uRefreshEntry e = entries[bk.x];
+  const float* src = reinterpret_cast<const float*>(e.src);
+  T* dst0 = reinterpret_cast<T*>(e.dst0);
+  T* dst1 = reinterpret_cast<T*>(e.dst1);
+  const long long total = e.kind == 0 ? (long long)e.d0 * e.d1 : (long long)e.d0 * e.d1 * e.d2 * e.d3;
+  const long long base = (long long)bk.y * 1024;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i >= total) break;
+    const float v = src[i];
+    if (e.kind == 0) {
+      if (dst0) stf(dst0 + i, v);
+      if (dst1) {
+        const int r = (int)(i / e.d1), c = (int)(i % e.d1);
+        stf(dst1 + (long long)c * e.d0 + r, v);
+      }
+    } else {
+      const int taps = e.d2 * e.d3;
+      const int tap = (int)(i % taps);
+      const int ci = (int)((i / taps) % e.d1);
+      const int co = (int)(i / ((long long)taps * e.d1));
+      if (dst0) stf(dst0 + ((long long)co * taps + tap) * e.d1 + ci, v);
+      if (dst1) stf(dst1 + ((long long)ci * taps + (taps - 1 - tap)) * e.d0 + co, v);
+    }
+  }
+}
+
 static inline int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   if (g > 148LL * 16) g = 148LL * 16;
@@ -153,6 +195,15 @@ int s2u_maxpool2_bwd(const void* x, const void* dout, void* dx, int B, int H, in
   S2U_DISPATCH_T(dtype, {
     maxpool2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dout,
                                                                                 (T*)dx, B, H, W, C);
+  })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+int s2u_refresh_shadows(const void* entries, const void* blocks, int nblocks, int dtype, void* stream) {
+  if (nblocks <= 0 || !entries || !blocks) return S2U_EINVAL;
+  S2U_DISPATCH_T(dtype, {
+    refresh_kernel<T><<<nblocks, 256, 0, (cudaStream_t)stream>>>((const S2uRefreshEntry*)entries, (const int2*)blocks);
   })
   S2U_LAUNCH_CHECK();
   return 0;

@@ -80,9 +80,10 @@ class Ops:
         _lib.call("s2u_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
                   _ptr(rstd), R, C, 1e-6, self.dt, self.stream)
 
-    def ln_bwd(self, dy, x, gamma, mean, rstd, dres, dx, R, C):
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dres, dx, R, C, pre=None, dx2=None, colsum=None):
         _lib.call("s2u_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), R, C, self.dt, self.stream)
+                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(pre), _ptr(dx2), _ptr(colsum), R, C, self.dt,
+                  self.stream)
 
     def dgelu_mul(self, dy, pre, out):
         _lib.call("s2u_dgelu_mul", dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), self.dt, self.stream)
@@ -122,6 +123,11 @@ class Ops:
 
     def bn_stats(self, x, ldx, sums, M, C):
         _lib.call("s2u_bn_stats", x.data_ptr(), ldx, sums.data_ptr(), M, C, self.dt, self.stream)
+
+    def bn_stats_finalize(self, x, ldx, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, rstd, M, C):
+        _lib.call("s2u_bn_stats_finalize", x.data_ptr(), ldx, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  rm.data_ptr(), rv.data_ptr(), _ptr(nbt), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                  rstd.data_ptr(), M, C, 1e-5, 0.1, self.dt, self.stream)
 
     def bn_finalize(self, sums, gamma, beta, rm, rv, nbt, scale, shift, mean, rstd, M, C, training):
         _lib.call("s2u_bn_finalize", sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
@@ -199,6 +205,7 @@ class Engine:
         self.tape: Optional[dict] = None
         self._prepare_frozen()
         self._shadow_version = -1
+        self._refresh = None
 
     # ------------------------------------------------------------------------------------------ weights
 
@@ -232,36 +239,50 @@ class Engine:
         return self._pos_cache[hp]
 
     def refresh_shadows(self):
-        """Compute-dtype operands of the TRAINABLE weights, rebuilt from the fp32 masters after every update."""
+        """Compute-dtype operands of the TRAINABLE weights, rebuilt from the fp32 masters after every update by ONE
+        kernel launch driven by a device-resident table (built on first use)."""
         flat = self.model.flat
         if self._shadow_version == flat.version:
             return
-        ops, sh, T = self.ops, self._shadow, self.T
-        P = flat.views
-        for i, spec in enumerate(self.cfg.blocks):
-            p = f"encoder.blocks.{i}.prompt_learn."
-            C = spec.dim
-            for nm, (r, c) in (("0", (32, C)), ("2", (C, 32))):
-                key = p + nm
-                if key + ".w" not in sh:
-                    sh[key + ".w"] = ops.empty(r, c)
-                    sh[key + ".wt"] = ops.empty(c, r)
-                ops.cast(P[key + ".weight"], sh[key + ".w"], r, c, False)
-                ops.cast(P[key + ".weight"], sh[key + ".wt"], r, c, True)
-        for cs in self.model.conv_units:
-            key = cs.name
-            taps = cs.kh * cs.kw
-            if key + ".wf" not in sh:
-                sh[key + ".wf"] = ops.empty(64, taps * cs.cin)
-                sh[key + ".wd"] = ops.empty(cs.cin, taps * 64)
-            ops.conv_weight_pack(P[key + ".weight"], sh[key + ".wf"], sh[key + ".wd"], 64, cs.cin, cs.kh, cs.kw)
+        ops, sh = self.ops, self._shadow
+        if self._refresh is None:
+            import numpy as np
+            P = flat.views
+            ent = []
+            for i, spec in enumerate(self.cfg.blocks):
+                p = f"encoder.blocks.{i}.prompt_learn."
+                C = spec.dim
+                for nm, (r, c) in (("0", (32, C)), ("2", (C, 32))):
+                    key = p + nm
+                    sh[key + ".w"], sh[key + ".wt"] = ops.empty(r, c), ops.empty(c, r)
+                    ent.append((P[key + ".weight"].data_ptr(), sh[key + ".w"].data_ptr(), sh[key + ".wt"].data_ptr(), 0,
+                                r, c, 0, 0, r * c))
+            for cs in self.model.conv_units:
+                key, taps = cs.name, cs.kh * cs.kw
+                sh[key + ".wf"], sh[key + ".wd"] = ops.empty(64, taps * cs.cin), ops.empty(cs.cin, taps * 64)
+                ent.append((P[key + ".weight"].data_ptr(), sh[key + ".wf"].data_ptr(), sh[key + ".wd"].data_ptr(), 1, 64,
+                            cs.cin, cs.kh, cs.kw, 64 * cs.cin * taps))
+            rec = np.zeros(len(ent), dtype=np.dtype([("src", "<u8"), ("d0p", "<u8"), ("d1p", "<u8"), ("kind", "<i4"),
+                                                     ("d0", "<i4"), ("d1", "<i4"), ("d2", "<i4"), ("d3", "<i4"),
+                                                     ("pad", "<i4")]))
+            blocks = []
+            for j, (src, d0p, d1p, kind, d0, d1, d2, d3, n) in enumerate(ent):
+                rec[j] = (src, d0p, d1p, kind, d0, d1, d2, d3, 0)
+                blocks += [(j, ch) for ch in range((n + 1023) // 1024)]
+            entries = torch.from_numpy(rec.view(np.uint8).copy()).to(self.device)
+            blk = torch.tensor(blocks, dtype=torch.int32).to(self.device)
+            self._refresh = (entries, blk, len(blocks), flat.master.data_ptr())
+        entries, blk, nblk, base = self._refresh
+        if base != flat.master.data_ptr():
+            raise RuntimeError("flat parameter buffer moved; the engine must be rebuilt")
+        _lib.call("s2u_refresh_shadows", entries.data_ptr(), blk.data_ptr(), nblk, ops.dt, ops.stream)
         self._shadow_version = flat.version
 
     def _bn_workspace(self, key: str, C: int) -> Dict[str, torch.Tensor]:
         ws = self._bn_ws.get(key)
         if ws is None:
             dev = self.device
-            ws = dict(sums=torch.zeros(2 * C, dtype=torch.float64, device=dev),
+            ws = dict(sums=torch.zeros(2 * C + 1, dtype=torch.float64, device=dev),
                       scale=torch.empty(C, dtype=torch.float32, device=dev),
                       shift=torch.empty(C, dtype=torch.float32, device=dev),
                       c1=torch.empty(C, dtype=torch.float32, device=dev),
@@ -371,11 +392,14 @@ class Engine:
         ws = self._bn_workspace(cs.bn, 64)
         mean = rstd = None
         if training:
-            ops.bn_stats(raw, 64, ws["sums"], M, 64)
             mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
-        ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
-                        Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"], mean,
-                        rstd, M, 64, training)
+            ops.bn_stats_finalize(raw, 64, ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"],
+                                  Bf[cs.bn + ".running_mean"], Bf[cs.bn + ".running_var"],
+                                  Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"], mean, rstd, M, 64)
+        else:
+            ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
+                            Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
+                            None, None, M, 64, False)
         out_ptr = out.data_ptr() + out_off * esz
         ops.bn_apply(raw, 64, ws["scale"], ws["shift"], resid, ld_res, out_ptr, ld_out, M, 64, relu)
         if tape is not None:
@@ -515,13 +539,12 @@ class Engine:
             ops.maxpool_bwd(tp["pr"], dy, dpr, B, H, W, C2)
             ops.gemm(dpr, fz[p + "proj.wt"], dn1, resid=dn1, flags=RESID)
             dres = None
-        dxa = ops.empty(R, C)
-        ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C)
-        # adapter backward: xa = x + gelu(h2), h2 = u W2^T + b2, u = gelu(h1), h1 = x W1^T + b1
-        dh2 = dn1                                       # reuse [R, C]
-        ops.dgelu_mul(dxa, tp["h2"], dh2)
+        # LN1 backward fused with the head of the adapter backward (xa = x + gelu(h2), h2 = u W2^T + b2,
+        # u = gelu(h1), h1 = x W1^T + b1): dxa, dh2 = dxa * gelu'(h2) and db2 = colsum(dh2) in one pass
+        dxa, dh2 = ops.empty(R, C), ops.empty(R, C)
+        ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C, pre=tp["h2"], dx2=dh2,
+                   colsum=G[a + "2.bias"])
         ops.wgrad(dh2, tp["u"], G[a + "2.weight"], ldg=32)              # [C, 32]
-        ops.colsum(dh2, G[a + "2.bias"])
         dh1 = ops.empty(R, 32)
         ops.gemm(dh2, sh[a + "2.wt"], dh1, aux=tp["h1"], flags=DGELU)   # (dh2 W2) * gelu'(h1)
         ops.wgrad(dh1, tp["x"], G[a + "0.weight"], ldg=C)               # [32, C]

@@ -141,6 +141,15 @@ def test_layernorm(cuda, dtype, C):
     ops.ln_bwd(dy, x, g, mean, rstd, dres, dx, R, C)
     (gx,) = torch.autograd.grad(ref, xr, dy.float())
     _close(dx, gx + dres.float(), _tol(dtype), "ln bwd")
+    # fused adapter tail: dx2 = dx * gelu'(pre), colsum += column sums of dx2
+    pre = _rand((R, C), dtype, cuda, 6)
+    dx_b, dx2, cs = ops.empty(R, C), ops.empty(R, C), torch.zeros(C, device=cuda)
+    ops.ln_bwd(dy, x, g, mean, rstd, dres, dx_b, R, C, pre=pre, dx2=dx2, colsum=cs)
+    assert torch.equal(dx_b, dx)
+    pr = pre.float().requires_grad_(True)
+    (dg,) = torch.autograd.grad(F.gelu(pr).sum(), pr)
+    _close(dx2, dx.float() * dg, _tol(dtype, 1e-5), "ln bwd fused gelu'")
+    _close(cs, dx2.float().sum(0), 1e-4, "ln bwd fused colsum")
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
@@ -286,10 +295,13 @@ def test_batchnorm(cuda, dtype, relu):
     g, b = _rand((C,), "fp32", cuda, 2) * 0.1 + 1, _rand((C,), "fp32", cuda, 3) * 0.1
     rm, rv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
     nbt = torch.zeros((), dtype=torch.long, device=cuda)
-    sums = torch.zeros(2 * C, dtype=torch.float64, device=cuda)
+    sums = torch.zeros(2 * C + 1, dtype=torch.float64, device=cuda)
     scale, shift, mean, rstd = (torch.empty(C, device=cuda) for _ in range(4))
-    ops.bn_stats(x, C, sums, M, C)
-    ops.bn_finalize(sums, g, b, rm, rv, nbt, scale, shift, mean, rstd, M, C, True)
+    if relu:                                              # both forms of the training forward
+        ops.bn_stats(x, C, sums, M, C)
+        ops.bn_finalize(sums, g, b, rm, rv, nbt, scale, shift, mean, rstd, M, C, True)
+    else:
+        ops.bn_stats_finalize(x, C, sums, g, b, rm, rv, nbt, scale, shift, mean, rstd, M, C)
     y = ops.empty(M, C)
     ops.bn_apply(x, C, scale, shift, None, 0, y, C, M, C, relu)
     xr = x.float().requires_grad_(True)

@@ -245,3 +245,49 @@ def test_single_block_forward_backward(cuda, blk, dtype):
     assert _maxnorm(dx.view(B, H, H, -1), grads[0]) <= tol_b, "dx"
     for k, gr in zip(keys, grads[1:]):
         assert _maxnorm(m.flat.grad_views[k], gr) <= tol_b, k
+
+
+def test_bf16_mask_criteria_after_prefit(cuda):
+    """North-star bf16 criteria (sigmoid max-abs <= 2e-2, IoU of binarised masks >= 0.999) against the fp32 oracle.
+
+    At random init the logits hover around 0 and ANY bf16 path — PyTorch's own autocast included — flips thousands of
+    mask pixels, so the criterion is evaluated after a short pre-fit on mask-correlated
+    synthetic images: 40 fp32 TrainStep updates of Hiera-T (352x352, 8 images; out1 is a x16 upsampling of a 22x22
+    map, so one low-resolution logit changing sign moves 256 pixels: fewer images make the IoU estimate too coarse), then the SAME fitted weights run
+    through the oracle port (CPU, fp32) and through the bf16 CUDA path, in eval and in train mode."""
+    from oracle import port
+    from sam2_unet_b200 import SAM2UNet, TrainStep
+    from sam2_unet_b200.params import fill_deterministic_
+    x, mask = port.synthetic_batch(8, 352, seed=11, correlated=True)
+    m32 = SAM2UNet(model_cfg="sam2_hiera_t.yaml", dtype="fp32")
+    fill_deterministic_(m32, 0)
+    m32 = m32.to(cuda)
+    step = TrainStep(m32, lr=1e-3, weight_decay=5e-4, use_graph=False)
+    first = last = None
+    for i in range(40):
+        loss = step(x.to(cuda), mask.to(cuda))
+        if i == 0:
+            first = loss.sum().item()
+    last = loss.sum().item()
+    assert last < 0.6 * first, (first, last)
+    sd = {k: v.detach().cpu().clone() for k, v in m32.state_dict().items()}
+    mb = SAM2UNet(model_cfg="sam2_hiera_t.yaml", dtype="bf16").to(cuda)
+    mb.load_state_dict(sd, strict=True)
+    report = {}
+    for train in (False, True):
+        mb.train(train)
+        with torch.no_grad():
+            got = mb(x.to(cuda))
+            ref = port.forward(sd, port.TRUNKS["t"], x, train)
+        if train:
+            mb.load_state_dict(sd, strict=True)           # undo the running-stat update of the train-mode forward
+        for g, r, name in zip(got, ref, ("out", "out1", "out2")):
+            sg, sr = torch.sigmoid(g.float().cpu()), torch.sigmoid(r)
+            pg, pr = sg > 0.5, sr > 0.5
+            iou = ((pg & pr).sum().item() + 1e-9) / ((pg | pr).sum().item() + 1e-9)
+            report[(train, name)] = ((sg - sr).abs().max().item(), iou, pr.float().mean().item())
+    print(report)
+    for (train, name), (err, iou, frac) in report.items():
+        assert 0.02 < frac < 0.98, ("degenerate masks", train, name, frac)
+        assert err <= 2e-2, (train, name, err)
+        assert iou >= 0.999, (train, name, iou)
