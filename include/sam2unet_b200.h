@@ -27,7 +27,8 @@ extern "C" {
  * C[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear forward (sam2/modeling/backbones/hieradet.py:59,79,
  * sam2/modeling/sam2_utils.py:127-132, SAM2UNet.py:57-63), its input gradient (W = pre-transposed weight), and
  * conv forward / input gradient on im2col rows (SAM2UNet.py:83-86).  epi(v): v += bias[n]; pre_out = v;
- * flags&1: v = gelu(v); flags&2: v *= gelu'(aux); flags&4: v += resid.
+ * flags&1: v = gelu(v); flags&2: v *= gelu'(aux); flags&4: v += resid; flags&16: C is fp32; flags&32: resid is
+ * fp32; flags&64: pre_out receives the FINAL value (compute-dtype copy of C) instead of the pre-activation one.
  * backend: 0 auto (tcgen05 + TMA for bf16), 1 SIMT fp32-FMA, 2 tcgen05 required, 16+bn tcgen05 with N tile bn. */
 int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
              const float* bias, void* pre_out, int ld_pre, const void* aux, int ld_aux, const void* resid,
@@ -40,13 +41,14 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
 int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype, void* stream);
 
 /* ---- LayerNorm (hieradet.py:99-100,104,120,134,166; eps 1e-6) ------------------------------------------- */
+/* x_f32 != 0: x (the residual stream) is fp32 even when dtype selects bf16 for y / dy / dx. */
 int s2u_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                      long long R, int C, float eps, int dtype, void* stream);
+                      long long R, int C, float eps, int x_f32, int dtype, void* stream);
 /* dx = LN'(dy) + dres (dres may be NULL); the affine parameters are frozen (SAM2UNet.py:146-147).
  * Optional fused adapter tail: dx2 = dx * gelu'(pre), colsum[C] += column sums of dx2 (NULL to skip). */
 int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                       const void* dres, void* dx, const void* pre, void* dx2, float* colsum, long long R, int C,
-                      int dtype, void* stream);
+                      int x_f32, int dtype, void* stream);
 
 /* ---- element-wise helpers --------------------------------------------------------------------------------- */
 int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int dtype, void* stream);
@@ -74,8 +76,9 @@ int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const 
 
 /* ---- stem and convolutions -------------------------------------------------------------------------------- *
  * 7x7/s4/p3 conv 3->E + bias + position-embedding table (backbones/utils.py:80-88, hieradet.py:268-283). */
-int s2u_patch_embed(const float* x, const float* w, const float* bias, const float* pos, void* out, int B, int S,
-                    int E, int dtype, void* stream);
+/* out: fp32 when out_f32 else the compute dtype; out_copy (optional): compute-dtype copy of the same tokens. */
+int s2u_patch_embed(const float* x, const float* w, const float* bias, const float* pos, void* out, int out_f32,
+                    void* out_copy, int B, int S, int E, int dtype, void* stream);
 /* taps of a stride-1 conv gathered to [B*H*W, KH*KW*Cin] (SAM2UNet.py:68-125,9-26). */
 int s2u_im2col(const void* x, int ldx, void* out, int B, int H, int W, int Cin, int KH, int KW, int dil_h, int dil_w,
                int pad_h, int pad_w, int dtype, void* stream);

@@ -104,7 +104,11 @@ __device__ __forceinline__ void st8(bf16* p, const F8& r) {
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // GEMM epilogue description shared by the SIMT and the tcgen05 GEMM (see gemm.cu)
-enum GemmFlags { GEMM_GELU = 1, GEMM_DGELU = 2, GEMM_RESID = 4, GEMM_ROWAFFINE = 8 };
+// GEMM_OUT_F32 / GEMM_RESID_F32: C / resid are fp32 although the operands are bf16 (the residual stream of the trunk is
+// kept in fp32 in bf16 mode); GEMM_PRE_FINAL: pre_out receives the FINAL value (a compute-dtype copy of C) instead of
+// the pre-activation one.
+enum GemmFlags { GEMM_GELU = 1, GEMM_DGELU = 2, GEMM_RESID = 4, GEMM_OUT_F32 = 16, GEMM_RESID_F32 = 32,
+                 GEMM_PRE_FINAL = 64 };
 struct GemmEpi {
   const float* bias;   // [N] or null
   void* pre_out;       // T [M, ld_pre]: value before the activation (saved for GELU'), or null

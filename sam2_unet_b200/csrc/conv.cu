@@ -11,11 +11,12 @@
 //    forward operand [Cout][(ky,kx,ci)] and flipped/transposed input-gradient operand [Cin][(ky,kx,co)].
 #include "common.cuh"
 
+// out: fp32 tokens (the residual stream) when out_f32, else T; out_copy (optional): the same values in T
 template <typename T>
 __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
-                                                         const float* __restrict__ pos, T* __restrict__ out, int B,
-                                                         int S, int E) {
+                                                         const float* __restrict__ pos, void* __restrict__ out,
+                                                         int out_f32, T* __restrict__ out_copy, int B, int S, int E) {
   extern __shared__ float sm[];
   float* wT = sm;                 // [147][E]
   float* patch = sm + 147 * E;    // [3][35][36]
@@ -60,7 +61,11 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
       const int ox = ox0 + t;
       if (ox >= Hp) continue;
       const long long o = ((long long)oy * Hp + ox) * E + c;
-      stf(out + (long long)b * Hp * Hp * E + o, acc[t] + bias[c] + pos[o]);
+      const long long go = (long long)b * Hp * Hp * E + o;
+      const float val = acc[t] + bias[c] + pos[o];
+      if (out_f32) reinterpret_cast<float*>(out)[go] = val;
+      else stf(reinterpret_cast<T*>(out) + go, val);
+      if (out_copy) stf(out_copy + go, val);
     }
   }
 }
@@ -126,8 +131,8 @@ static inline int grid_for(long long n, int threads) {
 
 extern "C" {
 
-int s2u_patch_embed(const float* x, const float* w, const float* bias, const float* pos, void* out, int B, int S,
-                    int E, int dtype, void* stream) {
+int s2u_patch_embed(const float* x, const float* w, const float* bias, const float* pos, void* out, int out_f32,
+                    void* out_copy, int B, int S, int E, int dtype, void* stream) {
   if (B <= 0 || S <= 0 || (S % 4) || E <= 0) return S2U_EINVAL;
   const int Hp = S / 4;
   const size_t smem = (size_t)(147 * E + 3 * 35 * 36) * sizeof(float);
@@ -135,7 +140,8 @@ int s2u_patch_embed(const float* x, const float* w, const float* bias, const flo
   dim3 grid(((Hp + 7) / 8) * ((Hp + 7) / 8), B);
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(patch_embed_kernel<T>);
-    patch_embed_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, pos, (T*)out, B, S, E);
+    patch_embed_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, pos, out, out_f32, (T*)out_copy, B, S,
+                                                                     E);
   })
   S2U_LAUNCH_CHECK();
   return 0;

@@ -34,11 +34,20 @@ struct EpiView {
 template <typename T>
 __device__ __forceinline__ float epi_scalar(const EpiView<T>& e, float v, long long row, int col) {
   if (e.bias) v += e.bias[col];
-  if (e.pre_out) stf(e.pre_out + row * e.ld_pre + col, v);
+  if (e.pre_out && !(e.flags & GEMM_PRE_FINAL)) stf(e.pre_out + row * e.ld_pre + col, v);
   if (e.flags & GEMM_GELU) v = gelu_f(v);
   if (e.flags & GEMM_DGELU) v *= dgelu_f(ldf(e.aux + row * e.ld_aux + col));
-  if (e.flags & GEMM_RESID) v += ldf(e.resid + row * e.ld_res + col);
+  if (e.flags & GEMM_RESID) {
+    if (e.flags & GEMM_RESID_F32) v += reinterpret_cast<const float*>(e.resid)[row * e.ld_res + col];
+    else v += ldf(e.resid + row * e.ld_res + col);
+  }
+  if (e.pre_out && (e.flags & GEMM_PRE_FINAL)) stf(e.pre_out + row * e.ld_pre + col, v);
   return v;
+}
+template <typename T>
+__device__ __forceinline__ void epi_store(const EpiView<T>& e, T* C, int ldc, float v, long long row, int col) {
+  if (e.flags & GEMM_OUT_F32) reinterpret_cast<float*>(C)[row * ldc + col] = v;
+  else stf(C + row * ldc + col, v);
 }
 
 // ----------------------------------------------------------------------------------------- SIMT GEMM
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + tx * 4 + j;
       if (col >= N) continue;
-      stf(C + row * ldc + col, epi_scalar(epi, acc[i][j], row, col));
+      epi_store(epi, C, ldc, epi_scalar(epi, acc[i][j], row, col), row, col);
     }
   }
 }
@@ -485,7 +494,9 @@ __device__ __forceinline__ void regs_to_stage(uint32_t stg, int lane, const floa
   }
 }
 
-template <int BN, int STAGES>
+// F32S = true: "stream" epilogue (fp32 output and/or fp32 residual and/or a compute-dtype copy of the final value, no
+// GELU'); false: everything in the compute dtype.  Two instantiations keep each epilogue's register footprint small.
+template <int BN, int STAGES, bool F32S>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                    const __grid_constant__ CUtensorMap tma_b,
                                                                    bf16* __restrict__ C, int ldc, int M, int N, int K,
@@ -575,26 +586,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     }
   } else {
     // ---- 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware restriction of tcgen05.ld); the two warps of a
-    //      quarter take alternate 32-column chunks.  The side input of the epilogue (GELU' argument or residual) is
-    //      prefetched one chunk ahead into registers so its global-load latency hides behind the math and the stores.
+    //      quarter take alternate 32-column chunks.  Every global access goes through the warp's swizzled staging tile
+    //      (32 rows x 64 bytes) so that 4 lanes move one contiguous 64-byte row segment: 32 bf16 columns per pass, or 16
+    //      fp32 columns per pass for the fp32 residual stream (F32S).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t stg = smem_base + (uint32_t)((warp - 2) * EPI_TILE_BYTES);
-    const bf16* side = (epi.flags & GEMM_DGELU) ? epi.aux : ((epi.flags & GEMM_RESID) ? epi.resid : nullptr);
-    const long long ld_side = (epi.flags & GEMM_DGELU) ? epi.ld_aux : epi.ld_res;
-    const bool second_resid = (epi.flags & GEMM_DGELU) && (epi.flags & GEMM_RESID);
-    uint4 pf[4];
-    auto prefetch = [&](int tile, int c0) {                    // chunk (tile, c0) of the side input -> pf
-      const long long r0 = (long long)(tile % m_tiles) * BM + q * 32;
-      const int cc = (tile / m_tiles) * BN + c0;
+    const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
+    const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;            // residual in the compute dtype
+    const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
+    // bf16 side tile -> this thread's 32 values (through the staging tile)
+    auto add_bf16_tile = [&](const bf16* src, long long ld, long long row0, int col0, int rows_ok, int cols_ok, float* v,
+                             bool dgelu) {
+      g2s_tile(stg, src + row0 * ld + col0, ld, rows_ok, cols_ok, lane);
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long r = r0 + i * 8 + (lane >> 2);
-        const int c = cc + (lane & 3) * 8;
-        pf[i] = (r < M && c < N) ? __ldg(reinterpret_cast<const uint4*>(side + r * ld_side + c)) : make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = lds16(stg_addr(stg, lane, j));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          if (dgelu) {
+            v[j * 8 + 2 * e] *= dgelu_fast(f.x);
+            v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
+          } else {
+            v[j * 8 + 2 * e] += f.x;
+            v[j * 8 + 2 * e + 1] += f.y;
+          }
+        }
       }
+      __syncwarp();
     };
-    if (side && (int)blockIdx.x < num_tiles && half * 32 < BN) prefetch(blockIdx.x, half * 32);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
@@ -607,86 +630,98 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         const int col0 = n0 + c0;
         const int cols_ok = min(32, N - col0);                              // may be <= 0
-        const bool live = rows_ok > 0 && cols_ok > 0;                       // warp-uniform
+        if (rows_ok <= 0 || cols_ok <= 0) continue;                         // warp-uniform
         float v[32];
-        if (live) {
+        {
           uint32_t r[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * cfg::ACC_COLS + c0), r);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (epi.bias) {
-            if (cols_ok == 32) {
+        }
+        if (epi.bias) {
+          if (cols_ok == 32) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
-                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
           }
-          if (epi.pre_out) {
+        }
+        if (epi.pre_out && !pre_final) {
+          regs_to_stage(stg, lane, v);
+          __syncwarp();
+          s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
+          __syncwarp();
+        }
+        if (epi.flags & GEMM_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (!F32S && (epi.flags & GEMM_DGELU)) add_bf16_tile(epi.aux, epi.ld_aux, row0, col0, rows_ok, cols_ok, v, true);
+        if (resid_t) add_bf16_tile(epi.resid, epi.ld_res, row0, col0, rows_ok, cols_ok, v, false);
+        if (F32S && resid_f32) {
+          const float* rsrc = reinterpret_cast<const float*>(epi.resid) + row0 * epi.ld_res + col0;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                                  // 16 fp32 columns per pass
+            const int cok = cols_ok - hh * 16;
+            if (cok <= 0) break;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2), c = lane & 3;
+              if (r < rows_ok && c * 4 < cok)
+                sts16(stg_addr(stg, r, c),
+                      __ldg(reinterpret_cast<const uint4*>(rsrc + (long long)r * epi.ld_res + hh * 16 + c * 4)));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = lds16(stg_addr(stg, lane, j));
+              v[hh * 16 + 4 * j] += __uint_as_float(u.x);
+              v[hh * 16 + 4 * j + 1] += __uint_as_float(u.y);
+              v[hh * 16 + 4 * j + 2] += __uint_as_float(u.z);
+              v[hh * 16 + 4 * j + 3] += __uint_as_float(u.w);
+            }
+            __syncwarp();
+          }
+        }
+        if (F32S && out_f32) {
+          float* cdst = reinterpret_cast<float*>(C) + row0 * ldc + col0;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cok = cols_ok - hh * 16;
+            if (cok <= 0) break;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts16(stg_addr(stg, lane, j),
+                    make_uint4(__float_as_uint(v[hh * 16 + 4 * j]), __float_as_uint(v[hh * 16 + 4 * j + 1]),
+                               __float_as_uint(v[hh * 16 + 4 * j + 2]), __float_as_uint(v[hh * 16 + 4 * j + 3])));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2), c = lane & 3;
+              if (r < rows_ok && c * 4 < cok)
+                *reinterpret_cast<uint4*>(cdst + (long long)r * ldc + hh * 16 + c * 4) = lds16(stg_addr(stg, r, c));
+            }
+            __syncwarp();
+          }
+          if (epi.pre_out && pre_final) {                                   // compute-dtype copy of the final value
             regs_to_stage(stg, lane, v);
             __syncwarp();
             s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
             __syncwarp();
           }
-          if (epi.flags & GEMM_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-          }
-        }
-        if (side) {
-          // the prefetched chunk is exactly this one (chunks are visited in prefetch order)
-          if (live) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sts16(stg_addr(stg, i * 8 + (lane >> 2), lane & 3), pf[i]);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = lds16(stg_addr(stg, lane, j));
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                if (epi.flags & GEMM_DGELU) {
-                  v[j * 8 + 2 * e] *= dgelu_fast(f.x);
-                  v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
-                } else {
-                  v[j * 8 + 2 * e] += f.x;
-                  v[j * 8 + 2 * e + 1] += f.y;
-                }
-              }
-            }
-            __syncwarp();
-          }
-          // next chunk of this warp: same tile, or the first chunk of its next tile
-          if (c0 + 64 < BN) prefetch(tile, c0 + 64);
-          else if (tile + (int)gridDim.x < num_tiles) prefetch(tile + gridDim.x, half * 32);
-        }
-        if (!live) continue;
-        if (second_resid) {
-          g2s_tile(stg, epi.resid + row0 * epi.ld_res + col0, epi.ld_res, rows_ok, cols_ok, lane);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = lds16(stg_addr(stg, lane, j));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              v[j * 8 + 2 * e] += f.x;
-              v[j * 8 + 2 * e + 1] += f.y;
-            }
-          }
-          __syncwarp();
+          continue;
         }
         regs_to_stage(stg, lane, v);
         __syncwarp();
         s2g_tile(stg, C + row0 * ldc + col0, ldc, rows_ok, cols_ok, lane);
+        if (F32S && epi.pre_out && pre_final)
+          s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
         __syncwarp();
       }
       // hand the accumulator back to the MMA warp
@@ -931,15 +966,24 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_ws_kernel<BN, STAGES>,
+    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_ws_kernel<BN, STAGES, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(gemm_umma_ws_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                cfg::SMEM_BYTES);
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_umma_ws_kernel<BN, STAGES><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
-                                                                          EpiView<bf16>(e));
+  if (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) {
+    if (e.flags & GEMM_DGELU) return S2U_EUNSUPPORTED;
+    gemm_umma_ws_kernel<BN, STAGES, true><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
+                                                                                  EpiView<bf16>(e));
+  } else {
+    gemm_umma_ws_kernel<BN, STAGES, false><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
+                                                                                   EpiView<bf16>(e));
+  }
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -954,6 +998,7 @@ static bool supported(const void* A, int lda, const void* W, int ldw, const void
   if (e.pre_out && (!aligned16(e.pre_out) || (e.ld_pre % 8))) return false;
   if ((e.flags & GEMM_DGELU) && (!aligned16(e.aux) || (e.ld_aux % 8))) return false;
   if ((e.flags & GEMM_RESID) && (!aligned16(e.resid) || (e.ld_res % 8))) return false;
+  if ((e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) && false) return false;
   return true;
 }
 
@@ -1034,6 +1079,7 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     const bf16 *a = (const bf16*)A, *w = (const bf16*)W;
     bf16* c = (bf16*)C;
     if (legacy) {
+      if (flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) return S2U_EUNSUPPORTED;
       switch (bn) {
         case 32: return umma::launch<32, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         case 64: return umma::launch<64, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);

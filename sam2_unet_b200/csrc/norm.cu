@@ -4,15 +4,16 @@
 // (2 elements/elem), backward reads dy, x (+ residual gradient) and writes dx.
 #include "common.cuh"
 
-template <typename T>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+// TX = storage type of the normalised tensor (the residual stream: fp32 in both modes), T = compute dtype of y
+template <typename T, typename TX>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, T* __restrict__ y,
                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                     long long R, int C, float eps) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
-  const T* xr = x + row * C;
+  const TX* xr = x + row * C;
   const int nv = C >> 3;
   float s = 0.f;
   for (int c = lane; c < nv; c += 32) {
@@ -51,8 +52,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
 // One block = 8 warps, one row each.
 constexpr int LN_BWD_ROWS = 8;               // one row per warp: enough blocks to fill the GPU at 5,808 rows
 constexpr int LN_MAX_CHUNKS = 5;             // C <= 5 * 32 * 8 = 1280 (Hiera-L stage 4: 1152)
-template <typename T>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, typename TX>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const TX* __restrict__ x,
                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
                                                     const float* __restrict__ rstd, const T* __restrict__ dres,
                                                     T* __restrict__ dx, const T* __restrict__ pre,
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
   for (int it = 0; it < LN_BWD_ROWS / 8; ++it) {
     const long long row = (long long)blockIdx.x * LN_BWD_ROWS + it * 8 + warp;
     if (row >= R) continue;
-    const T* xr = x + row * C;
+    const TX* xr = x + row * C;
     const T* dyr = dy + row * C;
     const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
@@ -132,26 +133,39 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 extern "C" {
 
 int s2u_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                      long long R, int C, float eps, int dtype, void* stream) {
+                      long long R, int C, float eps, int x_f32, int dtype, void* stream) {
   if (R <= 0 || C <= 0 || (C & 7)) return S2U_EINVAL;
-  S2U_DISPATCH_T(dtype, {
-    ln_fwd_kernel<T><<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, R,
-                                                                     C, eps);
-  })
+  if (x_f32 || dtype == S2U_F32) {
+    S2U_DISPATCH_T(dtype, {
+      ln_fwd_kernel<T, float><<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta, (T*)y,
+                                                                              mean, rstd, R, C, eps);
+    })
+  } else {
+    ln_fwd_kernel<bf16, bf16><<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
+                                                                              mean, rstd, R, C, eps);
+  }
   S2U_LAUNCH_CHECK();
   return 0;
 }
 
 int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                       const void* dres, void* dx, const void* pre, void* dx2, float* colsum, long long R, int C,
-                      int dtype, void* stream) {
+                      int x_f32, int dtype, void* stream) {
   if (R <= 0 || C <= 0 || (C & 7) || (dx2 && !pre) || (colsum && !dx2)) return S2U_EINVAL;
   if (C > LN_MAX_CHUNKS * 256) return S2U_EUNSUPPORTED;
   const size_t smem = colsum ? (size_t)C * sizeof(float) : 0;
-  S2U_DISPATCH_T(dtype, {
-    ln_bwd_kernel<T><<<ceil_div(R, LN_BWD_ROWS), 256, smem, (cudaStream_t)stream>>>(
-        (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, (const T*)pre, (T*)dx2, colsum, R, C);
-  })
+  const int grid = ceil_div(R, LN_BWD_ROWS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_f32 || dtype == S2U_F32) {
+    S2U_DISPATCH_T(dtype, {
+      ln_bwd_kernel<T, float><<<grid, 256, smem, st>>>((const T*)dy, (const float*)x, gamma, mean, rstd, (const T*)dres,
+                                                      (T*)dx, (const T*)pre, (T*)dx2, colsum, R, C);
+    })
+  } else {
+    ln_bwd_kernel<bf16, bf16><<<grid, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
+                                                      (const bf16*)dres, (bf16*)dx, (const bf16*)pre, (bf16*)dx2,
+                                                      colsum, R, C);
+  }
   S2U_LAUNCH_CHECK();
   return 0;
 }

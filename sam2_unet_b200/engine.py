@@ -25,7 +25,7 @@ from . import _lib
 from .config import TrunkConfig
 from .resample_tables import ResampleTables
 
-GELU, DGELU, RESID = 1, 2, 4
+GELU, DGELU, RESID, OUT_F32, RESID_F32, PRE_FINAL = 1, 2, 4, 16, 32, 64
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -78,12 +78,12 @@ class Ops:
 
     def ln_fwd(self, x, gamma, beta, y, mean, rstd, R, C):
         _lib.call("s2u_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
-                  _ptr(rstd), R, C, 1e-6, self.dt, self.stream)
+                  _ptr(rstd), R, C, 1e-6, 1 if x.dtype == torch.float32 else 0, self.dt, self.stream)
 
     def ln_bwd(self, dy, x, gamma, mean, rstd, dres, dx, R, C, pre=None, dx2=None, colsum=None):
         _lib.call("s2u_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(pre), _ptr(dx2), _ptr(colsum), R, C, self.dt,
-                  self.stream)
+                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(pre), _ptr(dx2), _ptr(colsum), R, C,
+                  1 if x.dtype == torch.float32 else 0, self.dt, self.stream)
 
     def dgelu_mul(self, dy, pre, out):
         _lib.call("s2u_dgelu_mul", dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), self.dt, self.stream)
@@ -110,9 +110,9 @@ class Ops:
                   dout.data_ptr(), dqkv.data_ptr(), dws.data_ptr(), B, H, W, nh, hd, window, 1 if pool else 0,
                   self.dt, self.stream)
 
-    def patch_embed(self, x, w, bias, pos, out, B, S, E):
-        _lib.call("s2u_patch_embed", x.data_ptr(), w.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(), B,
-                  S, E, self.dt, self.stream)
+    def patch_embed(self, x, w, bias, pos, out, B, S, E, out_copy=None):
+        _lib.call("s2u_patch_embed", x.data_ptr(), w.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(),
+                  1 if out.dtype == torch.float32 else 0, _ptr(out_copy), B, S, E, self.dt, self.stream)
 
     def im2col(self, x, ldx, out, B, H, W, Cin, KH, KW, dh, dw, ph, pw):
         _lib.call("s2u_im2col", x.data_ptr(), ldx, out.data_ptr(), B, H, W, Cin, KH, KW, dh, dw, ph, pw, self.dt,
@@ -305,21 +305,28 @@ class Engine:
         tape = dict(B=B, S=S, blocks=[], training=training) if save else None
         H = S // 4
         E = cfg.embed_dim
-        t = ops.empty(B * H * H, E)
-        ops.patch_embed(x, fz["pe.w"], fz["pe.b"], self._pos_table(H), t, B, S, E)
+        # the residual stream is kept in fp32 in both modes (in bf16 mode its rounding error would otherwise
+        # random-walk over 2 adds per block); `tc` is its compute-dtype copy, the operand of the next GEMMs
+        mixed = self.T != torch.float32
+        ts = ops.empty(B * H * H, E, dtype=torch.float32)
+        tc = ops.empty(B * H * H, E) if mixed else ts
+        ops.patch_embed(x, fz["pe.w"], fz["pe.b"], self._pos_table(H), ts, B, S, E, out_copy=tc if mixed else None)
         feats = []
         W = H
         for i, spec in enumerate(cfg.blocks):
-            t, H, W = self._block_fwd(i, spec, t, B, H, W, tape)
+            ts, tc, H, W = self._block_fwd(i, spec, ts, tc, B, H, W, tape)
             if spec.stage_end:
-                feats.append((t, H))
+                feats.append((tc, H))
         outs = self._decoder_fwd(feats, B, S, training, tape)
         if save:
             self.tape = tape
         return outs
 
-    def _block_fwd(self, i, spec, x, B, H, W, tape):
+    def _block_fwd(self, i, spec, xs, x, B, H, W, tape):
+        """xs: residual stream (fp32), x: its compute-dtype copy (the same tensor in fp32 mode)."""
         ops, fz, sh = self.ops, self._frozen, self._shadow
+        mixed = self.T != torch.float32
+        SF = (OUT_F32 | RESID_F32) if mixed else 0           # stream in, stream out
         P = self.model.flat.views
         p = f"encoder.blocks.{i}.block."
         a = f"encoder.blocks.{i}.prompt_learn."
@@ -330,8 +337,8 @@ class Engine:
         # adapter (SAM2UNet.py:61-63): xa = x + gelu(gelu(x W1^T + b1) W2^T + b2)
         h1, u = ops.empty(R, 32), ops.empty(R, 32)
         ops.gemm(x, sh[a + "0.w"], u, bias=P[a + "0.bias"], pre_out=h1, flags=GELU)
-        h2, xa = ops.empty(R, C), ops.empty(R, C)
-        ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=x, flags=GELU | RESID)
+        h2, xa = ops.empty(R, C), ops.empty(R, C, dtype=f32)
+        ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=xs, flags=GELU | RESID | SF)
         # norm1 (hieradet.py:134)
         n1 = ops.empty(R, C)
         mean1, rstd1 = ops.empty(R, dtype=f32), ops.empty(R, dtype=f32)
@@ -344,8 +351,9 @@ class Engine:
             Ho, Wo = H // 2, W // 2
             sc = ops.empty(B * Ho * Wo, C2)
             ops.maxpool_fwd(pr, sc, B, H, W, C2)
+            sc_flags = OUT_F32 if mixed else 0               # pooled shortcut is in the compute dtype
         else:
-            sc = xa
+            sc, sc_flags = xa, SF
         Ro = B * Ho * Wo
         # qkv on real tokens only; padding, windows, q-pool live inside the attention kernel
         qkv = ops.empty(R, 3 * C2)
@@ -353,8 +361,8 @@ class Engine:
         o = ops.empty(Ro, C2)
         lse = ops.empty(Ro, nh, dtype=f32)
         ops.attn_fwd(qkv, fz[p + "attn.qkv.b"], o, lse, B, H, W, nh, hd, spec.window, spec.q_pool)
-        y = ops.empty(Ro, C2)
-        ops.gemm(o, fz[p + "attn.proj.w"], y, bias=fz[p + "attn.proj.b"], resid=sc, flags=RESID)
+        y = ops.empty(Ro, C2, dtype=f32)
+        ops.gemm(o, fz[p + "attn.proj.w"], y, bias=fz[p + "attn.proj.b"], resid=sc, flags=RESID | sc_flags)
         n2 = ops.empty(Ro, C2)
         mean2, rstd2 = ops.empty(Ro, dtype=f32), ops.empty(Ro, dtype=f32)
         ops.ln_fwd(y, fz[p + "norm2.g"], fz[p + "norm2.b"], n2, mean2, rstd2, Ro, C2)
@@ -362,12 +370,14 @@ class Engine:
         act = ops.empty(Ro, 4 * C2)
         ops.gemm(n2, fz[p + "mlp.layers.0.w"], act, bias=fz[p + "mlp.layers.0.b"],
                  pre_out=hid if tape is not None else None, flags=GELU)
-        z = ops.empty(Ro, C2)
-        ops.gemm(act, fz[p + "mlp.layers.1.w"], z, bias=fz[p + "mlp.layers.1.b"], resid=y, flags=RESID)
+        z = ops.empty(Ro, C2, dtype=f32)
+        zc = ops.empty(Ro, C2) if mixed else z
+        ops.gemm(act, fz[p + "mlp.layers.1.w"], z, bias=fz[p + "mlp.layers.1.b"], resid=y, flags=RESID | SF | (PRE_FINAL if mixed else 0),
+                 pre_out=zc if mixed else None)
         if tape is not None:
             tape["blocks"].append(dict(x=x, h1=h1, u=u, h2=h2, xa=xa, mean1=mean1, rstd1=rstd1, pr=pr, qkv=qkv, o=o,
                                        lse=lse, y=y, mean2=mean2, rstd2=rstd2, hid=hid, H=H, W=W, Ho=Ho, Wo=Wo))
-        return z, Ho, Wo
+        return z, zc, Ho, Wo
 
     # conv (+ BN (+ residual) (+ ReLU)) on NHWC rows.  `src`: (tensor, ld, channel offset) of the input map.
     def _conv_bn(self, cs: _ConvSpec, src, B, H, out, ld_out, out_off, relu, training, tape, resid=None, ld_res=0):

@@ -12,8 +12,9 @@ ops = Ops(torch.bfloat16, dev)
 shapes = [(5808, 2304, 576), (5808, 576, 2304), (5808, 1728, 576), (5808, 576, 576), (92928, 576, 144),
           (92928, 144, 576), (23232, 1152, 288), (23232, 288, 1152), (1452, 4608, 1152), (1452, 1152, 4608),
           (92928, 64, 576), (92928, 32, 144), (8192, 8192, 8192)]
-variants = [("ws128", 16 + 128), ("ws256", 16 + 256), ("old128", 512 + 128), ("old256", 512 + 256)]
-flagsets = [("plain", 0, False), ("gelu+pre", 1, True), ("dgelu", 2, False), ("resid", 4, False)]
+variants = [("ws128", 16 + 128), ("ws256", 16 + 256), ("old128", 512 + 128)]
+flagsets = [("plain", 0, False), ("gelu+pre", 1, True), ("dgelu", 2, False), ("resid", 4, False),
+            ("stream", 4 | 16 | 32 | 64, True)]
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 
@@ -36,6 +37,8 @@ for (M, N, K) in shapes:
     aux = torch.randn(M, N, device=dev).bfloat16()
     C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    C32 = torch.empty(M, N, device=dev)
+    R32 = torch.randn(M, N, device=dev)
     fl = 2.0 * M * N * K
     t_ref = timeit(lambda: torch.matmul(A, W.t(), out=C))
     line = f"{str((M, N, K)):22s} cublas {t_ref:7.1f}us {fl / t_ref / 1e6:6.0f}TF |"
@@ -45,9 +48,12 @@ for (M, N, K) in shapes:
         for vname, be in variants:
             if N <= 64 and "256" in vname:
                 continue
+            if fname == "stream" and vname.startswith("old"):
+                continue
             try:
-                t = timeit(lambda: ops.gemm(A, W, C, bias=bias, pre_out=pre if use_pre else None,
-                                            aux=aux if fl_ & 2 else None, resid=aux if fl_ & 4 else None, flags=fl_,
+                t = timeit(lambda: ops.gemm(A, W, C32 if fl_ & 16 else C, bias=bias, pre_out=pre if use_pre else None,
+                                            aux=aux if fl_ & 2 else None,
+                                            resid=(R32 if fl_ & 32 else aux) if fl_ & 4 else None, flags=fl_,
                                             backend=be))
                 line += f" {fname}/{vname} {t:6.1f}us {fl / t / 1e6:5.0f}TF |"
             except Exception as e:  # noqa: BLE001

@@ -88,6 +88,17 @@ def test_gemm_umma(cuda, shape, bn):
     C2 = ops.empty(M, N)
     ops.gemm(A, W, C2, backend=backend)
     _close(C2, A.float() @ W.float().t(), 1e-2, "plain")
+    # fp32 residual stream: fp32 residual in, fp32 C out, bf16 copy of the final value
+    r32 = _rand((M, N), "fp32", cuda, 6)
+    C3, cp = torch.empty(M, N, device=cuda), ops.empty(M, N)
+    ops.gemm(A, W, C3, bias=bias, resid=r32, pre_out=cp, flags=4 | 16 | 32 | 64, backend=backend)
+    ref3 = A.float() @ W.float().t() + bias + r32
+    _close(C3, ref3, 1e-4, "fp32 stream out")
+    _close(cp, ref3, 1e-2, "bf16 copy of the stream")
+    C4, h4 = torch.empty(M, N, device=cuda), ops.empty(M, N)
+    ops.gemm(A, W, C4, bias=bias, resid=resid, pre_out=h4, flags=1 | 4 | 16, backend=backend)     # bf16 resid, fp32 out
+    _close(C4, F.gelu(A.float() @ W.float().t() + bias) + resid.float(), 1e-3, "gelu + bf16 resid, fp32 out")
+    _close(h4, A.float() @ W.float().t() + bias, 1e-2, "pre-activation copy")
 
 
 @pytest.mark.parametrize("shape", [(3000, 32, 144), (5808, 576, 32), (777, 64, 64), (92928, 64, 576), (100, 64, 2304),
@@ -150,6 +161,14 @@ def test_layernorm(cuda, dtype, C):
     (dg,) = torch.autograd.grad(F.gelu(pr).sum(), pr)
     _close(dx2, dx.float() * dg, _tol(dtype, 1e-5), "ln bwd fused gelu'")
     _close(cs, dx2.float().sum(0), 1e-4, "ln bwd fused colsum")
+    if dtype == "bf16":                                   # fp32 residual stream in, bf16 out
+        x32 = x.float()
+        y2, m2, r2 = ops.empty(R, C), ops.empty(R, dtype=torch.float32), ops.empty(R, dtype=torch.float32)
+        ops.ln_fwd(x32, g, b, y2, m2, r2, R, C)
+        _close(y2, ref, _tol(dtype), "ln fwd (fp32 x)")
+        dx3 = ops.empty(R, C)
+        ops.ln_bwd(dy, x32, g, m2, r2, dres, dx3, R, C)
+        _close(dx3, gx + dres.float(), _tol(dtype), "ln bwd (fp32 x)")
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
@@ -247,6 +266,10 @@ def test_patch_embed(cuda, dtype):
     ops.patch_embed(x, w, b, pos, out, B, S, E)
     ref = F.conv2d(x, w, b, stride=4, padding=3).permute(0, 2, 3, 1) + pos
     _close(out, ref, _tol(dtype, 1e-5, 1e-2), "patch embed")
+    o32, oc = torch.empty(B, S // 4, S // 4, E, device=cuda), ops.empty(B, S // 4, S // 4, E)
+    ops.patch_embed(x, w, b, pos, o32, B, S, E, out_copy=oc)
+    _close(o32, ref, 1e-5, "patch embed fp32 stream")
+    assert torch.equal(oc, out)
 
 
 CONVS = [(64, 1, 3, 1), (64, 3, 1, 1), (64, 1, 7, 1), (64, 7, 1, 1), (64, 3, 3, 3), (64, 3, 3, 7), (256, 3, 3, 1),
