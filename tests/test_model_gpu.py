@@ -292,3 +292,67 @@ def test_bf16_mask_criteria_after_prefit(cuda):
         assert 0.02 < frac < 0.98, ("degenerate masks", train, name, frac)
         assert err <= 2e-2, (train, name, err)
         assert iou >= 0.999, (train, name, iou)
+
+
+@pytest.mark.parametrize("variant", ["t", "s", "b+"])
+def test_trunk_variants_forward_fp32_vs_oracle(cuda, variant):
+    """BASELINE.json config 4 trunks (Hiera-T/S/B+; L is covered by the config-1 golden test): 352x352 forward, fp32,
+    eval mode, against the oracle.  At 352 these trunks pad 22x22 -> 28x28 (14x14 windows) and 11x11 -> 14x14
+    (7x7 windows): window token counts 196 / 49 exercise the masked tails of the attention kernels."""
+    from oracle import port
+    cfg = {"t": "sam2_hiera_t.yaml", "s": "sam2_hiera_s.yaml", "b+": "sam2_hiera_b+.yaml"}[variant]
+    m, sd = _build(cfg, "fp32", cuda)
+    x, _ = port.synthetic_batch(1, 352, seed=21)
+    m.eval()
+    with torch.no_grad():
+        got = m(x.to(cuda))
+        ref = port.forward(sd, port.TRUNKS[variant], x, False)
+    for g, r, name in zip(got, ref, ("out", "out1", "out2")):
+        assert _maxnorm(g, r) <= 1e-3, (variant, name, _maxnorm(g, r))
+    # the bf16 tensor-core path on the same weights
+    mb, _ = _build(cfg, "bf16", cuda)
+    mb.eval()
+    with torch.no_grad():
+        gb = mb(x.to(cuda))
+    for g, r in zip(gb, ref):
+        assert (torch.sigmoid(g.float().cpu()) - torch.sigmoid(r)).abs().max().item() <= 3e-2
+
+
+def test_hiera_l_1024_forward_vs_oracle(cuda):
+    """BASELINE.json config 5 geometry: Hiera-L at 1024x1024 (no window padding anywhere, 4096-token global
+    attention in blocks 23/33/43), batch 1, fp32 forward against the oracle, and the bf16 path against fp32."""
+    from oracle import port
+    m, sd = _build("sam2_hiera_l.yaml", "fp32", cuda)
+    x, _ = port.synthetic_batch(1, 1024, seed=5)
+    m.eval()
+    with torch.no_grad():
+        got = m(x.to(cuda))
+        ref = port.forward(sd, port.TRUNKS["l"], x, False)
+    for g, r, name in zip(got, ref, ("out", "out1", "out2")):
+        assert _maxnorm(g, r) <= 1e-3, (name, _maxnorm(g, r))
+    del m
+    mb, _ = _build("sam2_hiera_l.yaml", "bf16", cuda)
+    mb.eval()
+    with torch.no_grad():
+        gb = mb(x.to(cuda))
+    for g, r in zip(gb, ref):
+        assert (torch.sigmoid(g.float().cpu()) - torch.sigmoid(r)).abs().max().item() <= 3e-2
+
+
+def test_predictor_graph_matches_eager(cuda):
+    from sam2_unet_b200 import Predictor
+    m, _ = _build("tiny_test.yaml", "bf16", cuda)
+    m.eval()
+    x = torch.randn(2, 3, 96, 96, device=cuda)
+    with torch.no_grad():
+        ref = [o.clone() for o in m(x)]
+    pred = Predictor(m)
+    for _ in range(4):                       # 2 eager warm-ups, capture, replay
+        outs = pred(x)
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b)
+    x2 = torch.randn(2, 3, 96, 96, device=cuda)
+    with torch.no_grad():
+        ref2 = [o.clone() for o in m(x2)]
+    for a, b in zip(pred(x2.cpu()), ref2):   # host input: copied into the static buffer
+        assert torch.equal(a, b)
