@@ -203,9 +203,12 @@ class Engine:
         self._pos_cache: Dict[int, torch.Tensor] = {}
         self._bn_ws: Dict[str, Dict[str, torch.Tensor]] = {}
         self.tape: Optional[dict] = None
+        self._units = {cs.name: cs for cs in model.conv_units}
         self._prepare_frozen()
         self._shadow_version = -1
         self._refresh = None
+        self._streams = None
+        self.overlap = self.device.type == "cuda"   # RFB forward/backward on side streams, overlapped with the trunk
 
     # ------------------------------------------------------------------------------------------ weights
 
@@ -311,16 +314,42 @@ class Engine:
         ts = ops.empty(B * H * H, E, dtype=torch.float32)
         tc = ops.empty(B * H * H, E) if mixed else ts
         ops.patch_embed(x, fz["pe.w"], fz["pe.b"], self._pos_table(H), ts, B, S, E, out_copy=tc if mixed else None)
-        feats = []
+        if tape is not None:
+            tape["convs"] = {}
+            tape["dec"] = {}
+        # Each RFB only depends on its own stage output, so it runs on a side stream and overlaps the rest of the
+        # trunk (RFB1 works on the 88x88 map while stages 2-4 run); the streams are joined before the Up stages.
+        main = torch.cuda.current_stream(self.device) if self.overlap else None
+        side = self._side_streams() if self.overlap else None
+        feats, rfb_out, joins = [], [], []
         W = H
         for i, spec in enumerate(cfg.blocks):
             ts, tc, H, W = self._block_fwd(i, spec, ts, tc, B, H, W, tape)
             if spec.stage_end:
-                feats.append((tc, H))
-        outs = self._decoder_fwd(feats, B, S, training, tape)
+                k = len(feats)
+                feats.append(tc)                             # keeps the tensor alive until the join
+                if self.overlap:
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    side[k].wait_event(fork)
+                    with torch.cuda.stream(side[k]):
+                        rfb_out.append(self._rfb_fwd(k, tc, H, B, training, tape))
+                        done = torch.cuda.Event()
+                        done.record(side[k])
+                    joins.append(done)
+                else:
+                    rfb_out.append(self._rfb_fwd(k, tc, H, B, training, tape))
+        for done in joins:
+            main.wait_event(done)
+        outs = self._up_fwd(rfb_out, B, S, training, tape)
         if save:
             self.tape = tape
         return outs
+
+    def _side_streams(self):
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        return self._streams
 
     def _block_fwd(self, i, spec, xs, x, B, H, W, tape):
         """xs: residual stream (fp32), x: its compute-dtype copy (the same tensor in fp32 mode)."""
@@ -416,47 +445,40 @@ class Engine:
             tape["convs"][cs.name] = dict(col=col, ldcol=ldcol, coff=col_ptr_off, raw=raw, mean=mean, rstd=rstd, B=B,
                                           H=H)
 
-    def _decoder_fwd(self, feats, B, S, training, tape):
+    def _rfb_fwd(self, k, f, H, B, training, tape):
+        """RFB_modified k on the stage-k feature map f [B*H*H, Cin] (SAM2UNet.py:117-125); returns (dst, ld, H) where
+        dst is the left half of up-stage k's concat buffer [skip | upsampled] (plain [M,64] for the deepest level)."""
         ops = self.ops
-        units = {cs.name: cs for cs in self.model.conv_units}
-        P = self.model.flat.views
+        units = self._units
+        r = f"rfb{k + 1}."
+        M = B * H * H
+        Cin = f.shape[1]
+        if k < 3:
+            dst, ld_dst = ops.empty(M, 128), 128
+        else:
+            dst, ld_dst = ops.empty(M, 64), 64
+        cat = ops.empty(M, 256)
+        src = (f, Cin, 0)
+        self._conv_bn(units[r + "branch0.0.conv"], src, B, H, cat, 256, 0, False, training, tape)
+        for bi in (1, 2, 3):
+            t0, t1, t2 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
+            self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape)
+            self._conv_bn(units[r + f"branch{bi}.1.conv"], (t0, 64, 0), B, H, t1, 64, 0, False, training, tape)
+            self._conv_bn(units[r + f"branch{bi}.2.conv"], (t1, 64, 0), B, H, t2, 64, 0, False, training, tape)
+            self._conv_bn(units[r + f"branch{bi}.3.conv"], (t2, 64, 0), B, H, cat, 256, 64 * bi, False, training, tape)
+        res = ops.empty(M, 64)
+        self._conv_bn(units[r + "conv_res.conv"], src, B, H, res, 64, 0, False, training, tape)
+        self._conv_bn(units[r + "conv_cat.conv"], (cat, 256, 0), B, H, dst, ld_dst, 0, True, training, tape,
+                      resid=res, ld_res=64)
         if tape is not None:
-            tape["convs"] = {}
-            tape["dec"] = {}
-        rfb_out = []
-        cats = []
-        for k, (f, H) in enumerate(feats):
-            r = f"rfb{k + 1}."
-            M = B * H * H
-            Cin = f.shape[1]
-            # up-stage concat buffer [skip | upsampled]: the RFB output is written straight into its left half
-            if k < 3:
-                dst, ld_dst = ops.empty(M, 128), 128
-            else:
-                dst, ld_dst = ops.empty(M, 64), 64
-            cat = ops.empty(M, 256)
-            s1 = ops.empty(M, 64)      # per-branch scratch maps
-            s2 = ops.empty(M, 64)
-            src = (f, Cin, 0)
-            self._conv_bn(units[r + "branch0.0.conv"], src, B, H, cat, 256, 0, False, training, tape)
-            inter = {}
-            for bi in (1, 2, 3):
-                t0, t1, t2 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
-                self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape)
-                self._conv_bn(units[r + f"branch{bi}.1.conv"], (t0, 64, 0), B, H, t1, 64, 0, False, training, tape)
-                self._conv_bn(units[r + f"branch{bi}.2.conv"], (t1, 64, 0), B, H, t2, 64, 0, False, training, tape)
-                self._conv_bn(units[r + f"branch{bi}.3.conv"], (t2, 64, 0), B, H, cat, 256, 64 * bi, False, training,
-                              tape)
-                inter[bi] = (t0, t1, t2)
-            res = ops.empty(M, 64)
-            self._conv_bn(units[r + "conv_res.conv"], src, B, H, res, 64, 0, False, training, tape)
-            self._conv_bn(units[r + "conv_cat.conv"], (cat, 256, 0), B, H, dst, ld_dst, 0, True, training, tape,
-                          resid=res, ld_res=64)
-            rfb_out.append((dst, ld_dst, H))
-            if tape is not None:
-                tape["dec"][r] = dict(f=f, cat=cat, dst=dst, ld_dst=ld_dst, H=H, Cin=Cin)
-            del s1, s2
-        # decoder: up1(x4, x3) -> side1 ; up2(., x2) -> side2 ; up3(., x1) -> head   (SAM2UNet.py:167-172)
+            tape["dec"][r] = dict(f=f, cat=cat, dst=dst, ld_dst=ld_dst, H=H, Cin=Cin)
+        return dst, ld_dst, H
+
+    def _up_fwd(self, rfb_out, B, S, training, tape):
+        """up1(x4, x3) -> side1 ; up2(., x2) -> side2 ; up3(., x1) -> head   (SAM2UNet.py:167-172)."""
+        ops = self.ops
+        units = self._units
+        P = self.model.flat.views
         cur, cur_ld, cur_h = rfb_out[3]
         outs = {}
         for stage, (k, head_name, scale) in enumerate(((2, "side1", 16), (1, "side2", 8), (0, "head", 4))):
@@ -495,17 +517,36 @@ class Engine:
         B, S = tape["B"], tape["S"]
         nblocks = len(self.cfg.blocks)
         buckets = self.model.flat.buckets if on_bucket is not None else []
-        d_feats = self._decoder_bwd(tape, {"head": g_out, "side1": g_out1, "side2": g_out2}, B, S)
-        for lo, hi, ready in buckets:
-            if ready == nblocks:
-                on_bucket(lo, hi)
+        main = torch.cuda.current_stream(self.device) if self.overlap else None
+        side = self._side_streams() if self.overlap else None
+        d_rfb = self._up_bwd(tape, {"head": g_out, "side1": g_out1, "side2": g_out2}, B, S)
+        # the four RFB backwards are independent: side streams, deepest first (its gradient is needed first);
+        # RFB1's backward (the 88x88 map) overlaps the whole trunk backward
+        d_feats, joins = [None] * 4, [None] * 4
+        for k in (3, 2, 1, 0):
+            if self.overlap:
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side[k].wait_event(fork)
+                with torch.cuda.stream(side[k]):
+                    d_feats[k] = self._rfb_bwd(k, tape, d_rfb[k], B)
+                    joins[k] = torch.cuda.Event()
+                    joins[k].record(side[k])
+            else:
+                d_feats[k] = self._rfb_bwd(k, tape, d_rfb[k], B)
         # trunk: walk the blocks backwards; stage-end blocks receive the RFB's gradient of that feature map
         dz = None
         stage = len(d_feats) - 1
         for i in range(nblocks - 1, -1, -1):
             spec = self.cfg.blocks[i]
             if spec.stage_end:
+                if joins[stage] is not None:
+                    main.wait_event(joins[stage])
                 g = d_feats[stage]
+                if stage == 0:                           # every RFB / decoder gradient is final now
+                    for lo, hi, ready in buckets:
+                        if ready == nblocks:
+                            on_bucket(lo, hi)
                 stage -= 1
                 if dz is None:
                     dz = g
@@ -598,64 +639,63 @@ class Engine:
         ops.gemm(A, sh[cs.name + ".wd"], dv, M=M, N=cs.cin, K=taps * 64, lda=lda, ldw=taps * 64, ldc=ld_d,
                  resid=dv if accumulate else None, ld_res=ld_d, flags=RESID if accumulate else 0)
 
-    def _decoder_bwd(self, tape, g_heads, B, S):
+    def _up_bwd(self, tape, g_heads, B, S):
+        """Backward of the heads and the three Up stages; returns, per pyramid level k, (tensor, pitch) holding the
+        gradient of RFB k's output (the left half of the concat-buffer gradient; plain [M,64] for the deepest)."""
         ops = self.ops
-        units = {cs.name: cs for cs in self.model.conv_units}
+        units = self._units
         P, G = self.model.flat.views, self.model.flat.grad_views
         dec = tape["dec"]
-        # gradient w.r.t. each RFB output (the left half of the concat buffers) and rfb4's output
-        d_rfb: List[Optional[torch.Tensor]] = [None, None, None, None]
+        d_rfb = [None, None, None, None]
         d_cur = None                                    # gradient of the current decoder feature map [M,64]
         for stage in (2, 1, 0):                          # up3, up2, up1
             u = f"up{stage + 1}."
             tp = dec[u]
             H, M = tp["H"], B * tp["H"] * tp["H"]
             k = 2 - stage
-            # head on this level
             tab = ResampleTables.get(H, S, False, float(tp["scale"]), self.device)
             dlow = ops.empty(B, H, H, dtype=torch.float32)
             ops.resample1_bwd(g_heads[tp["head"]].contiguous().float(), dlow, B, H, S, tab)
             dfeat = ops.empty(M, 64) if d_cur is None else d_cur
             ops.head_bwd(tp["out"], 64, P[tp["head"] + ".weight"], dlow, dfeat, 64, d_cur is not None,
                          G[tp["head"] + ".weight"], G[tp["head"] + ".bias"], M)
-            # double conv backwards
             dmid = ops.empty(M, 64)
             self._conv_bn_bwd(units[u + "conv.double_conv.3"], tape, dfeat, 64, 0, tp["out"], 64, 0, (dmid, 64, 0),
                               False)
             dcat = ops.empty(M, 128)
             self._conv_bn_bwd(units[u + "conv.double_conv.0"], tape, dmid, 64, 0, tp["mid"], 64, 0, (dcat, 128, 0),
                               False)
-            d_rfb[k] = dcat                             # left half [:, :64] is d(rfb_k output), pitch 128
-            # right half -> transpose of the bilinear x2 upsample
+            d_rfb[k] = (dcat, 128)                      # left half [:, :64] is d(rfb_k output)
             h_in = tp["inp_h"]
             dprev = ops.empty(B * h_in * h_in, 64)
             ops.resample_bwd(dcat.data_ptr() + 64 * dcat.element_size(), 128, dprev, 64, B, h_in, H, 64,
                              ResampleTables.get(h_in, H, True, None, self.device))
             d_cur = dprev
-        d_feats = []
-        for k in range(4):
-            r = f"rfb{k + 1}."
-            tp = dec[r]
-            H, Cin = tp["H"], tp["Cin"]
-            M = B * H * H
-            if k < 3:
-                dy, ld_dy = d_rfb[k], 128
-            else:
-                dy, ld_dy = d_cur, 64
-            # out = relu(bn(conv_cat(cat)) + bn(conv_res(f))): g = dy * (out > 0) feeds both BN backwards
-            g = ops.empty(M, 64)
-            ops.relu_bwd(dy, ld_dy, tp["dst"], tp["ld_dst"], g, 64, M, 64)
-            df = ops.empty(M, Cin)
-            dcatb = ops.empty(M, 256)
-            self._conv_bn_bwd(units[r + "conv_cat.conv"], tape, g, 64, 0, None, 0, 0, (dcatb, 256, 0), False)
-            self._conv_bn_bwd(units[r + "conv_res.conv"], tape, g, 64, 0, None, 0, 0, (df, Cin, 0), False)
-            self._conv_bn_bwd(units[r + "branch0.0.conv"], tape, dcatb, 256, 0, None, 0, 0, (df, Cin, 0), True)
-            for bi in (1, 2, 3):
-                d2, d1, d0 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
-                self._conv_bn_bwd(units[r + f"branch{bi}.3.conv"], tape, dcatb, 256, 64 * bi, None, 0, 0, (d2, 64, 0),
-                                  False)
-                self._conv_bn_bwd(units[r + f"branch{bi}.2.conv"], tape, d2, 64, 0, None, 0, 0, (d1, 64, 0), False)
-                self._conv_bn_bwd(units[r + f"branch{bi}.1.conv"], tape, d1, 64, 0, None, 0, 0, (d0, 64, 0), False)
-                self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, (df, Cin, 0), True)
-            d_feats.append(df)
-        return d_feats
+        d_rfb[3] = (d_cur, 64)
+        return d_rfb
+
+    def _rfb_bwd(self, k, tape, d_out, B):
+        """Backward of RFB k given the gradient of its output; returns the gradient of the stage-k feature map."""
+        ops = self.ops
+        units = self._units
+        r = f"rfb{k + 1}."
+        tp = tape["dec"][r]
+        H, Cin = tp["H"], tp["Cin"]
+        M = B * H * H
+        dy, ld_dy = d_out
+        # out = relu(bn(conv_cat(cat)) + bn(conv_res(f))): g = dy * (out > 0) feeds both BN backwards
+        g = ops.empty(M, 64)
+        ops.relu_bwd(dy, ld_dy, tp["dst"], tp["ld_dst"], g, 64, M, 64)
+        df = ops.empty(M, Cin)
+        dcatb = ops.empty(M, 256)
+        self._conv_bn_bwd(units[r + "conv_cat.conv"], tape, g, 64, 0, None, 0, 0, (dcatb, 256, 0), False)
+        self._conv_bn_bwd(units[r + "conv_res.conv"], tape, g, 64, 0, None, 0, 0, (df, Cin, 0), False)
+        self._conv_bn_bwd(units[r + "branch0.0.conv"], tape, dcatb, 256, 0, None, 0, 0, (df, Cin, 0), True)
+        for bi in (1, 2, 3):
+            d2, d1, d0 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
+            self._conv_bn_bwd(units[r + f"branch{bi}.3.conv"], tape, dcatb, 256, 64 * bi, None, 0, 0, (d2, 64, 0), False)
+            self._conv_bn_bwd(units[r + f"branch{bi}.2.conv"], tape, d2, 64, 0, None, 0, 0, (d1, 64, 0), False)
+            self._conv_bn_bwd(units[r + f"branch{bi}.1.conv"], tape, d1, 64, 0, None, 0, 0, (d0, 64, 0), False)
+            self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, (df, Cin, 0), True)
+        tape["dec"][r]["keep"] = (g, dcatb, dy)         # alive until the streams are joined
+        return df

@@ -314,8 +314,11 @@ def test_trunk_variants_forward_fp32_vs_oracle(cuda, variant):
     mb.eval()
     with torch.no_grad():
         gb = mb(x.to(cuda))
-    for g, r in zip(gb, ref):
-        assert (torch.sigmoid(g.float().cpu()) - torch.sigmoid(r)).abs().max().item() <= 3e-2
+    # Untrained weights give logits of magnitude 10..3000 here, so the sigmoid criterion of the trained model
+    # (test_bf16_prefit_criteria) is ill-posed; the bf16 path is held to max-normalised logit error instead
+    # (measured 0.009..0.033 on a B200).
+    for g, r, name in zip(gb, ref, ("out", "out1", "out2")):
+        assert _maxnorm(g, r) <= 6e-2, (name, _maxnorm(g, r))
 
 
 def test_hiera_l_1024_forward_vs_oracle(cuda):
@@ -335,8 +338,11 @@ def test_hiera_l_1024_forward_vs_oracle(cuda):
     mb.eval()
     with torch.no_grad():
         gb = mb(x.to(cuda))
-    for g, r in zip(gb, ref):
-        assert (torch.sigmoid(g.float().cpu()) - torch.sigmoid(r)).abs().max().item() <= 3e-2
+    # Untrained weights give logits of magnitude 10..3000 here, so the sigmoid criterion of the trained model
+    # (test_bf16_prefit_criteria) is ill-posed; the bf16 path is held to max-normalised logit error instead
+    # (measured 0.009..0.033 on a B200).
+    for g, r, name in zip(gb, ref, ("out", "out1", "out2")):
+        assert _maxnorm(g, r) <= 6e-2, (name, _maxnorm(g, r))
 
 
 def test_predictor_graph_matches_eager(cuda):
