@@ -407,9 +407,17 @@ def run_b200(args):
                 c = by.setdefault(name, [0, 0.0])
                 c[0] += 1
                 c[1] += t
+            gs = {}
+            for name, t, a in rec:
+                if name == "s2u_gemm":
+                    c = gs.setdefault(f"{a[6]}x{a[7]}x{a[8]} flags={a[16]}", [0, 0.0])
+                    c[0] += 1
+                    c[1] += t
             with open(args.profile_out, "w") as f:
                 json.dump({"total_ms": total_ms, "by_op": {k: {"calls": v[0], "ms": v[1]} for k, v in
-                                                             sorted(by.items(), key=lambda kv: -kv[1][1])}}, f, indent=1)
+                                                             sorted(by.items(), key=lambda kv: -kv[1][1])},
+                           "gemm_shapes": {k: {"calls": v[0], "ms": v[1], "us_per_call": v[1] / v[0] * 1e3}
+                                           for k, v in sorted(gs.items(), key=lambda kv: -kv[1][1])}}, f, indent=1)
     if rank == 0:
         line = {"metric": METRIC[args.mode], "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm + 3, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -28,8 +28,10 @@ extern "C" {
  * sam2/modeling/sam2_utils.py:127-132, SAM2UNet.py:57-63), its input gradient (W = pre-transposed weight), and
  * conv forward / input gradient on im2col rows (SAM2UNet.py:83-86).  epi(v): v += bias[n]; pre_out = v;
  * flags&1: v = gelu(v); flags&2: v *= gelu'(aux); flags&4: v += resid; flags&16: C is fp32; flags&32: resid is
- * fp32; flags&64: pre_out receives the FINAL value (compute-dtype copy of C) instead of the pre-activation one.
- * backend: 0 auto (tcgen05 + TMA for bf16), 1 SIMT fp32-FMA, 2 tcgen05 required, 16+bn tcgen05 with N tile bn. */
+ * fp32; flags&64: pre_out receives the FINAL value (compute-dtype copy of C) instead of the pre-activation one;
+ * flags&128: pre_out receives gelu'(v) instead of v (so the backward pass only multiplies); flags&256: v *= aux.
+ * backend: 0 auto (tcgen05 + TMA for bf16: CTA-pair kernel when M > 128), 1 SIMT fp32-FMA, 2 tcgen05 required,
+ * 16+bn one-CTA persistent tcgen05 kernel with N tile bn, 1024+bn CTA-pair (cta_group::2) kernel with N tile bn. */
 int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
              const float* bias, void* pre_out, int ld_pre, const void* aux, int ld_aux, const void* resid,
              int ld_res, int flags, int dtype, int backend, void* stream);
@@ -45,10 +47,14 @@ int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype
 int s2u_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                       long long R, int C, float eps, int x_f32, int dtype, void* stream);
 /* dx = LN'(dy) + dres (dres may be NULL); the affine parameters are frozen (SAM2UNet.py:146-147).
- * Optional fused adapter tail: dx2 = dx * gelu'(pre), colsum[C] += column sums of dx2 (NULL to skip). */
+ * Optional fused adapter tail (SAM2UNet.py:57-63): dx2 = dx * gelu'(h) with pre = h (pre_is_grad 0) or pre = gelu'(h)
+ * as saved by s2u_gemm's GEMM_SAVE_DGELU epilogue (pre_is_grad 1); colsum[C] += column sums of dx2 (NULL to skip).
+ * ws: fp32 workspace of s2u_layernorm_ws_floats(C) elements, required with colsum; zero it once, the kernel leaves
+ * it zeroed.  Calls that may overlap on different streams need separate workspaces. */
+int s2u_layernorm_ws_floats(int C);
 int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      const void* dres, void* dx, const void* pre, void* dx2, float* colsum, long long R, int C,
-                      int x_f32, int dtype, void* stream);
+                      const void* dres, void* dx, const void* pre, void* dx2, float* colsum, float* ws,
+                      int pre_is_grad, long long R, int C, int x_f32, int dtype, void* stream);
 
 /* ---- element-wise helpers --------------------------------------------------------------------------------- */
 int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int dtype, void* stream);
@@ -86,8 +92,10 @@ int s2u_conv_weight_pack(const float* w, void* wf, void* wd, int Cout, int Cin, 
                          void* stream);
 
 /* ---- BatchNorm2d, eps 1e-5, momentum 0.1 (SAM2UNet.py:80,85,18,21) ---------------------------------------- */
-/* `sums`: fp64 workspace of 2C accumulators + 1 ticket word, zero on entry, left zero by the finalising kernel.
+/* `sums`: fp64 workspace of s2u_bn_ws_doubles(C) elements (replicated accumulators + 1 ticket word), zero on entry,
+ * left zero by the finalising kernel.
  * s2u_bn_stats_finalize = training-mode statistics + finalisation in ONE launch (the last block finalises). */
+int s2u_bn_ws_doubles(int C);
 int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream);
 int s2u_bn_stats_finalize(const void* x, int ldx, double* sums, const float* gamma, const float* beta,
                           float* running_mean, float* running_var, long long* num_batches, float* scale, float* shift,

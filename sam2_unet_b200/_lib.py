@@ -20,7 +20,8 @@ SIGNATURES = {
     "s2u_gemm_wgrad": [P, I, P, I, P, I, L, I, I, I, I, I, P],
     "s2u_colsum": [P, I, P, L, I, I, P],
     "s2u_layernorm_fwd": [P, P, P, P, P, P, L, I, F, I, I, P],
-    "s2u_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, L, I, I, I, P],
+    "s2u_layernorm_ws_floats": [I],
+    "s2u_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P],
     "s2u_dgelu_mul": [P, P, P, L, I, P],
     "s2u_add": [P, P, P, L, I, P],
     "s2u_maxpool2_fwd": [P, P, I, I, I, I, I, P],
@@ -32,6 +33,7 @@ SIGNATURES = {
     "s2u_patch_embed": [P, P, P, P, P, I, P, I, I, I, I, P],
     "s2u_im2col": [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "s2u_conv_weight_pack": [P, P, P, I, I, I, I, I, P],
+    "s2u_bn_ws_doubles": [I],
     "s2u_bn_stats": [P, I, P, L, I, I, P],
     "s2u_bn_stats_finalize": [P, I, P, P, P, P, P, P, P, P, P, P, L, I, F, F, I, P],
     "s2u_bn_finalize": [P, P, P, P, P, P, P, P, P, P, L, I, F, F, I, P],

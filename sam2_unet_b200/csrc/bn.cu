@@ -7,11 +7,28 @@
 //
 // Launch count matters here (66 layers, most of them tiny): the per-channel finalisation runs inside the reduction
 // kernel, in whichever block finishes last ("threadfence reduction"), so training forward is 2 launches per layer
-// (statistics+finalize, apply) and backward is 2 (reduce+finalize, apply).  The fp64 workspace `sums` holds 2C
-// accumulators followed by one ticket word; it is left zeroed for the next use.
+// (statistics+finalize, apply) and backward is 2 (reduce+finalize, apply).
+//
+// The fp64 workspace `sums` holds BN_NREP replicas of the 2C accumulators followed by one ticket word
+// (s2u_bn_ws_doubles(C) doubles); it is left zeroed for the next use.  Block b adds into replica b % BN_NREP: with a
+// single set, the ~1,500 blocks of a 88x88x12 map all add into the same 128 addresses and L2 serialises them
+// (measured 29 us for a 12 MB pass); the reduction grids are also persistent (<= 4 blocks per SM, grid-stride over
+// rows with four loads in flight per thread) so that each block contributes once.
 #include "common.cuh"
 
-constexpr int BN_ROWS = 64;   // rows per block in the reduction kernels
+constexpr int BN_NREP = 16;   // replicated accumulator sets
+constexpr int BN_UNROLL = 4;  // independent row loads in flight per thread
+
+// sum of one accumulator over the replicas; clears them
+__device__ __forceinline__ double rep_sum_clear(volatile double* sums, int i, int C2) {
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < BN_NREP; ++r) {
+    t += sums[r * C2 + i];
+    sums[r * C2 + i] = 0.0;
+  }
+  return t;
+}
 
 struct BnFin {
   const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches;
@@ -25,16 +42,14 @@ __device__ __forceinline__ void bn_finalize_block(volatile double* sums, const B
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     if (training) {
-      const double m = sums[c] / (double)M;
-      double var = sums[C + c] / (double)M - m * m;
+      const double m = rep_sum_clear(sums, c, 2 * C) / (double)M;
+      double var = rep_sum_clear(sums, C + c, 2 * C) / (double)M - m * m;
       if (var < 0) var = 0;
       mean = (float)m;
       rstd = (float)(1.0 / sqrt(var + (double)f.eps));
       const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
       f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
       f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
-      sums[c] = 0.0;
-      sums[C + c] = 0.0;
     } else {
       mean = f.running_mean[c];
       rstd = rsqrtf(f.running_var[c] + f.eps);
@@ -56,13 +71,11 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, BnFin f, long long
 __device__ __forceinline__ void bn_bwd_finalize_block(volatile double* sums, float* dgamma, float* dbeta, float* c1,
                                                       float* c2, long long M, int C) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double sb = sums[c], sg = sums[C + c];
+    const double sb = rep_sum_clear(sums, c, 2 * C), sg = rep_sum_clear(sums, C + c, 2 * C);
     dbeta[c] += (float)sb;
     dgamma[c] += (float)sg;
     c1[c] = (float)(sb / (double)M);
     c2[c] = (float)(sg / (double)M);
-    sums[c] = 0.0;
-    sums[C + c] = 0.0;
   }
 }
 
@@ -92,10 +105,11 @@ __device__ __forceinline__ void reduce_to_sums(float* red, const float* s, const
     }
   }
   __syncthreads();
+  double* rep = sums + (size_t)(blockIdx.x % BN_NREP) * 2 * C;
   for (int i = threadIdx.x; i < 2 * C; i += 256) {
     float t = 0.f;
     for (int k = 0; k < nsub; ++k) t += red[k * 2 * C + i];
-    atomicAdd(sums + i, (double)t);
+    atomicAdd(rep + i, (double)t);
   }
 }
 
@@ -110,16 +124,26 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  const long long r0 = (long long)blockIdx.x * BN_ROWS;
   if (sub < nsub) {
-    for (long long r = r0 + sub; r < min(M, r0 + BN_ROWS); r += nsub) {
+    const long long step = (long long)gridDim.x * nsub;
+    long long r = (long long)blockIdx.x * nsub + sub;
+    for (; r + (BN_UNROLL - 1) * step < M; r += BN_UNROLL * step) {
+      F8 v[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) v[u] = ld8(x + (r + u * step) * ldx + g * 8);
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[u].v[j]; q[j] = fmaf(v[u].v[j], v[u].v[j], q[j]); }
+    }
+    for (; r < M; r += step) {
       const F8 v = ld8(x + r * ldx + g * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; q[j] = fmaf(v.v[j], v.v[j], q[j]); }
     }
   }
   reduce_to_sums(red, s, q, sums, C, g, sub, nsub);
-  if (fuse_finalize && last_block(reinterpret_cast<unsigned int*>(sums + 2 * C))) bn_finalize_block(sums, fin, M, C, 1);
+  if (fuse_finalize && last_block(reinterpret_cast<unsigned int*>(sums + BN_NREP * 2 * C))) bn_finalize_block(sums, fin, M, C, 1);
 }
 
 // out = act(x * scale + shift (+ resid)); out may be a channel slice of a wider (concat) buffer via ld_out
@@ -185,26 +209,37 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  const long long r0 = (long long)blockIdx.x * BN_ROWS;
   if (sub < nsub) {
     const F8 mu = ld8(mean + g * 8), rs = ld8(rstd + g * 8);
-    for (long long r = r0 + sub; r < min(M, r0 + BN_ROWS); r += nsub) {
-      F8 d = ld8(dy + r * ld_dy + g * 8);
-      const F8 v = ld8(x + r * ldx + g * 8);
-      if (y) {
-        const F8 yy = ld8(y + r * ld_y + g * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d.v[j] = yy.v[j] > 0.f ? d.v[j] : 0.f;
-      }
+    const long long step = (long long)gridDim.x * nsub;
+    long long r = (long long)blockIdx.x * nsub + sub;
+    auto acc = [&](F8 d, const F8& v, const F8& yy) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s[j] += d.v[j];
-        q[j] = fmaf(d.v[j], (v.v[j] - mu.v[j]) * rs.v[j], q[j]);
+        const float dj = yy.v[j] > 0.f ? d.v[j] : 0.f;
+        s[j] += dj;
+        q[j] = fmaf(dj, (v.v[j] - mu.v[j]) * rs.v[j], q[j]);
       }
+    };
+    F8 one;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) one.v[j] = 1.f;
+    for (; r + (BN_UNROLL - 1) * step < M; r += BN_UNROLL * step) {
+      F8 d[BN_UNROLL], v[BN_UNROLL], yy[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const long long ru = r + u * step;
+        d[u] = ld8(dy + ru * ld_dy + g * 8);
+        v[u] = ld8(x + ru * ldx + g * 8);
+        yy[u] = y ? ld8(y + ru * ld_y + g * 8) : one;
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) acc(d[u], v[u], yy[u]);
     }
+    for (; r < M; r += step) acc(ld8(dy + r * ld_dy + g * 8), ld8(x + r * ldx + g * 8), y ? ld8(y + r * ld_y + g * 8) : one);
   }
   reduce_to_sums(red, s, q, sums, C, g, sub, nsub);
-  if (last_block(reinterpret_cast<unsigned int*>(sums + 2 * C))) bn_bwd_finalize_block(sums, dgamma, dbeta, c1, c2, M, C);
+  if (last_block(reinterpret_cast<unsigned int*>(sums + BN_NREP * 2 * C))) bn_bwd_finalize_block(sums, dgamma, dbeta, c1, c2, M, C);
 }
 
 // dx = gamma * rstd * (g - c1 - xhat * c2)
@@ -246,8 +281,19 @@ static inline int grid_for(long long n, int threads) {
   return (int)g;
 }
 static inline bool bn_c_ok(int C) { return C >= 8 && (C & 7) == 0 && (C >> 3) <= 256; }
+// reduction grid: every block gets at least BN_UNROLL rows per row lane, at most 4 blocks per SM
+static inline int bn_reduce_grid(long long M, int C) {
+  const int nsub = 256 / (C >> 3);
+  long long g = (M + (long long)nsub * BN_UNROLL - 1) / ((long long)nsub * BN_UNROLL);
+  if (g > 148 * 4) g = 148 * 4;
+  if (g < 1) g = 1;
+  return (int)g;
+}
 
 extern "C" {
+
+// size of the fp64 workspace `sums` of the functions below (replicated accumulators + ticket)
+int s2u_bn_ws_doubles(int C) { return BN_NREP * 2 * C + 1; }
 
 // statistics only (the caller finalises with s2u_bn_finalize)
 int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream) {
@@ -257,14 +303,14 @@ int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int d
   BnFin none{};
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_stats_kernel<T>);
-    bn_stats_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 0, none);
+    bn_stats_kernel<T><<<bn_reduce_grid(M, C), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 0, none);
   })
   S2U_LAUNCH_CHECK();
   return 0;
 }
 
 // training forward in ONE launch: statistics + (last block) scale/shift, saved mean/rstd, running-stat update.
-// `sums` must hold 2C+1 doubles (accumulators + ticket), zero on entry; it is zero again on exit.
+// `sums` must hold s2u_bn_ws_doubles(C) doubles, zero on entry; it is zero again on exit.
 int s2u_bn_stats_finalize(const void* x, int ldx, double* sums, const float* gamma, const float* beta,
                           float* running_mean, float* running_var, long long* num_batches, float* scale, float* shift,
                           float* save_mean, float* save_rstd, long long M, int C, float eps, float momentum, int dtype,
@@ -275,7 +321,7 @@ int s2u_bn_stats_finalize(const void* x, int ldx, double* sums, const float* gam
   BnFin f{gamma, beta, running_mean, running_var, num_batches, scale, shift, save_mean, save_rstd, eps, momentum};
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_stats_kernel<T>);
-    bn_stats_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 1, f);
+    bn_stats_kernel<T><<<bn_reduce_grid(M, C), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 1, f);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -314,7 +360,7 @@ int s2u_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, void* g, in
 }
 
 // y == null: plain BN backward; y given: backward through relu(bn(x)) using the saved output for the mask.
-// `sums`: 2C+1 doubles, zero on entry and on exit.
+// `sums`: s2u_bn_ws_doubles(C) doubles, zero on entry and on exit.
 int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x, int ldx, const float* mean,
                const float* rstd, const float* gamma, double* sums, float* dgamma, float* dbeta, float* c1, float* c2,
                void* dx, int ld_dx, long long M, int C, int dtype, void* stream) {
@@ -324,7 +370,7 @@ int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x
   const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_bwd_reduce_kernel<T>);
-    bn_bwd_reduce_kernel<T><<<ceil_div(M, BN_ROWS), 256, smem, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
+    bn_bwd_reduce_kernel<T><<<bn_reduce_grid(M, C), 256, smem, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
                                                                     (const T*)x, ldx, mean, rstd, sums, dgamma, dbeta,
                                                                     c1, c2, M, C);
   })

@@ -107,8 +107,10 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // GEMM_OUT_F32 / GEMM_RESID_F32: C / resid are fp32 although the operands are bf16 (the residual stream of the trunk is
 // kept in fp32 in bf16 mode); GEMM_PRE_FINAL: pre_out receives the FINAL value (a compute-dtype copy of C) instead of
 // the pre-activation one.
+// GEMM_SAVE_DGELU: pre_out receives gelu'(pre-activation) instead of the pre-activation, so that the backward GEMM
+// only multiplies by it (GEMM_MULAUX: result *= aux) and the erf/exp are evaluated once, in the forward epilogue.
 enum GemmFlags { GEMM_GELU = 1, GEMM_DGELU = 2, GEMM_RESID = 4, GEMM_OUT_F32 = 16, GEMM_RESID_F32 = 32,
-                 GEMM_PRE_FINAL = 64 };
+                 GEMM_PRE_FINAL = 64, GEMM_SAVE_DGELU = 128, GEMM_MULAUX = 256 };
 struct GemmEpi {
   const float* bias;   // [N] or null
   void* pre_out;       // T [M, ld_pre]: value before the activation (saved for GELU'), or null

@@ -34,9 +34,11 @@ struct EpiView {
 template <typename T>
 __device__ __forceinline__ float epi_scalar(const EpiView<T>& e, float v, long long row, int col) {
   if (e.bias) v += e.bias[col];
-  if (e.pre_out && !(e.flags & GEMM_PRE_FINAL)) stf(e.pre_out + row * e.ld_pre + col, v);
+  if (e.pre_out && !(e.flags & GEMM_PRE_FINAL))
+    stf(e.pre_out + row * e.ld_pre + col, (e.flags & GEMM_SAVE_DGELU) ? dgelu_f(v) : v);
   if (e.flags & GEMM_GELU) v = gelu_f(v);
   if (e.flags & GEMM_DGELU) v *= dgelu_f(ldf(e.aux + row * e.ld_aux + col));
+  if (e.flags & GEMM_MULAUX) v *= ldf(e.aux + row * e.ld_aux + col);
   if (e.flags & GEMM_RESID) {
     if (e.flags & GEMM_RESID_F32) v += reinterpret_cast<const float*>(e.resid)[row * e.ld_res + col];
     else v += ldf(e.resid + row * e.ld_res + col);
@@ -432,22 +434,77 @@ __device__ __forceinline__ float dgelu_fast(float x) {
 
 constexpr int WS_EPI_WARPS = 8;
 constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
-constexpr int EPI_TILE_BYTES = 32 * 64;        // per epilogue warp: 32 rows x 32 bf16, 16-byte chunks XOR-swizzled
+constexpr int EPI_BUF_BYTES = 32 * 64;                 // one staging tile: 32 rows x 64 bytes, 16-byte chunks XOR-swizzled
+constexpr int EPI_WARP_BYTES = 5 * EPI_BUF_BYTES;      // per epilogue warp: side input [chunk parity][half] + one output tile
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;            // shared::cluster address of the same offset in the pair's even CTA
 
 template <int BN, int STAGES>
 struct CfgWS {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + WS_EPI_WARPS * EPI_TILE_BYTES + 1024;
+  static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(BM >> 4) << 24);
 };
+// CTA pair (cta_group::2): the pair owns a 256 x BN tile; each CTA stages its own 128 rows of A and BN/2 rows of B and
+// keeps its own 128 x BN half of the accumulator, so the operand bytes each SM pulls from L2 per FLOP drop by a third
+template <int BN, int STAGES>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+  static constexpr int ACC_COLS = BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)((2 * BM) >> 4) << 24);
+};
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// both CTAs of a pair load into their own smem; the bytes are accounted on the even CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives at the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // staging tile: row r (0..31), 16-byte chunk c (0..3) at r*64 + ((c ^ ((r >> 1) & 3)) << 4): conflict-free both for
@@ -463,39 +520,235 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
-// global [32 rows x 32 cols] (row pitch ld) <-> staging tile; 4 lanes move one 64-byte row segment
-__device__ __forceinline__ void g2s_tile(uint32_t stg, const bf16* __restrict__ src, long long ld, int rows_ok,
-                                         int cols_ok, int lane) {
+// staging tile <-> global rows of 64 bytes (32 bf16 or 16 fp32), row pitch in bytes; 4 lanes move one row
+__device__ __forceinline__ void g2s_async(uint32_t stg, const char* __restrict__ src, long long pitch, int rows_ok,
+                                          int bytes_ok, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + (lane >> 2), c = lane & 3;
-    if (r < rows_ok && c * 8 < cols_ok)
-      sts16(stg_addr(stg, r, c), *reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8));
+    if (r < rows_ok && c * 16 < bytes_ok) cp_async16(stg_addr(stg, r, c), src + (long long)r * pitch + c * 16);
   }
 }
-__device__ __forceinline__ void s2g_tile(uint32_t stg, bf16* __restrict__ dst, long long ld, int rows_ok, int cols_ok,
-                                         int lane) {
+__device__ __forceinline__ void s2g_rows(uint32_t stg, char* __restrict__ dst, long long pitch, int rows_ok,
+                                         int bytes_ok, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + (lane >> 2), c = lane & 3;
-    if (r < rows_ok && c * 8 < cols_ok)
-      *reinterpret_cast<uint4*>(dst + (long long)r * ld + c * 8) = lds16(stg_addr(stg, r, c));
+    if (r < rows_ok && c * 16 < bytes_ok)
+      *reinterpret_cast<uint4*>(dst + (long long)r * pitch + c * 16) = lds16(stg_addr(stg, r, c));
   }
 }
-// this thread's row of the staging tile <-> 32 floats
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  return u;
+}
+// this thread's row of the staging tile <- 32 floats as bf16
 __device__ __forceinline__ void regs_to_stage(uint32_t stg, int lane, const float* v) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-    sts16(stg_addr(stg, lane, j), u);
-  }
+  for (int j = 0; j < 4; ++j) sts16(stg_addr(stg, lane, j), pack8(v + 8 * j));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Epilogue of one warp over all tiles of its CTA (shared by the one-CTA and the CTA-pair kernels).  TMEM lane quarter
+// q = warp % 4 (hardware restriction of tcgen05.ld); the two warps of a quarter (half = 0/1) take alternate 32-column
+// chunks.  Every global access goes through a swizzled staging tile so that 4 lanes move one contiguous 64-byte row
+// segment.  The side input of a chunk (GELU' operand, residual: bf16 32 columns, or the fp32 residual stream: 2 x 16
+// columns) is fetched with cp.async one chunk ahead, across tile boundaries, so its latency hides behind the
+// previous chunk's arithmetic instead of stalling the two warps an SM sub-partition has.
 // F32S = true: "stream" epilogue (fp32 output and/or fp32 residual and/or a compute-dtype copy of the final value, no
 // GELU'); false: everything in the compute dtype.  Two instantiations keep each epilogue's register footprint small.
+// ------------------------------------------------------------------------------------------------------------
+struct EpiTiles {
+  int first, stride, num_tiles, m_tiles;   // this CTA's tile walk
+  int tile_rows, row_off;                  // rows per (pair) tile and this CTA's row offset inside it
+  uint32_t tmem_base;
+  int acc_cols;
+  uint32_t tfull0, tempty0;                // barrier addresses (tempty0 is a shared::cluster address)
+};
+
+template <int BN, bool F32S>
+__device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, int q, int half, int lane,
+                                              bf16* __restrict__ C, int ldc, int M, int N,
+                                              const EpiView<bf16>& epi) {
+  const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
+  const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;              // residual in the compute dtype
+  const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
+  const bool dgelu = !F32S && (epi.flags & GEMM_DGELU), mulaux = !F32S && (epi.flags & GEMM_MULAUX);
+  const bf16* side16 = (dgelu || mulaux) ? epi.aux : (resid_t ? epi.resid : nullptr);
+  const long long ld16 = (dgelu || mulaux) ? epi.ld_aux : epi.ld_res;
+  const float* side32 = resid_f32 ? reinterpret_cast<const float*>(epi.resid) : nullptr;
+  const bool has_side = side16 != nullptr || side32 != nullptr;
+  const int nch = (BN - half * 32 + 63) / 64;                               // this warp's chunks per tile (0 when BN == 32)
+  const uint32_t so = stg + 4 * EPI_BUF_BYTES;                              // output staging tile
+
+  auto prefetch = [&](int tile, int ci, int par) {
+    const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
+    const int col0 = (tile / t.m_tiles) * BN + half * 32 + ci * 64;
+    const int rows_ok = (int)min((long long)32, (long long)M - row0), cols_ok = min(32, N - col0);
+    if (rows_ok <= 0 || cols_ok <= 0) return;
+    const uint32_t b = stg + (uint32_t)(par * 2 * EPI_BUF_BYTES);
+    if (side16) {
+      g2s_async(b, reinterpret_cast<const char*>(side16 + row0 * ld16 + col0), ld16 * 2, rows_ok, cols_ok * 2, lane);
+    } else {
+      const char* s = reinterpret_cast<const char*>(side32 + row0 * epi.ld_res + col0);
+      g2s_async(b, s, (long long)epi.ld_res * 4, rows_ok, min(cols_ok, 16) * 4, lane);
+      if (cols_ok > 16) g2s_async(b + EPI_BUF_BYTES, s + 64, (long long)epi.ld_res * 4, rows_ok, (cols_ok - 16) * 4, lane);
+    }
+  };
+  // bf16 rows of this warp's chunk: registers -> output staging tile -> global
+  auto store16 = [&](const float* v, bf16* dst, long long ld, int rows_ok, int cols_ok) {
+    regs_to_stage(so, lane, v);
+    __syncwarp();
+    s2g_rows(so, reinterpret_cast<char*>(dst), ld * 2, rows_ok, cols_ok * 2, lane);
+    __syncwarp();
+  };
+
+  uint32_t lt = 0, cc = 0;
+  if (has_side && nch > 0 && t.first < t.num_tiles) prefetch(t.first, 0, 0);
+  cp_async_commit();
+  for (int tile = t.first; tile < t.num_tiles; tile += t.stride, ++lt) {
+    const int acc = lt & 1;
+    mbar_wait(t.tfull0 + 8u * acc, (lt >> 1) & 1u);
+    tc_fence_after();
+    const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
+    const int n0 = (tile / t.m_tiles) * BN;
+    const int rows_ok = (int)min((long long)32, (long long)M - row0);       // may be <= 0
+#pragma unroll 1
+    for (int ci = 0; ci < nch; ++ci, ++cc) {
+      const int par = cc & 1;
+      const int c0 = half * 32 + ci * 64, col0 = n0 + c0;
+      const int cols_ok = min(32, N - col0);                                // may be <= 0
+      const bool live = rows_ok > 0 && cols_ok > 0;                         // warp-uniform
+      if (has_side) {                                                       // next chunk's side input
+        if (ci + 1 < nch) prefetch(tile, ci + 1, par ^ 1);
+        else if (tile + t.stride < t.num_tiles) prefetch(tile + t.stride, 0, par ^ 1);
+      }
+      cp_async_commit();
+      float v[32];
+      if (live) {
+        uint32_t r[32];
+        tc_ld32(t.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * t.acc_cols + c0), r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
+      cp_async_wait<1>();                                                   // this chunk's side input has landed
+      __syncwarp();
+      if (!live) continue;
+      const uint32_t h0 = stg + (uint32_t)(par * 2 * EPI_BUF_BYTES), h1 = h0 + EPI_BUF_BYTES;
+      if (epi.bias) {
+        if (cols_ok == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
+        }
+      }
+      if ((epi.flags & GEMM_GELU) && epi.pre_out && !pre_final && (epi.flags & GEMM_SAVE_DGELU)) {
+        // v <- gelu(v), pre_out <- gelu'(v): both from one erf evaluation
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float x = v[8 * j + e];
+            const float cdf = fmaf(0.5f, erf_poly(x * 0.70710678118654752f), 0.5f);
+            d[e] = fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf);
+            v[8 * j + e] = x * cdf;
+          }
+          sts16(stg_addr(so, lane, j), pack8(d));
+        }
+        __syncwarp();
+        s2g_rows(so, reinterpret_cast<char*>(epi.pre_out + row0 * epi.ld_pre + col0), (long long)epi.ld_pre * 2, rows_ok,
+                 cols_ok * 2, lane);
+        __syncwarp();
+      } else {
+        if (epi.pre_out && !pre_final) store16(v, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok);
+        if (epi.flags & GEMM_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+      }
+      if (side16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = lds16(stg_addr(h0, lane, j));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            if (dgelu) {
+              v[j * 8 + 2 * e] *= dgelu_fast(f.x);
+              v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
+            } else if (mulaux) {
+              v[j * 8 + 2 * e] *= f.x;
+              v[j * 8 + 2 * e + 1] *= f.y;
+            } else {
+              v[j * 8 + 2 * e] += f.x;
+              v[j * 8 + 2 * e + 1] += f.y;
+            }
+          }
+        }
+      }
+      if (F32S && side32) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (cols_ok <= hh * 16) break;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = lds16(stg_addr(hh ? h1 : h0, lane, j));
+            v[hh * 16 + 4 * j] += __uint_as_float(u.x);
+            v[hh * 16 + 4 * j + 1] += __uint_as_float(u.y);
+            v[hh * 16 + 4 * j + 2] += __uint_as_float(u.z);
+            v[hh * 16 + 4 * j + 3] += __uint_as_float(u.w);
+          }
+        }
+      }
+      if (F32S && out_f32) {
+        // 16 fp32 columns per staging tile; with an fp32 residual each thread overwrites exactly the row it just read
+        char* cdst = reinterpret_cast<char*>(reinterpret_cast<float*>(C) + row0 * ldc + col0);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cok = cols_ok - hh * 16;
+          if (cok <= 0) break;
+          const uint32_t x = side32 ? (hh ? h1 : h0) : (hh ? h1 : so);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts16(stg_addr(x, lane, j),
+                  make_uint4(__float_as_uint(v[hh * 16 + 4 * j]), __float_as_uint(v[hh * 16 + 4 * j + 1]),
+                             __float_as_uint(v[hh * 16 + 4 * j + 2]), __float_as_uint(v[hh * 16 + 4 * j + 3])));
+          __syncwarp();
+          s2g_rows(x, cdst + hh * 64, (long long)ldc * 4, rows_ok, min(cok, 16) * 4, lane);
+        }
+        __syncwarp();
+        if (epi.pre_out && pre_final)                                       // compute-dtype copy of the final value
+          store16(v, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok);
+        continue;
+      }
+      regs_to_stage(so, lane, v);
+      __syncwarp();
+      s2g_rows(so, reinterpret_cast<char*>(C + row0 * ldc + col0), (long long)ldc * 2, rows_ok, cols_ok * 2, lane);
+      if (F32S && epi.pre_out && pre_final)
+        s2g_rows(so, reinterpret_cast<char*>(epi.pre_out + row0 * epi.ld_pre + col0), (long long)epi.ld_pre * 2, rows_ok,
+                 cols_ok * 2, lane);
+      __syncwarp();
+    }
+    // hand the accumulator back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(t.tempty0 + 8u * acc);
+  }
+  cp_async_wait<0>();
+}
+
 template <int BN, int STAGES, bool F32S>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                    const __grid_constant__ CUtensorMap tma_b,
@@ -508,7 +761,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_base = smem_base + ((WS_EPI_WARPS * EPI_TILE_BYTES + 1023) & ~1023);
+  const uint32_t stage_base = smem_base + cfg::EPI_BYTES;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -585,155 +838,132 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
       }
     }
   } else {
-    // ---- 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware restriction of tcgen05.ld); the two warps of a
-    //      quarter take alternate 32-column chunks.  Every global access goes through the warp's swizzled staging tile
-    //      (32 rows x 64 bytes) so that 4 lanes move one contiguous 64-byte row segment: 32 bf16 columns per pass, or 16
-    //      fp32 columns per pass for the fp32 residual stream (F32S).
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const uint32_t stg = smem_base + (uint32_t)((warp - 2) * EPI_TILE_BYTES);
-    const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
-    const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;            // residual in the compute dtype
-    const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
-    // bf16 side tile -> this thread's 32 values (through the staging tile)
-    auto add_bf16_tile = [&](const bf16* src, long long ld, long long row0, int col0, int rows_ok, int cols_ok, float* v,
-                             bool dgelu) {
-      g2s_tile(stg, src + row0 * ld + col0, ld, rows_ok, cols_ok, lane);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = lds16(stg_addr(stg, lane, j));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h[e]);
-          if (dgelu) {
-            v[j * 8 + 2 * e] *= dgelu_fast(f.x);
-            v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
-          } else {
-            v[j * 8 + 2 * e] += f.x;
-            v[j * 8 + 2 * e + 1] += f.y;
-          }
-        }
-      }
-      __syncwarp();
-    };
-    uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
-      const int acc = lt & 1;
-      mbar_wait(tfull_bar(acc), (lt >> 1) & 1u);
-      tc_fence_after();
-      const long long row0 = (long long)m0 + q * 32;
-      const int rows_ok = (int)min((long long)32, (long long)M - row0);     // may be <= 0
-#pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        const int col0 = n0 + c0;
-        const int cols_ok = min(32, N - col0);                              // may be <= 0
-        if (rows_ok <= 0 || cols_ok <= 0) continue;                         // warp-uniform
-        float v[32];
-        {
-          uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * cfg::ACC_COLS + c0), r);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        }
-        if (epi.bias) {
-          if (cols_ok == 32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
-          }
-        }
-        if (epi.pre_out && !pre_final) {
-          regs_to_stage(stg, lane, v);
-          __syncwarp();
-          s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
-          __syncwarp();
-        }
-        if (epi.flags & GEMM_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-        }
-        if (!F32S && (epi.flags & GEMM_DGELU)) add_bf16_tile(epi.aux, epi.ld_aux, row0, col0, rows_ok, cols_ok, v, true);
-        if (resid_t) add_bf16_tile(epi.resid, epi.ld_res, row0, col0, rows_ok, cols_ok, v, false);
-        if (F32S && resid_f32) {
-          const float* rsrc = reinterpret_cast<const float*>(epi.resid) + row0 * epi.ld_res + col0;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {                                  // 16 fp32 columns per pass
-            const int cok = cols_ok - hh * 16;
-            if (cok <= 0) break;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = i * 8 + (lane >> 2), c = lane & 3;
-              if (r < rows_ok && c * 4 < cok)
-                sts16(stg_addr(stg, r, c),
-                      __ldg(reinterpret_cast<const uint4*>(rsrc + (long long)r * epi.ld_res + hh * 16 + c * 4)));
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = lds16(stg_addr(stg, lane, j));
-              v[hh * 16 + 4 * j] += __uint_as_float(u.x);
-              v[hh * 16 + 4 * j + 1] += __uint_as_float(u.y);
-              v[hh * 16 + 4 * j + 2] += __uint_as_float(u.z);
-              v[hh * 16 + 4 * j + 3] += __uint_as_float(u.w);
-            }
-            __syncwarp();
-          }
-        }
-        if (F32S && out_f32) {
-          float* cdst = reinterpret_cast<float*>(C) + row0 * ldc + col0;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int cok = cols_ok - hh * 16;
-            if (cok <= 0) break;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts16(stg_addr(stg, lane, j),
-                    make_uint4(__float_as_uint(v[hh * 16 + 4 * j]), __float_as_uint(v[hh * 16 + 4 * j + 1]),
-                               __float_as_uint(v[hh * 16 + 4 * j + 2]), __float_as_uint(v[hh * 16 + 4 * j + 3])));
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = i * 8 + (lane >> 2), c = lane & 3;
-              if (r < rows_ok && c * 4 < cok)
-                *reinterpret_cast<uint4*>(cdst + (long long)r * ldc + hh * 16 + c * 4) = lds16(stg_addr(stg, r, c));
-            }
-            __syncwarp();
-          }
-          if (epi.pre_out && pre_final) {                                   // compute-dtype copy of the final value
-            regs_to_stage(stg, lane, v);
-            __syncwarp();
-            s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
-            __syncwarp();
-          }
-          continue;
-        }
-        regs_to_stage(stg, lane, v);
-        __syncwarp();
-        s2g_tile(stg, C + row0 * ldc + col0, ldc, rows_ok, cols_ok, lane);
-        if (F32S && epi.pre_out && pre_final)
-          s2g_tile(stg, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok, lane);
-        __syncwarp();
-      }
-      // hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-    }
+    EpiTiles t;
+    t.first = blockIdx.x; t.stride = gridDim.x; t.num_tiles = num_tiles; t.m_tiles = m_tiles;
+    t.tile_rows = BM; t.row_off = 0;
+    t.tmem_base = tmem_base; t.acc_cols = cfg::ACC_COLS;
+    t.tfull0 = tfull_bar(0); t.tempty0 = tempty_bar(0);
+    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
+                            ldc, M, N, epi);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (launched as clusters of 2 = one TPC): tcgen05.mma.cta_group::2 with UMMA M = 256.  Roles as
+// above in BOTH CTAs, except that only the even CTA issues the MMAs: it waits on ITS full barrier, which collects the
+// TMA bytes of both CTAs, and its commits are multicast so that the smem-slot and accumulator barriers flip in both.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool F32S>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                     const __grid_constant__ CUtensorMap tma_b,
+                                                                     bf16* __restrict__ C, int ldc, int M, int N,
+                                                                     int K, EpiView<bf16> epi) {
+  using cfg = Cfg2<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base + cfg::EPI_BYTES;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);                   // used in the even CTA: its producer's arrive + both CTAs' bytes
+      mbar_init(empty_bar(s), 1);                  // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);                  // multicast commit
+      mbar_init(tempty_bar(a), 2 * WS_EPI_WARPS);  // used in the even CTA: the epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int m0 = (tile % m_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile / m_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (uint32_t)cfg::STAGE_BYTES);
+          const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
+          tma_load_2d_pair(sa, &tma_a, full_bar(s), kb * BK, m0);
+          tma_load_2d_pair(sa + cfg::A_BYTES, &tma_b, full_bar(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      uint32_t it = 0, lt = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), ((lt >> 1) & 1u) ^ 1u);     // both CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * cfg::ACC_COLS);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sa);
+          const uint64_t bdesc = smem_desc_sw128(sa + cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_bf16_pair(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), cfg::IDESC,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_pair(empty_bar(s));
+        }
+        tc_commit_pair(tfull_bar(acc));
+      }
+    }
+  } else {
+    EpiTiles t;
+    t.first = pair; t.stride = npairs; t.num_tiles = num_tiles; t.m_tiles = m_tiles;
+    t.tile_rows = 2 * BM; t.row_off = (int)rank * BM;
+    t.tmem_base = tmem_base; t.acc_cols = cfg::ACC_COLS;
+    t.tfull0 = tfull_bar(0); t.tempty0 = tempty_bar(0) & PEER_MASK;
+    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
+                            ldc, M, N, epi);
+  }
+  tc_fence_before();
+  cluster_sync_all();          // nobody leaves while the partner may still read its smem or signal its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)cfg::TMEM_COLS)
                  : "memory");
   }
@@ -977,13 +1207,58 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   if (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) {
-    if (e.flags & GEMM_DGELU) return S2U_EUNSUPPORTED;
+    if (e.flags & (GEMM_DGELU | GEMM_MULAUX)) return S2U_EUNSUPPORTED;
     gemm_umma_ws_kernel<BN, STAGES, true><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
                                                                                   EpiView<bf16>(e));
   } else {
     gemm_umma_ws_kernel<BN, STAGES, false><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
                                                                                    EpiView<bf16>(e));
   }
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+// CTA-pair kernel: clusters of 2, one pair per TPC
+template <int BN, int STAGES>
+static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
+                       const GemmEpi& e, cudaStream_t st) {
+  using cfg = Cfg2<BN, STAGES>;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, W, N, K, ldw, BN / 2);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_pair_kernel<BN, STAGES, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(gemm_umma_pair_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                cfg::SMEM_BYTES);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  const int tiles = ceil_div(M, 2 * BM) * ceil_div(N, BN);
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(2 * pairs);
+  lc.blockDim = dim3(WS_THREADS);
+  lc.dynamicSmemBytes = cfg::SMEM_BYTES;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  const bool f32s = e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL);
+  if (f32s && (e.flags & (GEMM_DGELU | GEMM_MULAUX))) return S2U_EUNSUPPORTED;
+  cudaError_t ce = f32s ? cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STAGES, true>, ma, mb, C, ldc, M, N, K,
+                                             EpiView<bf16>(e))
+                        : cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STAGES, false>, ma, mb, C, ldc, M, N, K,
+                                             EpiView<bf16>(e));
+  if (ce != cudaSuccess) return (int)ce;
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -996,7 +1271,7 @@ static bool supported(const void* A, int lda, const void* W, int ldw, const void
   if (!aligned16(A) || !aligned16(W) || !aligned16(C)) return false;
   if ((lda % 8) || (ldw % 8) || (ldc % 8) || (N % 8) || K < 8) return false;
   if (e.pre_out && (!aligned16(e.pre_out) || (e.ld_pre % 8))) return false;
-  if ((e.flags & GEMM_DGELU) && (!aligned16(e.aux) || (e.ld_aux % 8))) return false;
+  if ((e.flags & (GEMM_DGELU | GEMM_MULAUX)) && (!aligned16(e.aux) || (e.ld_aux % 8))) return false;
   if ((e.flags & GEMM_RESID) && (!aligned16(e.resid) || (e.ld_res % 8))) return false;
   if ((e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) && false) return false;
   return true;
@@ -1062,24 +1337,36 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
              void* pre_out, int ld_pre, const void* aux, int ld_aux, const void* resid, int ld_res, int flags,
              int dtype, int backend, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return M == 0 ? 0 : S2U_EINVAL;
-  if ((flags & GEMM_DGELU) && !aux) return S2U_EINVAL;
+  if ((flags & (GEMM_DGELU | GEMM_MULAUX)) && !aux) return S2U_EINVAL;
   if ((flags & GEMM_RESID) && !resid) return S2U_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   GemmEpi e{bias, pre_out, aux, resid, ld_pre, ld_aux, ld_res, flags};
   const bool want_umma = dtype == S2U_BF16 && backend != 1;
   if (want_umma && umma::supported(A, lda, W, ldw, C, ldc, N, K, e)) {
-    const bool legacy = backend >= 512;          // 512+bn: one-tile-per-CTA kernel (kept for A/B measurements)
-    int bn = legacy ? backend - 512 : (backend >= 16 ? backend - 16 : 0);
+    // backend: 512+bn legacy one-tile-per-CTA kernel, 1024+bn CTA-pair kernel, 16+bn one-CTA persistent kernel
+    const bool pair_forced = backend >= 1024;
+    const bool legacy = !pair_forced && backend >= 512;
+    int bn = pair_forced ? backend - 1024 : (legacy ? backend - 512 : (backend >= 16 ? backend - 16 : 0));
+    bool pair = pair_forced;
     if (bn == 0) {
-      if (N <= 32) bn = 32;
-      else if (N <= 64) bn = 64;
-      else if (N <= 128) bn = 128;
-      else bn = 256;   // 128x256 tiles: fewest operand bytes per FLOP from L2 (measured best on every model shape)
+      pair = M > 128;                              // a pair tile is 256 rows; below that the second CTA would idle
+      if (pair) {
+        // 256 x 256 pair tiles move the fewest operand bytes per FLOP; narrower ones when those leave SMs idle
+        const int pairs_avail = umma::num_sms() / 2;
+        const int mt = ceil_div(M, 256);
+        if (N > 128 && mt * ceil_div(N, 256) >= pairs_avail / 2) bn = 256;
+        else if (N > 64) bn = 128;
+        else bn = 64;
+      } else {
+        if (N <= 32) bn = 32;
+        else if (N <= 64) bn = 64;
+        else bn = 128;
+      }
     }
     const bf16 *a = (const bf16*)A, *w = (const bf16*)W;
     bf16* c = (bf16*)C;
     if (legacy) {
-      if (flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) return S2U_EUNSUPPORTED;
+      if (flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL | GEMM_SAVE_DGELU | GEMM_MULAUX)) return S2U_EUNSUPPORTED;
       switch (bn) {
         case 32: return umma::launch<32, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         case 64: return umma::launch<64, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
@@ -1088,11 +1375,19 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
         default: return S2U_EINVAL;
       }
     }
+    if (pair) {
+      switch (bn) {
+        case 64: return umma::launch_pair<64, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 128: return umma::launch_pair<128, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 256: return umma::launch_pair<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        default: return S2U_EINVAL;
+      }
+    }
     switch (bn) {
       case 32: return umma::launch_ws<32, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
       case 64: return umma::launch_ws<64, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 128: return umma::launch_ws<128, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 256: return umma::launch_ws<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 128: return umma::launch_ws<128, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 256: return umma::launch_ws<256, 3>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
       default: return S2U_EINVAL;
     }
   }

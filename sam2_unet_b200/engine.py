@@ -25,7 +25,7 @@ from . import _lib
 from .config import TrunkConfig
 from .resample_tables import ResampleTables
 
-GELU, DGELU, RESID, OUT_F32, RESID_F32, PRE_FINAL = 1, 2, 4, 16, 32, 64
+GELU, DGELU, RESID, OUT_F32, RESID_F32, PRE_FINAL, SAVE_DGELU, MULAUX = 1, 2, 4, 16, 32, 64, 128, 256
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -42,6 +42,7 @@ class Ops:
         self.dt = 0 if dtype == torch.float32 else 1
         self.device = device
         self.gemm_backend = gemm_backend
+        self._ln_ws = {}
         _lib.load()
 
     @property
@@ -80,10 +81,18 @@ class Ops:
         _lib.call("s2u_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
                   _ptr(rstd), R, C, 1e-6, 1 if x.dtype == torch.float32 else 0, self.dt, self.stream)
 
-    def ln_bwd(self, dy, x, gamma, mean, rstd, dres, dx, R, C, pre=None, dx2=None, colsum=None):
+    def ln_bwd(self, dy, x, gamma, mean, rstd, dres, dx, R, C, pre=None, dx2=None, colsum=None, pre_is_grad=False):
+        ws = None
+        if colsum is not None:
+            # replicated column-sum accumulators, zeroed once and left zeroed by the kernel; one per (C, stream)
+            key = (C, self.stream)
+            ws = self._ln_ws.get(key)
+            if ws is None:
+                n = _lib.load().s2u_layernorm_ws_floats(C)
+                ws = self._ln_ws[key] = torch.zeros(n, dtype=torch.float32, device=self.device)
         _lib.call("s2u_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(pre), _ptr(dx2), _ptr(colsum), R, C,
-                  1 if x.dtype == torch.float32 else 0, self.dt, self.stream)
+                  rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(pre), _ptr(dx2), _ptr(colsum), _ptr(ws),
+                  1 if pre_is_grad else 0, R, C, 1 if x.dtype == torch.float32 else 0, self.dt, self.stream)
 
     def dgelu_mul(self, dy, pre, out):
         _lib.call("s2u_dgelu_mul", dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), self.dt, self.stream)
@@ -285,7 +294,7 @@ class Engine:
         ws = self._bn_ws.get(key)
         if ws is None:
             dev = self.device
-            ws = dict(sums=torch.zeros(2 * C + 1, dtype=torch.float64, device=dev),
+            ws = dict(sums=torch.zeros(_lib.load().s2u_bn_ws_doubles(C), dtype=torch.float64, device=dev),
                       scale=torch.empty(C, dtype=torch.float32, device=dev),
                       shift=torch.empty(C, dtype=torch.float32, device=dev),
                       c1=torch.empty(C, dtype=torch.float32, device=dev),
@@ -364,10 +373,12 @@ class Engine:
         R = B * H * W
         f32 = torch.float32
         # adapter (SAM2UNet.py:61-63): xa = x + gelu(gelu(x W1^T + b1) W2^T + b2)
-        h1, u = ops.empty(R, 32), ops.empty(R, 32)
-        ops.gemm(x, sh[a + "0.w"], u, bias=P[a + "0.bias"], pre_out=h1, flags=GELU)
-        h2, xa = ops.empty(R, C), ops.empty(R, C, dtype=f32)
-        ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=xs, flags=GELU | RESID | SF)
+        # h1 / hid hold gelu'(pre-activation), evaluated by the forward epilogue next to gelu itself (SAVE_DGELU)
+        h1, u = (ops.empty(R, 32) if tape is not None else None), ops.empty(R, 32)
+        ops.gemm(x, sh[a + "0.w"], u, bias=P[a + "0.bias"], pre_out=h1, flags=GELU | (SAVE_DGELU if tape is not None else 0))
+        h2, xa = (ops.empty(R, C) if tape is not None else None), ops.empty(R, C, dtype=f32)
+        ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=xs,
+                 flags=GELU | RESID | SF | (SAVE_DGELU if tape is not None else 0))
         # norm1 (hieradet.py:134)
         n1 = ops.empty(R, C)
         mean1, rstd1 = ops.empty(R, dtype=f32), ops.empty(R, dtype=f32)
@@ -395,10 +406,10 @@ class Engine:
         n2 = ops.empty(Ro, C2)
         mean2, rstd2 = ops.empty(Ro, dtype=f32), ops.empty(Ro, dtype=f32)
         ops.ln_fwd(y, fz[p + "norm2.g"], fz[p + "norm2.b"], n2, mean2, rstd2, Ro, C2)
-        hid = ops.empty(Ro, 4 * C2)
+        hid = ops.empty(Ro, 4 * C2) if tape is not None else None
         act = ops.empty(Ro, 4 * C2)
-        ops.gemm(n2, fz[p + "mlp.layers.0.w"], act, bias=fz[p + "mlp.layers.0.b"],
-                 pre_out=hid if tape is not None else None, flags=GELU)
+        ops.gemm(n2, fz[p + "mlp.layers.0.w"], act, bias=fz[p + "mlp.layers.0.b"], pre_out=hid,
+                 flags=GELU | (SAVE_DGELU if tape is not None else 0))
         z = ops.empty(Ro, C2, dtype=f32)
         zc = ops.empty(Ro, C2) if mixed else z
         ops.gemm(act, fz[p + "mlp.layers.1.w"], z, bias=fz[p + "mlp.layers.1.b"], resid=y, flags=RESID | SF | (PRE_FINAL if mixed else 0),
@@ -569,7 +580,7 @@ class Engine:
         R, Ro = B * H * W, B * Ho * Wo
         # z = y + fc2(gelu(fc1(LN2(y))))
         dh = ops.empty(Ro, 4 * C2)
-        ops.gemm(dz, fz[p + "mlp.layers.1.wt"], dh, aux=tp["hid"], flags=DGELU)
+        ops.gemm(dz, fz[p + "mlp.layers.1.wt"], dh, aux=tp["hid"], flags=MULAUX)
         dn2 = ops.empty(Ro, C2)
         ops.gemm(dh, fz[p + "mlp.layers.0.wt"], dn2)
         del dh
@@ -594,10 +605,10 @@ class Engine:
         # u = gelu(h1), h1 = x W1^T + b1): dxa, dh2 = dxa * gelu'(h2) and db2 = colsum(dh2) in one pass
         dxa, dh2 = ops.empty(R, C), ops.empty(R, C)
         ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C, pre=tp["h2"], dx2=dh2,
-                   colsum=G[a + "2.bias"])
+                   colsum=G[a + "2.bias"], pre_is_grad=True)         # h2 holds gelu'(pre-activation)
         ops.wgrad(dh2, tp["u"], G[a + "2.weight"], ldg=32)              # [C, 32]
         dh1 = ops.empty(R, 32)
-        ops.gemm(dh2, sh[a + "2.wt"], dh1, aux=tp["h1"], flags=DGELU)   # (dh2 W2) * gelu'(h1)
+        ops.gemm(dh2, sh[a + "2.wt"], dh1, aux=tp["h1"], flags=MULAUX)  # (dh2 W2) * gelu'(h1)
         ops.wgrad(dh1, tp["x"], G[a + "0.weight"], ldg=C)               # [32, C]
         ops.colsum(dh1, G[a + "0.bias"])
         dx = ops.empty(R, C)

@@ -12,9 +12,9 @@ ops = Ops(torch.bfloat16, dev)
 shapes = [(5808, 2304, 576), (5808, 576, 2304), (5808, 1728, 576), (5808, 576, 576), (92928, 576, 144),
           (92928, 144, 576), (23232, 1152, 288), (23232, 288, 1152), (1452, 4608, 1152), (1452, 1152, 4608),
           (92928, 64, 576), (92928, 32, 144), (8192, 8192, 8192)]
-variants = [("ws128", 16 + 128), ("ws256", 16 + 256), ("old128", 512 + 128)]
-flagsets = [("plain", 0, False), ("gelu+pre", 1, True), ("dgelu", 2, False), ("resid", 4, False),
-            ("stream", 4 | 16 | 32 | 64, True)]
+variants = [("ws128", 16 + 128), ("ws256", 16 + 256), ("pair128", 1024 + 128), ("pair256", 1024 + 256), ("auto", 2)]
+flagsets = [("plain", 0, False), ("gelu+pre", 1, True), ("gelu+dg", 1 | 128, True), ("dgelu", 2, False),
+            ("mulaux", 256, False), ("resid", 4, False), ("stream", 4 | 16 | 32 | 64, True)]
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 
@@ -52,7 +52,7 @@ for (M, N, K) in shapes:
                 continue
             try:
                 t = timeit(lambda: ops.gemm(A, W, C32 if fl_ & 16 else C, bias=bias, pre_out=pre if use_pre else None,
-                                            aux=aux if fl_ & 2 else None,
+                                            aux=aux if fl_ & (2 | 256) else None,
                                             resid=(R32 if fl_ & 32 else aux) if fl_ & 4 else None, flags=fl_,
                                             backend=be))
                 line += f" {fname}/{vname} {t:6.1f}us {fl / t / 1e6:5.0f}TF |"

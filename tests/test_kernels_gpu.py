@@ -42,7 +42,7 @@ GEMM_SHAPES = [(300, 96, 32), (1000, 432, 144), (484, 2304, 576), (777, 32, 144)
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
-@pytest.mark.parametrize("flags", [0, 1, 4, 5, 2])
+@pytest.mark.parametrize("flags", [0, 1, 4, 5, 2, 256, 1 | 128])
 def test_gemm_simt(cuda, dtype, shape, flags):
     M, N, K = shape
     ops = _ops(dtype, cuda, backend=1)
@@ -50,12 +50,17 @@ def test_gemm_simt(cuda, dtype, shape, flags):
     bias = _rand((N,), "fp32", cuda, 3)
     aux, resid = _rand((M, N), dtype, cuda, 4), _rand((M, N), dtype, cuda, 5)
     C, pre = ops.empty(M, N), ops.empty(M, N)
-    ops.gemm(A, W, C, bias=bias, pre_out=pre, aux=aux if flags & 2 else None, resid=resid if flags & 4 else None,
-             flags=flags)
+    ops.gemm(A, W, C, bias=bias, pre_out=pre, aux=aux if flags & (2 | 256) else None,
+             resid=resid if flags & 4 else None, flags=flags)
     ref_pre = A.float() @ W.float().t() + bias
     ref = ref_pre
     if flags & 1:
         ref = F.gelu(ref)
+    if flags & 256:
+        ref = ref * aux.float()
+    if flags & 128:                                       # pre_out holds gelu'(pre-activation)
+        p = ref_pre.clone().requires_grad_(True)
+        (ref_pre,) = torch.autograd.grad(F.gelu(p).sum(), p)
     if flags & 2:
         a = aux.float().requires_grad_(True)
         (dg,) = torch.autograd.grad(F.gelu(a).sum(), a)
@@ -67,9 +72,10 @@ def test_gemm_simt(cuda, dtype, shape, flags):
 
 
 @pytest.mark.parametrize("shape", GEMM_SHAPES + [(92928, 144, 144), (1452, 4608, 1152), (256, 1152, 4608)])
-@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
-def test_gemm_umma(cuda, shape, bn):
-    """tcgen05 + TMA GEMM vs fp32 matmul of the same bf16 operands, all tile widths, with the full epilogue."""
+@pytest.mark.parametrize("kernel", ["auto", "ws32", "ws64", "ws128", "ws256", "pair64", "pair128", "pair256"])
+def test_gemm_umma(cuda, shape, kernel):
+    """tcgen05 + TMA GEMM vs fp32 matmul of the same bf16 operands: the one-CTA persistent kernel and the CTA-pair
+    (cta_group::2) kernel at every tile width, with every epilogue the engine uses."""
     M, N, K = shape
     if K % 8 or N % 8:
         pytest.skip("TMA path needs 16-byte row pitches (the engine routes such shapes to the SIMT kernel)")
@@ -77,28 +83,51 @@ def test_gemm_umma(cuda, shape, bn):
     A, W = _rand((M, K), "bf16", cuda, 1), _rand((N, K), "bf16", cuda, 2, K ** -0.5)
     bias = _rand((N,), "fp32", cuda, 3)
     resid = _rand((M, N), "bf16", cuda, 5)
+    aux = _rand((M, N), "bf16", cuda, 7)
     C, pre = ops.empty(M, N), ops.empty(M, N)
-    backend = 2 if bn == 0 else 16 + bn
+    backend = 2 if kernel == "auto" else (16 + int(kernel[2:]) if kernel.startswith("ws") else 1024 + int(kernel[4:]))
     ops.gemm(A, W, C, bias=bias, pre_out=pre, resid=resid, flags=1 | 4, backend=backend)
-    ref_pre = A.float() @ W.float().t() + bias
+    prod = A.float() @ W.float().t()
+    ref_pre = prod + bias
     ref = F.gelu(ref_pre) + resid.float()
     _close(pre, ref_pre, 1e-2, "pre_out")
     _close(C, ref, 1e-2, "C")
-    # plain (no epilogue) and DGELU variants
+    # plain (no epilogue)
     C2 = ops.empty(M, N)
     ops.gemm(A, W, C2, backend=backend)
-    _close(C2, A.float() @ W.float().t(), 1e-2, "plain")
+    _close(C2, prod, 1e-2, "plain")
+    # GELU' of a saved pre-activation multiplies the result (backward of fc2 / adapter layer 2)
+    a = aux.float().requires_grad_(True)
+    (dg,) = torch.autograd.grad(F.gelu(a).sum(), a)
+    C5 = ops.empty(M, N)
+    ops.gemm(A, W, C5, aux=aux, flags=2, backend=backend)
+    _close(C5, prod * dg, 1e-2, "dgelu")
+    # the same with GELU' evaluated by the forward epilogue: pre_out <- gelu'(pre), backward multiplies by it
+    C6, d6 = ops.empty(M, N), ops.empty(M, N)
+    ops.gemm(A, W, C6, bias=bias, pre_out=d6, flags=1 | 128, backend=backend)
+    p = ref_pre.clone().requires_grad_(True)
+    (dp,) = torch.autograd.grad(F.gelu(p).sum(), p)
+    _close(C6, F.gelu(ref_pre), 1e-2, "gelu (save gelu')")
+    _close(d6, dp, 1e-2, "saved gelu'")
+    C7 = ops.empty(M, N)
+    ops.gemm(A, W, C7, aux=aux, flags=256, backend=backend)
+    _close(C7, prod * aux.float(), 1e-2, "mulaux")
     # fp32 residual stream: fp32 residual in, fp32 C out, bf16 copy of the final value
     r32 = _rand((M, N), "fp32", cuda, 6)
     C3, cp = torch.empty(M, N, device=cuda), ops.empty(M, N)
     ops.gemm(A, W, C3, bias=bias, resid=r32, pre_out=cp, flags=4 | 16 | 32 | 64, backend=backend)
-    ref3 = A.float() @ W.float().t() + bias + r32
+    ref3 = prod + bias + r32
     _close(C3, ref3, 1e-4, "fp32 stream out")
     _close(cp, ref3, 1e-2, "bf16 copy of the stream")
     C4, h4 = torch.empty(M, N, device=cuda), ops.empty(M, N)
     ops.gemm(A, W, C4, bias=bias, resid=resid, pre_out=h4, flags=1 | 4 | 16, backend=backend)     # bf16 resid, fp32 out
-    _close(C4, F.gelu(A.float() @ W.float().t() + bias) + resid.float(), 1e-3, "gelu + bf16 resid, fp32 out")
-    _close(h4, A.float() @ W.float().t() + bias, 1e-2, "pre-activation copy")
+    _close(C4, F.gelu(ref_pre) + resid.float(), 1e-3, "gelu + bf16 resid, fp32 out")
+    _close(h4, ref_pre, 1e-2, "pre-activation copy")
+    # adapter layer 2 forward: gelu + fp32 residual in / out with the pre-activation saved
+    C8, h8 = torch.empty(M, N, device=cuda), ops.empty(M, N)
+    ops.gemm(A, W, C8, bias=bias, resid=r32, pre_out=h8, flags=1 | 4 | 16 | 32, backend=backend)
+    _close(C8, F.gelu(ref_pre) + r32, 1e-3, "gelu + fp32 resid, fp32 out")
+    _close(h8, ref_pre, 1e-2, "pre-activation copy (stream)")
 
 
 @pytest.mark.parametrize("shape", [(3000, 32, 144), (5808, 576, 32), (777, 64, 64), (92928, 64, 576), (100, 64, 2304),
@@ -136,7 +165,7 @@ def test_wgrad_colsum(cuda, dtype):
 # ------------------------------------------------------------------------------------------ norm / pointwise
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("C", [32, 144, 1152])
+@pytest.mark.parametrize("C", [32, 64, 96, 144, 288, 576, 1152])
 def test_layernorm(cuda, dtype, C):
     ops = _ops(dtype, cuda)
     R = 1001
@@ -161,6 +190,14 @@ def test_layernorm(cuda, dtype, C):
     (dg,) = torch.autograd.grad(F.gelu(pr).sum(), pr)
     _close(dx2, dx.float() * dg, _tol(dtype, 1e-5), "ln bwd fused gelu'")
     _close(cs, dx2.float().sum(0), 1e-4, "ln bwd fused colsum")
+    # the same with gelu'(pre) already evaluated (GEMM_SAVE_DGELU epilogue); the workspace must have come back clean,
+    # and the column sums accumulate
+    dgs = dg.to(DT[dtype])
+    dx_c, dx2c = ops.empty(R, C), ops.empty(R, C)
+    ops.ln_bwd(dy, x, g, mean, rstd, dres, dx_c, R, C, pre=dgs, dx2=dx2c, colsum=cs, pre_is_grad=True)
+    assert torch.equal(dx_c, dx)
+    _close(dx2c, dx.float() * dgs.float(), _tol(dtype, 1e-5), "ln bwd fused saved gelu'")
+    _close(cs, dx2.float().sum(0) + dx2c.float().sum(0), 1e-4, "ln bwd fused colsum accumulates")
     if dtype == "bf16":                                   # fp32 residual stream in, bf16 out
         x32 = x.float()
         y2, m2, r2 = ops.empty(R, C), ops.empty(R, dtype=torch.float32), ops.empty(R, dtype=torch.float32)
@@ -311,14 +348,16 @@ def test_conv_im2col_gemm(cuda, dtype, conv):
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("relu", [False, True])
-def test_batchnorm(cuda, dtype, relu):
+@pytest.mark.parametrize("M", [2 * 11 * 11, 12 * 44 * 44 + 3])
+def test_batchnorm(cuda, dtype, relu, M):
+    from sam2_unet_b200 import _lib
     ops = _ops(dtype, cuda)
-    M, C = 2 * 11 * 11, 64
+    C = 64
     x = _rand((M, C), dtype, cuda, 1) * 1.5 + 0.3
     g, b = _rand((C,), "fp32", cuda, 2) * 0.1 + 1, _rand((C,), "fp32", cuda, 3) * 0.1
     rm, rv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
     nbt = torch.zeros((), dtype=torch.long, device=cuda)
-    sums = torch.zeros(2 * C + 1, dtype=torch.float64, device=cuda)
+    sums = torch.zeros(_lib.load().s2u_bn_ws_doubles(C), dtype=torch.float64, device=cuda)
     scale, shift, mean, rstd = (torch.empty(C, device=cuda) for _ in range(4))
     if relu:                                              # both forms of the training forward
         ops.bn_stats(x, C, sums, M, C)
