@@ -158,31 +158,78 @@ __device__ __forceinline__ void put_o(bf16* d, const bf16* src, const Geom& g, c
     *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
 }
 
-// 64-row tiles: rows = key / query indices r0..r0+63 of ONE window
+// 64-row tiles: rows = key / query indices r0..r0+63 of ONE window.  Two threads per row (NT = 2 * 64): the token
+// address is worked out once per row and each thread then moves every other 16-byte chunk of it - the per-chunk
+// index arithmetic of a chunk-per-thread loop was 40 % of the forward kernel's instructions (ncu), and these kernels
+// are bound by instruction issue.
+static_assert(NT == 2 * BM && BM == BN, "tile loaders assume two threads per row");
 template <int HDP>
-__device__ __forceinline__ void load_kv(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
-                                        int head, int which, int r0) {
+__device__ __forceinline__ void load_kv(bf16* Kdst, bf16* Vdst, const bf16* qkv, const float* bias, const Geom& g,
+                                        const Win& w, int head, int r0) {
   constexpr int LD = HDP + 8, CH = HDP / 8;
-  for (int e = threadIdx.x; e < BN * CH; e += NT) {
-    const int r = e / CH, c = e - r * CH;
-    put_kv(dst + r * LD + c * 8, qkv, bias, g, w, head, which, r0 + r, c);
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  const int idx = r0 + r;
+  const int C = g.nh * g.hd;
+  bf16* kd = Kdst + r * LD;
+  bf16* vd = Vdst + r * LD;
+  if (idx < w.n_real) {
+    const int ty = idx / w.rw, tx = idx - ty * w.rw;
+    const bf16* src = qkv + (((long long)w.b * g.H + (w.wy * g.wh + ty)) * g.W + (w.wx * g.ww + tx)) * (3LL * C) +
+                      head * g.hd;
+#pragma unroll
+    for (int c = par; c < CH; c += 2) {
+      if (c * 8 < g.hd) {
+        cp_async16(kd + c * 8, src + C + c * 8);
+        cp_async16(vd + c * 8, src + 2 * C + c * 8);
+      } else {
+        *reinterpret_cast<uint4*>(kd + c * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(vd + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  } else {
+    const bool pad_key = idx < w.nk;                           // the virtual pad key: k = v = bias
+#pragma unroll
+    for (int c = par; c < CH; c += 2) {
+      const bool live = pad_key && c * 8 < g.hd;
+      *reinterpret_cast<uint4*>(kd + c * 8) =
+          live ? tok8(qkv, bias, g, w.b, g.H, g.W, C + head * g.hd + c * 8) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(vd + c * 8) =
+          live ? tok8(qkv, bias, g, w.b, g.H, g.W, 2 * C + head * g.hd + c * 8) : make_uint4(0, 0, 0, 0);
+    }
   }
 }
 template <int HDP>
 __device__ __forceinline__ void load_q(bf16* dst, const bf16* qkv, const float* bias, const Geom& g, const Win& w,
                                        int head, int r0) {
   constexpr int LD = HDP + 8, CH = HDP / 8;
-  for (int e = threadIdx.x; e < BM * CH; e += NT) {
-    const int r = e / CH, c = e - r * CH;
-    put_q(dst + r * LD + c * 8, qkv, bias, g, w, head, r0 + r, c);
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  const int idx = r0 + r;
+  bf16* d = dst + r * LD;
+  if (idx < w.nq && !g.pool) {
+    const int py = idx / w.qrw, px = idx - py * w.qrw;
+    const bf16* src = qkv + (((long long)w.b * g.H + (w.wy * g.wh + py)) * g.W + (w.wx * g.ww + px)) *
+                                (3LL * g.nh * g.hd) + head * g.hd;
+#pragma unroll
+    for (int c = par; c < CH; c += 2) {
+      if (c * 8 < g.hd) cp_async16(d + c * 8, src + c * 8);
+      else *reinterpret_cast<uint4*>(d + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int c = par; c < CH; c += 2) put_q(d + c * 8, qkv, bias, g, w, head, idx, c);   // pooled queries / padding
   }
 }
 template <int HDP>
 __device__ __forceinline__ void load_o(bf16* dst, const bf16* src, const Geom& g, const Win& w, int head, int r0) {
   constexpr int LD = HDP + 8, CH = HDP / 8;
-  for (int e = threadIdx.x; e < BM * CH; e += NT) {
-    const int r = e / CH, c = e - r * CH;
-    put_o(dst + r * LD + c * 8, src, g, w, head, r0 + r, c);
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  const long long tok = out_token(g, w, r0 + r);
+  bf16* d = dst + r * LD;
+  const bf16* s = src + tok * (g.nh * g.hd) + head * g.hd;
+#pragma unroll
+  for (int c = par; c < CH; c += 2) {
+    if (tok >= 0 && c * 8 < g.hd) cp_async16(d + c * 8, s + c * 8);
+    else *reinterpret_cast<uint4*>(d + c * 8) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -299,8 +346,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
   const float sl2 = g.scale * 1.4426950408889634f;
 
   load_q<HDP>(Qs, qkv, bias, g, w, head, q0);
-  load_kv<HDP>(KV, qkv, bias, g, w, head, 1, 0);
-  load_kv<HDP>(KV + BN * LD, qkv, bias, g, w, head, 2, 0);
+  load_kv<HDP>(KV, KV + BN * LD, qkv, bias, g, w, head, 0);
   cp_async_commit();
   float o[HDP / 8][4];
 #pragma unroll
@@ -313,8 +359,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
     const bf16* Vs = Ks + BN * LD;
     if (k0 + BN < nk) {                                         // prefetch the next key tile into the other buffer
       bf16* nxt = KV + ((it + 1) & 1) * 2 * BN * LD;
-      load_kv<HDP>(nxt, qkv, bias, g, w, head, 1, k0 + BN);
-      load_kv<HDP>(nxt + BN * LD, qkv, bias, g, w, head, 2, k0 + BN);
+      load_kv<HDP>(nxt, nxt + BN * LD, qkv, bias, g, w, head, k0 + BN);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -322,13 +367,16 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
     float s[8][4];
     mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
     float t0 = -INFINITY, t1 = -INFINITY;
+    const bool ragged = k0 + BN > w.n_real;                     // the tile holds the pad key and / or the window's end
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = k0 + j * 8 + 2 * (lane & 3);
-      if (c == w.n_real) { s[j][0] += w.bonus; s[j][2] += w.bonus; }
-      if (c + 1 == w.n_real) { s[j][1] += w.bonus; s[j][3] += w.bonus; }
-      if (c >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-      if (c + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      if (ragged) {
+        const int c = k0 + j * 8 + 2 * (lane & 3);
+        if (c == w.n_real) { s[j][0] += w.bonus; s[j][2] += w.bonus; }
+        if (c + 1 == w.n_real) { s[j][1] += w.bonus; s[j][3] += w.bonus; }
+        if (c >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (c + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
       t0 = fmaxf(t0, fmaxf(s[j][0], s[j][1]));
       t1 = fmaxf(t1, fmaxf(s[j][2], s[j][3]));
     }
@@ -422,8 +470,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
 
   load_q<HDP>(Qs, qkv, bias, g, w, head, q0);
   load_o<HDP>(dOs, dout, g, w, head, q0);
-  load_kv<HDP>(KV, qkv, bias, g, w, head, 1, 0);
-  load_kv<HDP>(KV + BN * LD, qkv, bias, g, w, head, 2, 0);
+  load_kv<HDP>(KV, KV + BN * LD, qkv, bias, g, w, head, 0);
   cp_async_commit();
   const int r0 = warp * 16 + (lane >> 2);
   const long long tok0 = out_token(g, w, q0 + r0), tok1 = out_token(g, w, q0 + r0 + 8);
@@ -441,8 +488,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
     const bf16* Vs = Ks + BN * LD;
     if (k0 + BN < nk) {
       bf16* nxt = KV + ((it + 1) & 1) * 2 * BN * LD;
-      load_kv<HDP>(nxt, qkv, bias, g, w, head, 1, k0 + BN);
-      load_kv<HDP>(nxt + BN * LD, qkv, bias, g, w, head, 2, k0 + BN);
+      load_kv<HDP>(nxt, nxt + BN * LD, qkv, bias, g, w, head, k0 + BN);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -450,12 +496,17 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
     float s[8][4], dp[8][4];
     mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
     mm_ab_t<HDP>(dp, dOs, Vs, warp, lane);
+    const bool ragged = k0 + BN > w.n_real;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = k0 + j * 8 + 2 * (lane & 3);
-      if (c == w.n_real) { s[j][0] += w.bonus; s[j][2] += w.bonus; }
-      if (c + 1 == w.n_real) { s[j][1] += w.bonus; s[j][3] += w.bonus; }
-      const bool v0 = c < nk, v1 = c + 1 < nk;
+      bool v0 = true, v1 = true;
+      if (ragged) {
+        const int c = k0 + j * 8 + 2 * (lane & 3);
+        if (c == w.n_real) { s[j][0] += w.bonus; s[j][2] += w.bonus; }
+        if (c + 1 == w.n_real) { s[j][1] += w.bonus; s[j][3] += w.bonus; }
+        v0 = c < nk;
+        v1 = c + 1 < nk;
+      }
       const float p00 = v0 ? ex2(s[j][0] * sl2 - L0) : 0.f, p01 = v1 ? ex2(s[j][1] * sl2 - L0) : 0.f;
       const float p10 = v0 ? ex2(s[j][2] * sl2 - L1) : 0.f, p11 = v1 ? ex2(s[j][3] * sl2 - L1) : 0.f;
       s[j][0] = p00 * (dp[j][0] - D0) * g.scale;
@@ -501,8 +552,7 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qk
       LD2[buf * 2 * BM + BM + threadIdx.x] = tok >= 0 ? Dv[tok * g.nh + head] : 0.f;
     }
   };
-  load_kv<HDP>(Ks, qkv, bias, g, w, head, 1, k0);
-  load_kv<HDP>(Vs, qkv, bias, g, w, head, 2, k0);
+  load_kv<HDP>(Ks, Vs, qkv, bias, g, w, head, k0);
   stage_q(0, 0);
   cp_async_commit();
   float dk[HDP / 8][4], dv[HDP / 8][4];
