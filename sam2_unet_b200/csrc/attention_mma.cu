@@ -387,12 +387,13 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
     const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
     const float a0 = ex2((m0 - n0) * sl2), a1 = ex2((m1 - n1) * sl2);
     float p0 = 0.f, p1 = 0.f;
+    const float b0 = -n0 * sl2, b1 = -n1 * sl2;                 // one FMA per score: exp2(s * sl2 - n * sl2)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = ex2((s[j][0] - n0) * sl2);
-      s[j][1] = ex2((s[j][1] - n0) * sl2);
-      s[j][2] = ex2((s[j][2] - n1) * sl2);
-      s[j][3] = ex2((s[j][3] - n1) * sl2);
+      s[j][0] = ex2(fmaf(s[j][0], sl2, b0));
+      s[j][1] = ex2(fmaf(s[j][1], sl2, b0));
+      s[j][2] = ex2(fmaf(s[j][2], sl2, b1));
+      s[j][3] = ex2(fmaf(s[j][3], sl2, b1));
       p0 += s[j][0] + s[j][1];
       p1 += s[j][2] + s[j][3];
     }
@@ -430,30 +431,12 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
   }
 }
 
-// D[token, head] = sum_d dO * O  (one warp per token)
-__global__ void bwd_prep_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ D,
-                                long long ntok, int nh, int hd) {
-  const long long tok = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (tok >= ntok) return;
-  const int C = nh * hd;
-  for (int h = 0; h < nh; ++h) {
-    float s = 0.f;
-    for (int d = lane * 2; d < hd; d += 64) {
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + tok * C + h * hd + d));
-      const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + tok * C + h * hd + d));
-      s += a.x * c.x + a.y * c.y;
-    }
-    s = warp_sum(s);
-    if (lane == 0) D[tok * nh + h] = s;
-  }
-}
-
 // ------------------------------------------------------------------------------------------- backward: dQ
 template <int HDP>
 __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
-                                                   const float* __restrict__ lse, const float* __restrict__ Dv,
-                                                   const bf16* __restrict__ dout, bf16* __restrict__ dqkv, Geom g) {
+                                                   const bf16* __restrict__ out, const float* __restrict__ lse,
+                                                   float* __restrict__ Dv, const bf16* __restrict__ dout,
+                                                   bf16* __restrict__ dqkv, Geom g) {
   constexpr int LD = HDP + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
@@ -468,16 +451,45 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
   const int nk = w.nk;
   const float sl2 = g.scale * 1.4426950408889634f;
 
+  __shared__ float Dsm[BM];
   load_q<HDP>(Qs, qkv, bias, g, w, head, q0);
   load_o<HDP>(dOs, dout, g, w, head, q0);
+  bf16* Os = KV + 2 * BN * LD;                                  // second K/V buffer: free until the first prefetch
+  load_o<HDP>(Os, out, g, w, head, q0);
   load_kv<HDP>(KV, KV + BN * LD, qkv, bias, g, w, head, 0);
   cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  {
+    // D[row] = sum_d dO * O (the softmax-backward row term), two threads per row; written out for the dK/dV kernel,
+    // which runs after this one on the same stream
+    const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = par; c < HDP / 8; c += 2) {
+      const uint4 ua = *reinterpret_cast<const uint4*>(dOs + r * LD + c * 8);
+      const uint4 ub = *reinterpret_cast<const uint4*>(Os + r * LD + c * 8);
+      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+        acc = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, acc));
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (par == 0) {
+      Dsm[r] = acc;
+      const long long tok = out_token(g, w, q0 + r);
+      if (tok >= 0) Dv[tok * g.nh + head] = acc;
+    }
+  }
+  __syncthreads();
   const int r0 = warp * 16 + (lane >> 2);
   const long long tok0 = out_token(g, w, q0 + r0), tok1 = out_token(g, w, q0 + r0 + 8);
   const float L0 = tok0 >= 0 ? lse[tok0 * g.nh + head] * 1.4426950408889634f : INFINITY;
   const float L1 = tok1 >= 0 ? lse[tok1 * g.nh + head] * 1.4426950408889634f : INFINITY;
-  const float D0 = tok0 >= 0 ? Dv[tok0 * g.nh + head] : 0.f;
-  const float D1 = tok1 >= 0 ? Dv[tok1 * g.nh + head] : 0.f;
+  const float D0 = Dsm[r0], D1 = Dsm[r0 + 8];
   float dq[HDP / 8][4];
 #pragma unroll
   for (int j = 0; j < HDP / 8; ++j)
@@ -919,14 +931,11 @@ static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const
     S2U_LAUNCH_CHECK();
     return 0;
   }
-  const long long ntok = (long long)g.B * g.Ho * g.Wo;
-  bwd_prep_kernel<<<ceil_div(ntok * 32, 256), 256, 0, st>>>(out, dout, Dws, ntok, g.nh, g.hd);
-  S2U_LAUNCH_CHECK();
   {
     dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
     const size_t smem = (size_t)(2 * BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
     S2U_ALLOW_SMEM(bwd_dq_kernel<HDP>);
-    bwd_dq_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, lse, Dws, dout, dqkv, g);
+    bwd_dq_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, out, lse, Dws, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
   }
   {
