@@ -496,8 +496,8 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
-  static constexpr int ACC_COLS = BN;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // accumulator stride
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)((2 * BM) >> 4) << 24);
 };
@@ -624,7 +624,8 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   auto prefetch = [&](int tile, int ci, int par) {
     const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
     const int col0 = (tile / t.m_tiles) * BN + half * 32 + ci * 64;
-    const int rows_ok = (int)min((long long)32, (long long)M - row0), cols_ok = min(32, N - col0);
+    const int rows_ok = (int)min((long long)32, (long long)M - row0);
+    const int cols_ok = min(min(32, BN - half * 32 - ci * 64), N - col0);
     if (rows_ok <= 0 || cols_ok <= 0) return;
     const uint32_t b = stg + (uint32_t)(par * 2 * EPI_BUF_BYTES);
     if (side16) {
@@ -657,7 +658,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
     for (int ci = 0; ci < nch; ++ci, ++cc) {
       const int par = cc & 1;
       const int c0 = half * 32 + ci * 64, col0 = n0 + c0;
-      const int cols_ok = min(32, N - col0);                                // may be <= 0
+      const int cols_ok = min(min(32, BN - c0), N - col0);                  // tile edge (BN = 144) / matrix edge; may be <= 0
       const bool live = rows_ok > 0 && cols_ok > 0;                         // warp-uniform
       if (has_side) {                                                       // next chunk's side input
         if (ci + 1 < nch) prefetch(tile, ci + 1, par ^ 1);
@@ -1391,12 +1392,17 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     if (bn == 0) {
       pair = M > 128;                              // a pair tile is 256 rows; below that the second CTA would idle
       if (pair) {
-        // 256 x 256 pair tiles move the fewest operand bytes per FLOP; narrower ones when those leave SMs idle
+        // tile width: fewest waves x (tile width + fixed per-tile cost).  256 moves the fewest operand bytes per FLOP,
+        // 192 / 144 fit N = 576, 1728, 288, 144 (Hiera-L) without a mostly empty last column of tiles
         const int pairs_avail = umma::num_sms() / 2;
         const int mt = ceil_div(M, 256);
-        if (N > 128 && mt * ceil_div(N, 256) >= pairs_avail / 2) bn = 256;
-        else if (N > 64) bn = 128;
-        else bn = 64;
+        int best = 1 << 30;
+        for (int cand : {256, 192, 144, 128, 64, 32}) {
+          if (cand > 64 && N <= cand / 2) continue;
+          const int tiles = mt * ceil_div(N, cand);
+          const int cost = ceil_div(tiles, pairs_avail) * (cand + 64);
+          if (cost < best) { best = cost; bn = cand; }
+        }
       } else {
         if (N <= 32) bn = 32;
         else if (N <= 64) bn = 64;
@@ -1417,8 +1423,11 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     }
     if (pair) {
       switch (bn) {
-        case 64: return umma::launch_pair<64, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 32: return umma::launch_pair<32, 8>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 64: return umma::launch_pair<64, 7>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         case 128: return umma::launch_pair<128, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 144: return umma::launch_pair<144, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 192: return umma::launch_pair<192, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         case 256: return umma::launch_pair<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         default: return S2U_EINVAL;
       }

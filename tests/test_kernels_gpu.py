@@ -72,7 +72,8 @@ def test_gemm_simt(cuda, dtype, shape, flags):
 
 
 @pytest.mark.parametrize("shape", GEMM_SHAPES + [(92928, 144, 144), (1452, 4608, 1152), (256, 1152, 4608)])
-@pytest.mark.parametrize("kernel", ["auto", "ws32", "ws64", "ws128", "ws256", "pair64", "pair128", "pair256"])
+@pytest.mark.parametrize("kernel", ["auto", "ws32", "ws64", "ws128", "ws256", "pair32", "pair64", "pair128", "pair144",
+                                    "pair192", "pair256"])
 def test_gemm_umma(cuda, shape, kernel):
     """tcgen05 + TMA GEMM vs fp32 matmul of the same bf16 operands: the one-CTA persistent kernel and the CTA-pair
     (cta_group::2) kernel at every tile width, with every epilogue the engine uses."""
