@@ -86,6 +86,7 @@ __device__ __forceinline__ bool out_pos(const AttnGeom& g, int wy, int wx, int i
 template <typename T>
 __global__ void __launch_bounds__(NTH) attn_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ bias,
                                                       T* __restrict__ out, float* __restrict__ lse, AttnGeom g) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int ldd = g.hd + 1;
   float* Qs = sm;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_dq_kernel(const T* __restrict__ 
                                                          const T* __restrict__ out, const float* __restrict__ lse,
                                                          const T* __restrict__ dout, T* __restrict__ dqkv,
                                                          AttnGeom g) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int ldd = g.hd + 1;
   float* Qs = sm;
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_dkv_kernel(const T* __restrict__
                                                           const T* __restrict__ out, const float* __restrict__ lse,
                                                           const T* __restrict__ dout, T* __restrict__ dqkv,
                                                           AttnGeom g) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int ldd = g.hd + 1;
   float* Ks = sm;
@@ -436,7 +439,7 @@ int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, 
   const size_t smem = (size_t)((QT + 2 * KT) * (hd + 1) + QT * (KT + 1)) * sizeof(float);
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(attn_fwd_kernel<T>);
-    attn_fwd_kernel<T><<<grid, NTH, smem, (cudaStream_t)stream>>>((const T*)qkv, bias, (T*)out, lse, g);
+    S2U_LAUNCH((attn_fwd_kernel<T>), grid, NTH, smem, (cudaStream_t)stream, (const T*)qkv, bias, (T*)out, lse, g);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -461,7 +464,7 @@ int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const 
     const size_t smem = (size_t)((2 * QT + 2 * KT) * (hd + 1) + QT * (KT + 1)) * sizeof(float);
     S2U_DISPATCH_T(dtype, {
       S2U_ALLOW_SMEM(attn_bwd_dq_kernel<T>);
-      attn_bwd_dq_kernel<T><<<grid, NTH, smem, st>>>((const T*)qkv, bias, (const T*)out, lse, (const T*)dout,
+      S2U_LAUNCH((attn_bwd_dq_kernel<T>), grid, NTH, smem, st, (const T*)qkv, bias, (const T*)out, lse, (const T*)dout,
                                                      (T*)dqkv, g);
     })
     S2U_LAUNCH_CHECK();
@@ -471,7 +474,7 @@ int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const 
     const size_t smem = (size_t)((2 * QT + 2 * KT) * (hd + 1) + 2 * KT * (QT + 1) + 2 * QT) * sizeof(float);
     S2U_DISPATCH_T(dtype, {
       S2U_ALLOW_SMEM(attn_bwd_dkv_kernel<T>);
-      attn_bwd_dkv_kernel<T><<<grid, NTH, smem, st>>>((const T*)qkv, bias, (const T*)out, lse, (const T*)dout,
+      S2U_LAUNCH((attn_bwd_dkv_kernel<T>), grid, NTH, smem, st, (const T*)qkv, bias, (const T*)out, lse, (const T*)dout,
                                                       (T*)dqkv, g);
     })
     S2U_LAUNCH_CHECK();

@@ -233,7 +233,7 @@ __device__ __forceinline__ void load_o(bf16* dst, const bf16* src, const Geom& g
   }
 }
 
-// write this thread's dq fragment rows (query idx, 2 adjacent head-dim columns per 8-column tile j) into the q third
+// (packed kernel) write this thread's dq fragment rows (query idx, 2 adjacent head-dim columns per 8-column tile j) into the q third
 // of dqkv, routing through the arg-max of the 2x2 q max-pool when g.pool (first maximum in scan order, like ATen)
 template <int NJ>
 __device__ __forceinline__ void scatter_dq(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv,
@@ -280,6 +280,58 @@ __device__ __forceinline__ void scatter_dq(bf16* __restrict__ dqkv, const bf16* 
           dqkv[(((long long)w.b * g.H + yy) * g.W + xx) * row3 + col] =
               __float2bfloat16(k == best ? dq[j][half * 2 + e] : 0.f);
       }
+    }
+  }
+}
+
+// dq tile (bf16, [64 rows][LD] in shared memory, rows = queries q0..q0+63) -> q third of dqkv with 16-byte stores, two
+// threads per row.  With q pooling the gradient of a pooled query goes to the arg-max of its 2x2 source tokens per
+// channel (first maximum in scan order, like ATen's max_pool2d backward) and the other three receive zero.
+template <int HDP>
+__device__ __forceinline__ void store_dq_rows(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv,
+                                              const float* __restrict__ bias, const Geom& g, const Win& w, int head,
+                                              int q0, const bf16* Ts) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  const int idx = q0 + r;
+  if (idx >= w.nq) return;
+  const int C = g.nh * g.hd;
+  const long long row3 = 3LL * C;
+  const int py = idx / w.qrw, px = idx - py * w.qrw;
+  if (!g.pool) {
+    bf16* dst = dqkv + (((long long)w.b * g.H + (w.wy * g.wh + py)) * g.W + (w.wx * g.ww + px)) * row3 + head * g.hd;
+#pragma unroll
+    for (int c = par; c < CH; c += 2)
+      if (c * 8 < g.hd) *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(Ts + r * LD + c * 8);
+    return;
+  }
+  const int y = w.wy * g.wh + 2 * py, x = w.wx * g.ww + 2 * px;
+#pragma unroll
+  for (int c = par; c < CH; c += 2) {
+    if (c * 8 >= g.hd) continue;
+    const int col = head * g.hd + c * 8;
+    uint4 src[4], o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) src[k] = tok8(qkv, bias, g, w.b, y + (k >> 1), x + (k & 1), col);
+    const uint4 dv = *reinterpret_cast<const uint4*>(Ts + r * LD + c * 8);
+    const bf16* de = reinterpret_cast<const bf16*>(&dv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int best = 0;
+      float vb = __bfloat162float(reinterpret_cast<const bf16*>(&src[0])[e]);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const float vk = __bfloat162float(reinterpret_cast<const bf16*>(&src[k])[e]);
+        if (vk > vb) { vb = vk; best = k; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<bf16*>(&o[k])[e] = k == best ? de[e] : __float2bfloat16(0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = y + (k >> 1), xx = x + (k & 1);
+      if (yy < g.H && xx < g.W)
+        *reinterpret_cast<uint4*>(dqkv + (((long long)w.b * g.H + yy) * g.W + xx) * row3 + col) = o[k];
     }
   }
 }
@@ -333,6 +385,7 @@ __device__ __forceinline__ void mm_p_b(float (*out)[4], const float (*p)[4], con
 template <int HDP>
 __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                 bf16* __restrict__ out, float* __restrict__ lse, Geom g) {
+  pdl_sync();
   constexpr int LD = HDP + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
@@ -437,6 +490,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
                                                    const bf16* __restrict__ out, const float* __restrict__ lse,
                                                    float* __restrict__ Dv, const bf16* __restrict__ dout,
                                                    bf16* __restrict__ dqkv, Geom g) {
+  pdl_sync();
   constexpr int LD = HDP + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
@@ -529,9 +583,17 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
     mm_p_b<HDP>(dq, s, Ks, lane);
     __syncthreads();
   }
-  // scatter into the q third of dqkv (argmax routing through the q max-pool)
-  scatter_dq<HDP / 8>(dqkv, qkv, bias, g, w, head, q0 + r0, dq, 0, lane);
-  scatter_dq<HDP / 8>(dqkv, qkv, bias, g, w, head, q0 + r0 + 8, dq, 1, lane);
+  // dq fragments -> shared tile (the Q tile is dead after the loop's last barrier) -> routed 16-byte stores
+  bf16* Ts = Qs;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j)
+      *reinterpret_cast<__nv_bfloat162*>(Ts + (r0 + half * 8) * LD + j * 8 + 2 * (lane & 3)) =
+          __floats2bfloat162_rn(dq[j][half * 2], dq[j][half * 2 + 1]);
+  }
+  __syncthreads();
+  store_dq_rows<HDP>(dqkv, qkv, bias, g, w, head, q0, Ts);
 }
 
 // --------------------------------------------------------------------------------------- backward: dK, dV
@@ -539,6 +601,7 @@ template <int HDP>
 __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                     const float* __restrict__ lse, const float* __restrict__ Dv,
                                                     const bf16* __restrict__ dout, bf16* __restrict__ dqkv, Geom g) {
+  pdl_sync();
   constexpr int LD = HDP + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Ks = reinterpret_cast<bf16*>(smraw);
@@ -735,6 +798,7 @@ __device__ __forceinline__ void softmax16(float (*s)[4], const Win& w, float sl2
 template <int HDP>
 __global__ void __launch_bounds__(NT) fwd_packed_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                        bf16* __restrict__ out, float* __restrict__ lse, Geom g) {
+  pdl_sync();
   constexpr int LD = HDP + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   __shared__ Win wins[PACK];
@@ -785,6 +849,7 @@ template <int HDP>
 __global__ void __launch_bounds__(NT) bwd_packed_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                        const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                                        Geom g) {
+  pdl_sync();
   constexpr int LD = HDP + 8, TP = 24;                         // TP: pitch of the 16x16 transpose tiles (48 B rows)
   extern __shared__ __align__(16) uint8_t smraw[];
   __shared__ Win wins[PACK];
@@ -908,14 +973,14 @@ static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse,
     dim3 pgrid(1, ceil_div(g.B * g.nwy * g.nwx, PACK), g.nh);
     const size_t psmem = (size_t)3 * BM * (HDP + 8) * sizeof(bf16);
     S2U_ALLOW_SMEM(fwd_packed_kernel<HDP>);
-    fwd_packed_kernel<HDP><<<pgrid, NT, psmem, st>>>(qkv, bias, out, lse, g);
+    S2U_LAUNCH((fwd_packed_kernel<HDP>), pgrid, NT, psmem, st, qkv, bias, out, lse, g);
     S2U_LAUNCH_CHECK();
     return 0;
   }
   dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
   const size_t smem = (size_t)(BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
   S2U_ALLOW_SMEM(fwd_kernel<HDP>);
-  fwd_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, out, lse, g);
+  S2U_LAUNCH((fwd_kernel<HDP>), grid, NT, smem, st, qkv, bias, out, lse, g);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -927,7 +992,7 @@ static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const
     dim3 pgrid(1, ceil_div(g.B * g.nwy * g.nwx, PACK), g.nh);
     const size_t psmem = (size_t)(4 * BM * (HDP + 8) + 4 * 2 * 16 * 24) * sizeof(bf16);
     S2U_ALLOW_SMEM(bwd_packed_kernel<HDP>);
-    bwd_packed_kernel<HDP><<<pgrid, NT, psmem, st>>>(qkv, bias, dout, dqkv, g);
+    S2U_LAUNCH((bwd_packed_kernel<HDP>), pgrid, NT, psmem, st, qkv, bias, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
     return 0;
   }
@@ -935,14 +1000,14 @@ static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const
     dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
     const size_t smem = (size_t)(2 * BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
     S2U_ALLOW_SMEM(bwd_dq_kernel<HDP>);
-    bwd_dq_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, out, lse, Dws, dout, dqkv, g);
+    S2U_LAUNCH((bwd_dq_kernel<HDP>), grid, NT, smem, st, qkv, bias, out, lse, Dws, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
   }
   {
     dim3 grid(ceil_div(g.wh * g.ww, BN), g.B * g.nwy * g.nwx, g.nh);
     const size_t smem = (size_t)(4 * BM + 2 * BN) * (HDP + 8) * sizeof(bf16) + 4 * BM * sizeof(float);
     S2U_ALLOW_SMEM(bwd_dkv_kernel<HDP>);
-    bwd_dkv_kernel<HDP><<<grid, NT, smem, st>>>(qkv, bias, lse, Dws, dout, dqkv, g);
+    S2U_LAUNCH((bwd_dkv_kernel<HDP>), grid, NT, smem, st, qkv, bias, lse, Dws, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
   }
   return 0;

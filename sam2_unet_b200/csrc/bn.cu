@@ -64,6 +64,7 @@ __device__ __forceinline__ void bn_finalize_block(volatile double* sums, const B
 }
 
 __global__ void bn_finalize_kernel(double* __restrict__ sums, BnFin f, long long M, int C, int training) {
+  pdl_sync();
   bn_finalize_block(sums, f, M, C, training);
 }
 
@@ -117,6 +118,7 @@ __device__ __forceinline__ void reduce_to_sums(float* red, const float* s, const
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int ldx, double* __restrict__ sums,
                                                       long long M, int C, int fuse_finalize, BnFin fin) {
+  pdl_sync();
   extern __shared__ float red[];              // [row lanes][2*C]
   const int cg = C >> 3;                      // 8-channel groups
   const int nsub = 256 / cg;                  // row lanes per block
@@ -151,6 +153,7 @@ template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const T* __restrict__ resid, int ld_res,
                                 T* __restrict__ out, int ld_out, long long M, int C, int relu) {
+  pdl_sync();
   const int cg = C >> 3;
   const long long total = M * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -178,6 +181,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* _
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ dy, int ld_dy, const T* __restrict__ y, int ld_y,
                                 T* __restrict__ g, int ld_g, long long M, int C) {
+  pdl_sync();
   const int cg = C >> 3;
   const long long total = M * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
                                                            double* __restrict__ sums, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, float* __restrict__ c1,
                                                            float* __restrict__ c2, long long M, int C) {
+  pdl_sync();
   extern __shared__ float red[];
   const int cg = C >> 3;
   const int nsub = 256 / cg;
@@ -249,6 +254,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, int ld_dy, const T
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const float* __restrict__ c1, const float* __restrict__ c2, T* __restrict__ dx,
                                     int ld_dx, long long M, int C) {
+  pdl_sync();
   const int cg = C >> 3;
   const long long total = M * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -303,7 +309,7 @@ int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int d
   BnFin none{};
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_stats_kernel<T>);
-    bn_stats_kernel<T><<<bn_reduce_grid(M, C), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 0, none);
+    S2U_LAUNCH((bn_stats_kernel<T>), bn_reduce_grid(M, C), 256, smem, (cudaStream_t)stream, (const T*)x, ldx, sums, M, C, 0, none);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -321,7 +327,7 @@ int s2u_bn_stats_finalize(const void* x, int ldx, double* sums, const float* gam
   BnFin f{gamma, beta, running_mean, running_var, num_batches, scale, shift, save_mean, save_rstd, eps, momentum};
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_stats_kernel<T>);
-    bn_stats_kernel<T><<<bn_reduce_grid(M, C), 256, smem, (cudaStream_t)stream>>>((const T*)x, ldx, sums, M, C, 1, f);
+    S2U_LAUNCH((bn_stats_kernel<T>), bn_reduce_grid(M, C), 256, smem, (cudaStream_t)stream, (const T*)x, ldx, sums, M, C, 1, f);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -332,7 +338,7 @@ int s2u_bn_finalize(double* sums, const float* gamma, const float* beta, float* 
                     long long M, int C, float eps, float momentum, int training, void* stream) {
   if (C <= 0) return S2U_EINVAL;
   BnFin f{gamma, beta, running_mean, running_var, num_batches, scale, shift, save_mean, save_rstd, eps, momentum};
-  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, f, M, C, training);
+  S2U_LAUNCH((bn_finalize_kernel), 1, 256, 0, (cudaStream_t)stream, sums, f, M, C, training);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -341,7 +347,7 @@ int s2u_bn_apply(const void* x, int ldx, const float* scale, const float* shift,
                  void* out, int ld_out, long long M, int C, int relu, int dtype, void* stream) {
   if (M <= 0 || !bn_c_ok(C) || (ldx & 7) || (ld_out & 7) || (resid && (ld_res & 7))) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    bn_apply_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+    S2U_LAUNCH((bn_apply_kernel<T>), grid_for(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream, 
         (const T*)x, ldx, scale, shift, (const T*)resid, ld_res, (T*)out, ld_out, M, C, relu);
   })
   S2U_LAUNCH_CHECK();
@@ -352,7 +358,7 @@ int s2u_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, void* g, in
                  void* stream) {
   if (M <= 0 || (C & 7) || (ld_dy & 7) || (ld_y & 7) || (ld_g & 7)) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    relu_bwd_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, ld_dy, (const T*)y,
+    S2U_LAUNCH((relu_bwd_kernel<T>), grid_for(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream, (const T*)dy, ld_dy, (const T*)y,
                                                                                    ld_y, (T*)g, ld_g, M, C);
   })
   S2U_LAUNCH_CHECK();
@@ -370,13 +376,13 @@ int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x
   const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(bn_bwd_reduce_kernel<T>);
-    bn_bwd_reduce_kernel<T><<<bn_reduce_grid(M, C), 256, smem, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
+    S2U_LAUNCH((bn_bwd_reduce_kernel<T>), bn_reduce_grid(M, C), 256, smem, st, (const T*)dy, ld_dy, (const T*)y, ld_y,
                                                                     (const T*)x, ldx, mean, rstd, sums, dgamma, dbeta,
                                                                     c1, c2, M, C);
   })
   S2U_LAUNCH_CHECK();
   S2U_DISPATCH_T(dtype, {
-    bn_bwd_apply_kernel<T><<<grid_for(M * (C >> 3), 256), 256, 0, st>>>((const T*)dy, ld_dy, (const T*)y, ld_y,
+    S2U_LAUNCH((bn_bwd_apply_kernel<T>), grid_for(M * (C >> 3), 256), 256, 0, st, (const T*)dy, ld_dy, (const T*)y, ld_y,
                                                                        (const T*)x, ldx, mean, rstd, gamma, c1, c2,
                                                                        (T*)dx, ld_dx, M, C);
   })

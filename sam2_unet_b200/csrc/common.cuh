@@ -19,6 +19,47 @@ enum S2uDtype { S2U_F32 = 0, S2U_BF16 = 1 };
     if (e__ != cudaSuccess) return (int)e__;    \
   } while (0)
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------
+// A train step is ~1,700 short kernels in dependency order; the launch + scheduling latency between two of them is
+// comparable to the run time of the small ones.  Every kernel of this library starts with pdl_sync(): it lets the NEXT
+// kernel of the stream be scheduled (griddepcontrol.launch_dependents) and then waits until the PREVIOUS one has
+// completed and flushed (griddepcontrol.wait) before touching memory, and every launch goes through S2U_LAUNCH,
+// which marks the kernel as programmatically serialised - so the launch latency of kernel N+1 overlaps kernel N
+// (CUDA graphs record this as programmatic edges).  S2U_PDL=0 in the environment restores plain stream order.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+#ifdef __CUDACC__
+#include <cstdlib>
+static inline bool s2u_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("S2U_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+static inline void s2u_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = s2u_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface in S2U_LAUNCH_CHECK
+}
+#define S2U_LAUNCH(kernel, grid, block, smem, stream, ...) s2u_launch(kernel, grid, block, smem, stream, __VA_ARGS__)
+#endif
+
 // opt a kernel into > 48 KB of dynamic shared memory, once per instantiation
 #define S2U_ALLOW_SMEM(kernel)                                                                          \
   do {                                                                                                  \

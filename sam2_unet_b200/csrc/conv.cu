@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
                                                          const float* __restrict__ bias,
                                                          const float* __restrict__ pos, void* __restrict__ out,
                                                          int out_f32, T* __restrict__ out_copy, int B, int S, int E) {
+  pdl_sync();
   extern __shared__ float sm[];
   float* wT = sm;                 // [147][E]
   float* patch = sm + 147 * E;    // [3][35][36]
@@ -77,6 +78,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int B,
                                                     int H, int W, int Cin, int KH, int KW, int dh, int dw, int ph,
                                                     int pw) {
+  pdl_sync();
   const int C8 = Cin >> 3;
   const int taps = KH * KW;
   const long long total = (long long)B * H * W * C8;
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ x, in
 template <typename T>
 __global__ void conv_weight_pack_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout,
                                         int Cin, int KH, int KW) {
+  pdl_sync();
   const int taps = KH * KW;
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -140,7 +143,7 @@ int s2u_patch_embed(const float* x, const float* w, const float* bias, const flo
   dim3 grid(((Hp + 7) / 8) * ((Hp + 7) / 8), B);
   S2U_DISPATCH_T(dtype, {
     S2U_ALLOW_SMEM(patch_embed_kernel<T>);
-    patch_embed_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, pos, out, out_f32, (T*)out_copy, B, S,
+    S2U_LAUNCH((patch_embed_kernel<T>), grid, 256, smem, (cudaStream_t)stream, x, w, bias, pos, out, out_f32, (T*)out_copy, B, S,
                                                                      E);
   })
   S2U_LAUNCH_CHECK();
@@ -152,7 +155,7 @@ int s2u_im2col(const void* x, int ldx, void* out, int B, int H, int W, int Cin, 
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin & 7) || (ldx & 7)) return S2U_EINVAL;
   const long long total = (long long)B * H * W * (Cin / 8);
   S2U_DISPATCH_T(dtype, {
-    im2col_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, B, H, W, Cin,
+    S2U_LAUNCH((im2col_kernel<T>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x, ldx, (T*)out, B, H, W, Cin,
                                                                           KH, KW, dil_h, dil_w, pad_h, pad_w);
   })
   S2U_LAUNCH_CHECK();
@@ -164,7 +167,7 @@ int s2u_conv_weight_pack(const float* w, void* wf, void* wd, int Cout, int Cin, 
   if (Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0) return S2U_EINVAL;
   const long long total = (long long)Cout * Cin * KH * KW;
   S2U_DISPATCH_T(dtype, {
-    conv_weight_pack_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cout, Cin,
+    S2U_LAUNCH((conv_weight_pack_kernel<T>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, w, (T*)wf, (T*)wd, Cout, Cin,
                                                                                     KH, KW);
   })
   S2U_LAUNCH_CHECK();

@@ -5,6 +5,7 @@
 template <typename T>
 __global__ void dgelu_mul_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ out,
                                  long long n8) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const F8 d = ld8(dy + i * 8), p = ld8(pre + i * 8);
     F8 o;
@@ -16,6 +17,7 @@ __global__ void dgelu_mul_kernel(const T* __restrict__ dy, const T* __restrict__
 
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n8) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const F8 x = ld8(a + i * 8), y = ld8(b + i * 8);
     F8 o;
@@ -28,6 +30,7 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
 // x [B,H,W,C] -> out [B,H/2,W/2,C]  (floor mode)
 template <typename T>
 __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C) {
+  pdl_sync();
   const int Ho = H / 2, Wo = W / 2, C8 = C >> 3;
   const long long total = (long long)B * Ho * Wo * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -51,6 +54,7 @@ __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ out
 template <typename T>
 __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dout, T* __restrict__ dx, int B,
                                     int H, int W, int C) {
+  pdl_sync();
   const int Ho = H / 2, Wo = W / 2, C8 = C >> 3;
   const int Hc = (H + 1) / 2, Wc = (W + 1) / 2;
   const long long total = (long long)B * Hc * Wc * C8;
@@ -97,6 +101,7 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
 // dst[c, r] = (T) src[r, c]  (or plain cast when transpose == 0)
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int R, int C, int transpose) {
+  pdl_sync();
   const long long total = (long long)R * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -122,6 +127,7 @@ struct S2uRefreshEntry {
 template <typename T>
 __global__ void __launch_bounds__(256) refresh_kernel(const S2uRefreshEntry* __restrict__ entries,
                                                      const int2* __restrict__ blocks) {
+  pdl_sync();
   const int2 bk = blocks[blockIdx.x];
   const S2uRefreshEntry e = entries[bk.x];
   const float* src = reinterpret_cast<const float*>(e.src);
@@ -163,7 +169,7 @@ extern "C" {
 int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int dtype, void* stream) {
   if (n <= 0 || (n & 7)) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    dgelu_mul_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)pre, (T*)out,
+    S2U_LAUNCH((dgelu_mul_kernel<T>), grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, (const T*)dy, (const T*)pre, (T*)out,
                                                                              n / 8);
   })
   S2U_LAUNCH_CHECK();
@@ -173,7 +179,7 @@ int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int d
 int s2u_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
   if (n <= 0 || (n & 7)) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    add_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n / 8);
+    S2U_LAUNCH((add_kernel<T>), grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, (T*)out, n / 8);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -183,7 +189,7 @@ int s2u_maxpool2_fwd(const void* x, void* out, int B, int H, int W, int C, int d
   if (B <= 0 || H < 2 || W < 2 || (C & 7)) return S2U_EINVAL;
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   S2U_DISPATCH_T(dtype, {
-    maxpool2_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, B, H, W, C);
+    S2U_LAUNCH((maxpool2_fwd_kernel<T>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)out, B, H, W, C);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -193,7 +199,7 @@ int s2u_maxpool2_bwd(const void* x, const void* dout, void* dx, int B, int H, in
   if (B <= 0 || H < 2 || W < 2 || (C & 7)) return S2U_EINVAL;
   const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   S2U_DISPATCH_T(dtype, {
-    maxpool2_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dout,
+    S2U_LAUNCH((maxpool2_bwd_kernel<T>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x, (const T*)dout,
                                                                                 (T*)dx, B, H, W, C);
   })
   S2U_LAUNCH_CHECK();
@@ -203,7 +209,7 @@ int s2u_maxpool2_bwd(const void* x, const void* dout, void* dx, int B, int H, in
 int s2u_refresh_shadows(const void* entries, const void* blocks, int nblocks, int dtype, void* stream) {
   if (nblocks <= 0 || !entries || !blocks) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    refresh_kernel<T><<<nblocks, 256, 0, (cudaStream_t)stream>>>((const S2uRefreshEntry*)entries, (const int2*)blocks);
+    S2U_LAUNCH((refresh_kernel<T>), nblocks, 256, 0, (cudaStream_t)stream, (const S2uRefreshEntry*)entries, (const int2*)blocks);
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -212,7 +218,7 @@ int s2u_refresh_shadows(const void* entries, const void* blocks, int nblocks, in
 int s2u_cast(const float* src, void* dst, int R, int C, int transpose, int dtype, void* stream) {
   if (R <= 0 || C <= 0) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    cast_kernel<T><<<grid_for((long long)R * C, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, R, C, transpose);
+    S2U_LAUNCH((cast_kernel<T>), grid_for((long long)R * C, 256), 256, 0, (cudaStream_t)stream, src, (T*)dst, R, C, transpose);
   })
   S2U_LAUNCH_CHECK();
   return 0;

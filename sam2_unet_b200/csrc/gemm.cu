@@ -58,6 +58,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W,
                                                        int ldw, T* __restrict__ C, int ldc, int M, int N, int K,
                                                        EpiView<T> epi) {
+  pdl_sync();
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
@@ -116,6 +117,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B,
                                                         int ldb, float* __restrict__ G, int ldg, long long M, int P,
                                                         int Q, int q_inner, int q_taps, int rows_per_split) {
+  pdl_sync();
   constexpr int BP = 64, BQ = 64, BK = 16;
   __shared__ float As[BK][BP + 4];
   __shared__ float Bs[BK][BQ + 4];
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const T* __restrict__ A
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ A, int lda, float* __restrict__ out,
                                                     long long M, int P, int rows_per_block) {
+  pdl_sync();
   const int p = blockIdx.x * 64 + (threadIdx.x & 63);
   const int sub = threadIdx.x >> 6;
   const long long mbeg = (long long)blockIdx.y * rows_per_block;
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const __grid_constant__ 
                                                        const __grid_constant__ CUtensorMap tma_b,
                                                        bf16* __restrict__ C, int ldc, int M, int N, int K,
                                                        EpiView<bf16> epi) {
+  pdl_sync();
   using cfg = Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -813,6 +817,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
 
+  pdl_launch_dependents();                     // the prologue below overlaps the tail of the previous kernel
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -836,6 +841,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  pdl_wait();                                  // operands / side inputs of the previous kernel are complete
 
   if (warp == 0) {
     if (lane == 0) {
@@ -926,6 +932,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
   const int num_kb = (K + BK - 1) / BK;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
+  pdl_launch_dependents();                     // the prologue below overlaps the tail of the previous kernel
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -949,6 +956,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  pdl_wait();                                  // operands / side inputs of the previous kernel are complete
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1041,6 +1049,7 @@ __global__ void __launch_bounds__(128) wgrad_umma_kernel(const __grid_constant__
                                                         const __grid_constant__ CUtensorMap tma_y,
                                                         float* __restrict__ G, int ldg, int M, int X, int Y, int swap,
                                                         int q_inner, int q_taps, int kb_per_split) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
   __shared__ uint32_t tmem_holder;
@@ -1211,7 +1220,7 @@ static int launch(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int l
     attr_set = true;
   }
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  gemm_umma_kernel<BN, STAGES><<<grid, 128, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K, EpiView<bf16>(e));
+  S2U_LAUNCH((gemm_umma_kernel<BN, STAGES>), grid, 128, cfg::SMEM_BYTES, st, ma, mb, C, ldc, M, N, K, EpiView<bf16>(e));
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -1249,10 +1258,10 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
   const int grid = tiles < num_sms() ? tiles : num_sms();
   if (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) {
     if (e.flags & (GEMM_DGELU | GEMM_MULAUX)) return S2U_EUNSUPPORTED;
-    gemm_umma_ws_kernel<BN, STAGES, true><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
+    S2U_LAUNCH((gemm_umma_ws_kernel<BN, STAGES, true>), grid, WS_THREADS, cfg::SMEM_BYTES, st, ma, mb, C, ldc, M, N, K,
                                                                                   EpiView<bf16>(e));
   } else {
-    gemm_umma_ws_kernel<BN, STAGES, false><<<grid, WS_THREADS, cfg::SMEM_BYTES, st>>>(ma, mb, C, ldc, M, N, K,
+    S2U_LAUNCH((gemm_umma_ws_kernel<BN, STAGES, false>), grid, WS_THREADS, cfg::SMEM_BYTES, st, ma, mb, C, ldc, M, N, K,
                                                                                    EpiView<bf16>(e));
   }
   S2U_LAUNCH_CHECK();
@@ -1286,13 +1295,15 @@ static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, 
   lc.blockDim = dim3(WS_THREADS);
   lc.dynamicSmemBytes = cfg::SMEM_BYTES;
   lc.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
-  lc.numAttrs = 1;
+  lc.numAttrs = s2u_pdl_enabled() ? 2 : 1;
   const bool f32s = e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL);
   if (f32s && (e.flags & (GEMM_DGELU | GEMM_MULAUX))) return S2U_EUNSUPPORTED;
   cudaError_t ce = f32s ? cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STAGES, true>, ma, mb, C, ldc, M, N, K,
@@ -1360,7 +1371,7 @@ static int launch_wgrad(const bf16* A, int lda, const bf16* B, int ldb, float* G
   const int kb_per = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per - 1) / kb_per;
   dim3 grid(x_tiles, 1, splits);
-  wgrad_umma_kernel<<<grid, 128, WG_SMEM_BYTES, st>>>(mx, my, G, ldg, (int)M, X, Y, swap, q_inner, q_taps, kb_per);
+  S2U_LAUNCH((wgrad_umma_kernel), grid, 128, WG_SMEM_BYTES, st, mx, my, G, ldg, (int)M, X, Y, swap, q_inner, q_taps, kb_per);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -1443,7 +1454,7 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
   if (backend >= 2) return S2U_EUNSUPPORTED;
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
   S2U_DISPATCH_T(dtype, {
-    gemm_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)A, lda, (const T*)W, ldw, (T*)C, ldc, M, N, K, EpiView<T>(e));
+    S2U_LAUNCH((gemm_simt_kernel<T>), grid, 256, 0, st, (const T*)A, lda, (const T*)W, ldw, (T*)C, ldc, M, N, K, EpiView<T>(e));
   })
   S2U_LAUNCH_CHECK();
   return 0;
@@ -1469,7 +1480,7 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
   splits = (int)((M + rows - 1) / rows);
   dim3 grid(ceil_div(Q, 64), ceil_div(P, 64), splits);
   S2U_DISPATCH_T(dtype, {
-    gemm_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, lda, (const T*)B, ldb, G, ldg, M, P, Q,
+    S2U_LAUNCH((gemm_wgrad_kernel<T>), grid, 256, 0, (cudaStream_t)stream, (const T*)A, lda, (const T*)B, ldb, G, ldg, M, P, Q,
                                                                  q_inner, q_taps, rows);
   })
   S2U_LAUNCH_CHECK();
@@ -1484,7 +1495,7 @@ int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype
   const int rows = (int)((M + blocks_y - 1) / blocks_y);
   dim3 grid(ceil_div(P, 64), blocks_y);
   S2U_DISPATCH_T(dtype, {
-    colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, lda, out, M, P, rows);
+    S2U_LAUNCH((colsum_kernel<T>), grid, 256, 0, (cudaStream_t)stream, (const T*)A, lda, out, M, P, rows);
   })
   S2U_LAUNCH_CHECK();
   return 0;

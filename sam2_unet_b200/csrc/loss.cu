@@ -21,6 +21,7 @@ struct LossPtrs { const float* pred[MAXH]; float* grad[MAXH]; };
 __global__ void __launch_bounds__(256) loss_fwd_kernel(LossPtrs p, const float* __restrict__ mask,
                                                       float* __restrict__ weit, double* __restrict__ sums, int B,
                                                       int H, int W, int nheads) {
+  pdl_sync();
   __shared__ float tile[LT_H + 2 * LR][LT_W + 2 * LR + 2];   // mask halo tile
   __shared__ float hsum[LT_H + 2 * LR][LT_W + 1];            // horizontal 31-tap sums
   __shared__ float red[8][MAXH * 3];
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(LossPtrs p, const float* 
 // loss[h] = bce_h / (B H W) + (1/B) sum_b (1 - N_b / D_b)
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, float* __restrict__ loss, int B, int H, int W,
                                      int nheads) {
+  pdl_sync();
   const int h = threadIdx.x;
   if (h >= nheads) return;
   double l = sums[(long long)nheads * B * 2 + h] / ((double)B * H * W);
@@ -96,6 +98,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, float* __r
 __global__ void loss_bwd_kernel(LossPtrs p, const float* __restrict__ mask, const float* __restrict__ weit,
                                 const double* __restrict__ sums, const float* __restrict__ gscale, int B, int H,
                                 int W, int nheads) {
+  pdl_sync();
   const long long hw = (long long)H * W;
   const long long total = (long long)B * hw;
   const float inv_n = 1.f / (float)total, inv_b = 1.f / (float)B;
@@ -118,6 +121,7 @@ __global__ void loss_bwd_kernel(LossPtrs p, const float* __restrict__ mask, cons
 // The step counter lives on the device ([2], [3] are advanced by adamw_tick_kernel right before the update), so a
 // captured CUDA graph replays the step without any host-side hyper-parameter traffic.
 __global__ void adamw_tick_kernel(float* __restrict__ hyper, float beta1, float beta2) {
+  pdl_sync();
   hyper[2] *= beta1;
   hyper[3] *= beta2;
 }
@@ -125,6 +129,7 @@ __global__ void adamw_tick_kernel(float* __restrict__ hyper, float beta1, float 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, const float* __restrict__ hyper, float beta1,
                              float beta2, float eps, float wd) {
+  pdl_sync();
   const float lr = hyper[0], gs = hyper[1], bc1 = 1.f - hyper[2], bc2 = 1.f - hyper[3];
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
@@ -151,9 +156,9 @@ int s2u_structure_loss_fwd(const float* pred0, const float* pred1, const float* 
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * ((size_t)nheads * B * 2 + nheads), st);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(ceil_div(W, LT_W), ceil_div(H, LT_H), B);
-  loss_fwd_kernel<<<grid, 256, 0, st>>>(p, mask, weit, sums, B, H, W, nheads);
+  S2U_LAUNCH((loss_fwd_kernel), grid, 256, 0, st, p, mask, weit, sums, B, H, W, nheads);
   S2U_LAUNCH_CHECK();
-  loss_finalize_kernel<<<1, 32, 0, st>>>(sums, loss, B, H, W, nheads);
+  S2U_LAUNCH((loss_finalize_kernel), 1, 32, 0, st, sums, loss, B, H, W, nheads);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -166,7 +171,7 @@ int s2u_structure_loss_bwd(const float* pred0, const float* pred1, const float* 
   long long total = (long long)B * H * W;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  loss_bwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, mask, weit, sums, gscale, B, H, W, nheads);
+  S2U_LAUNCH((loss_bwd_kernel), (int)g, 256, 0, (cudaStream_t)stream, p, mask, weit, sums, gscale, B, H, W, nheads);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -176,9 +181,9 @@ int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, float* 
   if (n <= 0) return S2U_EINVAL;
   long long gsz = (n + 255) / 256;
   if (gsz > 148 * 16) gsz = 148 * 16;
-  adamw_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, beta1, beta2);
+  S2U_LAUNCH((adamw_tick_kernel), 1, 1, 0, (cudaStream_t)stream, hyper, beta1, beta2);
   S2U_LAUNCH_CHECK();
-  adamw_kernel<<<(int)gsz, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, beta1, beta2, eps, wd);
+  S2U_LAUNCH((adamw_kernel), (int)gsz, 256, 0, (cudaStream_t)stream, p, g, m, v, n, hyper, beta1, beta2, eps, wd);
   S2U_LAUNCH_CHECK();
   return 0;
 }

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
                                                     const float* __restrict__ beta, T* __restrict__ y,
                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                     long long R, int C, float eps, int lpr) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rpw = 32 / lpr, sub = lane & (lpr - 1);
   const long long row = ((long long)blockIdx.x * 8 + warp) * rpw + lane / lpr;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
                                                     T* __restrict__ dx2, float* __restrict__ colsum,
                                                     float* __restrict__ ws, int pre_is_grad, long long R, int C,
                                                     int lpr) {
+  pdl_sync();
   extern __shared__ float tile[];            // [8 * rpw rows][C] dx2 values of this block (only when colsum != null)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rpw = 32 / lpr, sub = lane & (lpr - 1);
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 // (tiny) launch on purpose: a "last block done" ticket inside ln_bwd_kernel needs a __threadfence and an atomic round
 // trip at the end of every block, which doubled the lifetime of these short blocks (measured 35 us instead of 17).
 __global__ void __launch_bounds__(256) ln_colsum_fold_kernel(float* __restrict__ ws, float* __restrict__ colsum, int C) {
+  pdl_sync();
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= C) return;
   float v[LN_NREP];
@@ -258,13 +261,13 @@ int s2u_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
   if (x_f32 || dtype == S2U_F32) {
     S2U_DISPATCH_T(dtype, {
       LN_DISPATCH_NCH(nch, {
-        ln_fwd_kernel<T, float, NCH><<<grid, 256, 0, st>>>((const float*)x, gamma, beta, (T*)y, mean, rstd, R, C, eps,
+        S2U_LAUNCH((ln_fwd_kernel<T, float, NCH>), grid, 256, 0, st, (const float*)x, gamma, beta, (T*)y, mean, rstd, R, C, eps,
                                                           lpr);
       })
     })
   } else {
     LN_DISPATCH_NCH(nch, {
-      ln_fwd_kernel<bf16, bf16, NCH><<<grid, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, R, C, eps,
+      S2U_LAUNCH((ln_fwd_kernel<bf16, bf16, NCH>), grid, 256, 0, st, (const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, R, C, eps,
                                                           lpr);
     })
   }
@@ -291,21 +294,21 @@ int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   if (x_f32 || dtype == S2U_F32) {
     S2U_DISPATCH_T(dtype, {
       LN_DISPATCH_NCH(nch, {
-        ln_bwd_kernel<T, float, NCH><<<grid, 256, smem, st>>>((const T*)dy, (const float*)x, gamma, mean, rstd,
+        S2U_LAUNCH((ln_bwd_kernel<T, float, NCH>), grid, 256, smem, st, (const T*)dy, (const float*)x, gamma, mean, rstd,
                                                              (const T*)dres, (T*)dx, (const T*)pre, (T*)dx2, colsum,
                                                              ws, pre_is_grad, R, C, lpr);
       })
     })
   } else {
     LN_DISPATCH_NCH(nch, {
-      ln_bwd_kernel<bf16, bf16, NCH><<<grid, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
+      S2U_LAUNCH((ln_bwd_kernel<bf16, bf16, NCH>), grid, 256, smem, st, (const bf16*)dy, (const bf16*)x, gamma, mean, rstd,
                                                              (const bf16*)dres, (bf16*)dx, (const bf16*)pre,
                                                              (bf16*)dx2, colsum, ws, pre_is_grad, R, C, lpr);
     })
   }
   S2U_LAUNCH_CHECK();
   if (colsum) {
-    ln_colsum_fold_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ws, colsum, C);
+    S2U_LAUNCH((ln_colsum_fold_kernel), ceil_div(C, 256), 256, 0, st, ws, colsum, C);
     S2U_LAUNCH_CHECK();
   }
   return 0;

@@ -16,6 +16,7 @@ struct AxisBwd { const int* idx; const float* w; int taps; };   // [n_in, taps],
 template <typename T>
 __global__ void resample_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ld_out, int B, int Hi,
                                     int Wi, int Ho, int Wo, int C, AxisFwd ay, AxisFwd ax) {
+  pdl_sync();
   const int cg = C >> 3;
   const long long total = (long long)B * Ho * Wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -41,6 +42,7 @@ __global__ void resample_fwd_kernel(const T* __restrict__ x, int ldx, T* __restr
 template <typename T>
 __global__ void resample_bwd_kernel(const T* __restrict__ dout, int ld_do, T* __restrict__ dx, int ld_dx, int B,
                                     int Hi, int Wi, int Ho, int Wo, int C, AxisBwd ay, AxisBwd ax) {
+  pdl_sync();
   const int cg = C >> 3;
   const long long total = (long long)B * Hi * Wi * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -74,6 +76,7 @@ __global__ void resample_bwd_kernel(const T* __restrict__ dout, int ld_do, T* __
 // single-channel fp32 variants (the logits maps)
 __global__ void resample1_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Hi, int Wi,
                                      int Ho, int Wo, AxisFwd ay, AxisFwd ax) {
+  pdl_sync();
   const long long total = (long long)B * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -89,6 +92,7 @@ __global__ void resample1_fwd_kernel(const float* __restrict__ x, float* __restr
 
 __global__ void resample1_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int Hi, int Wi,
                                      int Ho, int Wo, AxisBwd ay, AxisBwd ax) {
+  pdl_sync();
   // one warp per input pixel: lanes split the (up to taps^2) contributing output pixels
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +117,7 @@ __global__ void resample1_bwd_kernel(const float* __restrict__ dout, float* __re
 template <typename T>
 __global__ void head_fwd_kernel(const T* __restrict__ feat, int ldf_, const float* __restrict__ w,
                                 const float* __restrict__ bias, float* __restrict__ out, long long M, int C) {
+  pdl_sync();
   const int cg = C >> 3;                    // lanes per pixel (8 for C = 64)
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = gid / cg;
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ fea
                                                       T* __restrict__ dfeat, int ld_df, int accumulate,
                                                       float* __restrict__ dw, float* __restrict__ db, long long M,
                                                       int C, int rows_per_block) {
+  pdl_sync();
   __shared__ float red[32][65];
   const int cg = C >> 3;                    // 8
   const int g = threadIdx.x % cg, sub = threadIdx.x / cg;     // sub: 0..31
@@ -183,7 +189,7 @@ int s2u_resample_fwd(const void* x, int ldx, void* out, int ld_out, int B, int H
   if (B <= 0 || (C & 7) || (ldx & 7) || (ld_out & 7)) return S2U_EINVAL;
   AxisFwd ay{y_i0, y_i1, y_w0, y_w1}, ax{x_i0, x_i1, x_w0, x_w1};
   S2U_DISPATCH_T(dtype, {
-    resample_fwd_kernel<T><<<grid_for((long long)B * Ho * Wo * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+    S2U_LAUNCH((resample_fwd_kernel<T>), grid_for((long long)B * Ho * Wo * (C >> 3), 256), 256, 0, (cudaStream_t)stream, 
         (const T*)x, ldx, (T*)out, ld_out, B, Hi, Wi, Ho, Wo, C, ay, ax);
   })
   S2U_LAUNCH_CHECK();
@@ -196,7 +202,7 @@ int s2u_resample_bwd(const void* dout, int ld_do, void* dx, int ld_dx, int B, in
   if (B <= 0 || (C & 7) || (ld_do & 7) || (ld_dx & 7)) return S2U_EINVAL;
   AxisBwd ay{y_idx, y_w, y_taps}, ax{x_idx, x_w, x_taps};
   S2U_DISPATCH_T(dtype, {
-    resample_bwd_kernel<T><<<grid_for((long long)B * Hi * Wi * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+    S2U_LAUNCH((resample_bwd_kernel<T>), grid_for((long long)B * Hi * Wi * (C >> 3), 256), 256, 0, (cudaStream_t)stream, 
         (const T*)dout, ld_do, (T*)dx, ld_dx, B, Hi, Wi, Ho, Wo, C, ay, ax);
   })
   S2U_LAUNCH_CHECK();
@@ -208,7 +214,7 @@ int s2u_resample1_fwd(const float* x, float* out, int B, int Hi, int Wi, int Ho,
                       const float* x_w0, const float* x_w1, void* stream) {
   if (B <= 0) return S2U_EINVAL;
   AxisFwd ay{y_i0, y_i1, y_w0, y_w1}, ax{x_i0, x_i1, x_w0, x_w1};
-  resample1_fwd_kernel<<<grid_for((long long)B * Ho * Wo, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, Hi, Wi, Ho,
+  S2U_LAUNCH((resample1_fwd_kernel), grid_for((long long)B * Ho * Wo, 256), 256, 0, (cudaStream_t)stream, x, out, B, Hi, Wi, Ho,
                                                                                              Wo, ay, ax);
   S2U_LAUNCH_CHECK();
   return 0;
@@ -219,7 +225,7 @@ int s2u_resample1_bwd(const float* dout, float* dx, int B, int Hi, int Wi, int H
   if (B <= 0) return S2U_EINVAL;
   AxisBwd ay{y_idx, y_w, y_taps}, ax{x_idx, x_w, x_taps};
   const long long warps = (long long)B * Hi * Wi;
-  resample1_bwd_kernel<<<ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, Hi, Wi, Ho, Wo, ay,
+  S2U_LAUNCH((resample1_bwd_kernel), ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream, dout, dx, B, Hi, Wi, Ho, Wo, ay,
                                                                                   ax);
   S2U_LAUNCH_CHECK();
   return 0;
@@ -229,7 +235,7 @@ int s2u_head_fwd(const void* feat, int ldf_, const float* w, const float* bias, 
                  int dtype, void* stream) {
   if (M <= 0 || C != 64 || (ldf_ & 7)) return S2U_EINVAL;
   S2U_DISPATCH_T(dtype, {
-    head_fwd_kernel<T><<<ceil_div(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>((const T*)feat, ldf_, w, bias,
+    S2U_LAUNCH((head_fwd_kernel<T>), ceil_div(M * (C >> 3), 256), 256, 0, (cudaStream_t)stream, (const T*)feat, ldf_, w, bias,
                                                                                     out, M, C);
   })
   S2U_LAUNCH_CHECK();
@@ -241,7 +247,7 @@ int s2u_head_bwd(const void* feat, int ldf_, const float* w, const float* dlogit
   if (M <= 0 || C != 64 || (ldf_ & 7) || (ld_df & 7)) return S2U_EINVAL;
   const int rows = 1024;
   S2U_DISPATCH_T(dtype, {
-    head_bwd_kernel<T><<<ceil_div(M, rows), 256, 0, (cudaStream_t)stream>>>((const T*)feat, ldf_, w, dlogit, (T*)dfeat,
+    S2U_LAUNCH((head_bwd_kernel<T>), ceil_div(M, rows), 256, 0, (cudaStream_t)stream, (const T*)feat, ldf_, w, dlogit, (T*)dfeat,
                                                                            ld_df, accumulate, dw, db, M, C, rows);
   })
   S2U_LAUNCH_CHECK();
