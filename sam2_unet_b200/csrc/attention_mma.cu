@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
 
 // --------------------------------------------------------------------------------------- backward: dK, dV
 template <int HDP>
-__global__ void __launch_bounds__(NT) bwd_dkv_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+__global__ void __launch_bounds__(NT, 3) bwd_dkv_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                     const float* __restrict__ lse, const float* __restrict__ Dv,
                                                     const bf16* __restrict__ dout, bf16* __restrict__ dqkv, Geom g) {
   pdl_sync();
