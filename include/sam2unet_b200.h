@@ -85,6 +85,10 @@ int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const 
 /* out: fp32 when out_f32 else the compute dtype; out_copy (optional): compute-dtype copy of the same tokens. */
 int s2u_patch_embed(const float* x, const float* w, const float* bias, const float* pos, void* out, int out_f32,
                     void* out_copy, int B, int S, int E, int dtype, void* stream);
+/* Tensor-core form of the stem in bf16 mode: rows [B*(S/4)^2, 320] of the 7x7 / stride 4 / pad 3 patch matrix of the
+ * NCHW fp32 image, columns [0,147) = bf16(x) in nn.Conv2d weight order (ci, ky, kx), columns [160,307) =
+ * bf16(x - bf16(x)), zero elsewhere; multiplied by [W | W] with s2u_gemm (bias + position table as fp32 residual). */
+int s2u_patch_im2col(const float* x, void* out, int B, int S, void* stream);
 /* taps of a stride-1 conv gathered to [B*H*W, KH*KW*Cin] (SAM2UNet.py:68-125,9-26). */
 int s2u_im2col(const void* x, int ldx, void* out, int B, int H, int W, int Cin, int KH, int KW, int dil_h, int dil_w,
                int pad_h, int pad_w, int dtype, void* stream);

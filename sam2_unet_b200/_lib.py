@@ -31,6 +31,7 @@ SIGNATURES = {
     "s2u_win_attn_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P],
     "s2u_win_attn_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     "s2u_patch_embed": [P, P, P, P, P, I, P, I, I, I, I, P],
+    "s2u_patch_im2col": [P, P, I, I, P],
     "s2u_im2col": [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "s2u_conv_weight_pack": [P, P, P, I, I, I, I, I, P],
     "s2u_bn_ws_doubles": [I],

@@ -71,6 +71,44 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   }
 }
 
+// Tensor-core form of the stem (bf16 mode): rows of the 7x7/s4/p3 patch matrix, one row per token,
+//   out[m, k]       = bf16(x)              k = ci*49 + ky*7 + kx < 147   (nn.Conv2d weight order, utils.py:80-88)
+//   out[m, 160 + k] = bf16(x - bf16(x))    the rounding residual, so that the image enters the GEMM with ~16
+//                                          mantissa bits (the weight operand repeats W in both halves)
+// and zeros elsewhere (row pitch PE_K = 320).  One thread = one 16-byte chunk of a row.
+constexpr int PE_K = 320, PE_HALF = 160;
+__global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
+                                                          int S) {
+  pdl_sync();
+  const int Hp = S / 4;
+  const long long total = (long long)B * Hp * Hp * (PE_K / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (PE_K / 8));
+    const long long m = i / (PE_K / 8);
+    const int ox = (int)(m % Hp), oy = (int)((m / Hp) % Hp);
+    const long long b = m / ((long long)Hp * Hp);
+    const bool lo = c >= PE_HALF / 8;
+    const int kbase = (lo ? c - PE_HALF / 8 : c) * 8;
+    F8 v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kbase + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int ci = k / 49, r = k - ci * 49, ky = r / 7, kx = r - ky * 7;
+        const int iy = oy * 4 - 3 + ky, ix = ox * 4 - 3 + kx;
+        if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+          val = x[((b * 3 + ci) * S + iy) * S + ix];
+          if (lo) val -= __bfloat162float(__float2bfloat16(val));
+        }
+      }
+      v.v[j] = val;
+    }
+    st8(out + m * PE_K + c * 8, v);
+  }
+}
+
 // out[m, (ky*KW+kx)*Cin + ci] = x[b, y + ky*dh - ph, x + kx*dw - pw, ci]  (0 outside the map)
 // One thread = one (pixel, 8-channel group); it walks the taps, so the pixel decomposition is done once and a warp
 // writes full 16-byte-per-lane rows of the output matrix for every tap.
@@ -146,6 +184,15 @@ int s2u_patch_embed(const float* x, const float* w, const float* bias, const flo
     S2U_LAUNCH((patch_embed_kernel<T>), grid, 256, smem, (cudaStream_t)stream, x, w, bias, pos, out, out_f32, (T*)out_copy, B, S,
                                                                      E);
   })
+  S2U_LAUNCH_CHECK();
+  return 0;
+}
+
+// bf16 patch matrix [B*(S/4)^2, 320] of the stem for s2u_gemm (see patch_im2col_kernel)
+int s2u_patch_im2col(const float* x, void* out, int B, int S, void* stream) {
+  if (B <= 0 || S <= 0 || (S % 4)) return S2U_EINVAL;
+  const long long total = (long long)B * (S / 4) * (S / 4) * (PE_K / 8);
+  S2U_LAUNCH(patch_im2col_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, x, (bf16*)out, B, S);
   S2U_LAUNCH_CHECK();
   return 0;
 }

@@ -123,6 +123,9 @@ class Ops:
         _lib.call("s2u_patch_embed", x.data_ptr(), w.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(),
                   1 if out.dtype == torch.float32 else 0, _ptr(out_copy), B, S, E, self.dt, self.stream)
 
+    def patch_im2col(self, x, out, B, S):
+        _lib.call("s2u_patch_im2col", x.data_ptr(), out.data_ptr(), B, S, self.stream)
+
     def im2col(self, x, ldx, out, B, H, W, Cin, KH, KW, dh, dw, ph, pw):
         _lib.call("s2u_im2col", x.data_ptr(), ldx, out.data_ptr(), B, H, W, Cin, KH, KW, dh, dw, ph, pw, self.dt,
                   self.stream)
@@ -238,6 +241,12 @@ class Engine:
                 fz[p + nm + ".b"] = sd[p + nm + ".bias"].detach().float().contiguous()
         fz["pe.w"] = sd["encoder.patch_embed.proj.weight"].detach().float().contiguous()
         fz["pe.b"] = sd["encoder.patch_embed.proj.bias"].detach().float().contiguous()
+        if T != torch.float32:
+            # tensor-core stem: [W | W] against the (hi, lo) bf16 split of the image patches (s2u_patch_im2col)
+            w2 = torch.zeros(fz["pe.w"].shape[0], 320, dtype=T, device=fz["pe.w"].device)
+            w2[:, :147] = fz["pe.w"].reshape(-1, 147).to(T)
+            w2[:, 160:307] = w2[:, :147]
+            fz["pe.w2"] = w2
         self._pos_cache.clear()
 
     def _pos_table(self, hp: int) -> torch.Tensor:
@@ -249,6 +258,14 @@ class Engine:
             pos = pos + pw.tile([a // b for a, b in zip(pos.shape, pw.shape)])
             self._pos_cache[hp] = pos.permute(0, 2, 3, 1).contiguous().view(hp, hp, -1)
         return self._pos_cache[hp]
+
+    def _pos_bias_rows(self, B: int, hp: int) -> torch.Tensor:
+        """position table + stem bias expanded to one fp32 row per token of the batch (setup, cached)."""
+        key = ("rows", B, hp)
+        if key not in self._pos_cache:
+            t = self._pos_table(hp).reshape(1, hp * hp, -1) + self._frozen["pe.b"].view(1, 1, -1)
+            self._pos_cache[key] = t.expand(B, -1, -1).reshape(B * hp * hp, -1).contiguous()
+        return self._pos_cache[key]
 
     def refresh_shadows(self):
         """Compute-dtype operands of the TRAINABLE weights, rebuilt from the fp32 masters after every update by ONE
@@ -322,7 +339,15 @@ class Engine:
         mixed = self.T != torch.float32
         ts = ops.empty(B * H * H, E, dtype=torch.float32)
         tc = ops.empty(B * H * H, E) if mixed else ts
-        ops.patch_embed(x, fz["pe.w"], fz["pe.b"], self._pos_table(H), ts, B, S, E, out_copy=tc if mixed else None)
+        if mixed and E % 8 == 0:
+            # stem on the tensor cores: patch matrix (bf16 hi/lo split) x [W | W], bias + position table as the fp32
+            # residual of the stream epilogue
+            col = ops.empty(B * H * H, 320)
+            ops.patch_im2col(x, col, B, S)
+            ops.gemm(col, fz["pe.w2"], ts, resid=self._pos_bias_rows(B, H), pre_out=tc,
+                     flags=RESID | OUT_F32 | RESID_F32 | PRE_FINAL)
+        else:
+            ops.patch_embed(x, fz["pe.w"], fz["pe.b"], self._pos_table(H), ts, B, S, E, out_copy=tc if mixed else None)
         if tape is not None:
             tape["convs"] = {}
             tape["dec"] = {}

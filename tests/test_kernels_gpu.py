@@ -310,6 +310,33 @@ def test_patch_embed(cuda, dtype):
     assert torch.equal(oc, out)
 
 
+def test_patch_embed_tensor_core(cuda):
+    """bf16-mode stem: patch matrix with the image split into bf16 (hi, lo) halves x [W | W] on the GEMM kernel, bias +
+    position table as the fp32 residual; against F.conv2d with the bf16-rounded weights in fp32."""
+    ops = _ops("bf16", cuda)
+    B, S, E = 2, 96, 144
+    Hp = S // 4
+    x = _rand((B, 3, S, S), "fp32", cuda, 1) * 2
+    w, b = _rand((E, 3, 7, 7), "fp32", cuda, 2, 0.1), _rand((E,), "fp32", cuda, 3)
+    pos = _rand((Hp, Hp, E), "fp32", cuda, 4)
+    col = ops.empty(B * Hp * Hp, 320)
+    ops.patch_im2col(x, col, B, S)
+    patches = F.unfold(x, 7, padding=3, stride=4).transpose(1, 2).reshape(B * Hp * Hp, 147)
+    hi = patches.bfloat16()
+    assert torch.equal(col[:, :147], hi)
+    assert torch.equal(col[:, 160:307], (patches - hi.float()).bfloat16())
+    assert float(col[:, 147:160].abs().max()) == 0.0 and float(col[:, 307:].abs().max()) == 0.0
+    w2 = torch.zeros(E, 320, device=cuda, dtype=torch.bfloat16)
+    w2[:, :147] = w.reshape(E, 147).bfloat16()
+    w2[:, 160:307] = w2[:, :147]
+    rows = (pos.reshape(1, Hp * Hp, E) + b).expand(B, -1, -1).reshape(B * Hp * Hp, E).contiguous()
+    ts, tc = torch.empty(B * Hp * Hp, E, device=cuda), ops.empty(B * Hp * Hp, E)
+    ops.gemm(col, w2, ts, resid=rows, pre_out=tc, flags=4 | 16 | 32 | 64)
+    ref = F.conv2d(x, w.bfloat16().float(), b, stride=4, padding=3).permute(0, 2, 3, 1) + pos
+    _close(ts, ref.reshape(-1, E), 2e-4, "tensor-core stem (fp32 stream)")
+    _close(tc, ref.reshape(-1, E), 1e-2, "tensor-core stem (bf16 copy)")
+
+
 CONVS = [(64, 1, 3, 1), (64, 3, 1, 1), (64, 1, 7, 1), (64, 7, 1, 1), (64, 3, 3, 3), (64, 3, 3, 7), (256, 3, 3, 1),
          (128, 3, 3, 1)]
 
