@@ -33,7 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # (M, N, K) -> DRAM bytes of one launch measured by ncu --set full (see profiles/); filled per round
-NCU_TRAFFIC = {(5808, 2304, 576): 18.95e6}   # r1: 9.41 MB read + 9.54 MB written (L2 absorbs the rest)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM (stage-3 fc1, GELU + saved GELU'
+# epilogue) from profiles/r1_gemm_pair_full_raw.csv rows 3 and 9: 9.41 MB read + 3.2 / 2.6 MB written before the kernel
+# ends (the 126 MB L2 absorbs the rest of the 53 MB of output)
+NCU_TRAFFIC = {(5808, 2304, 576): 12.3e6}
 
 METRIC = {"train": "train img/s, SAM2-UNet Hiera-L 352x352 (fwd + 3x structure_loss + bwd + AdamW)",
           "infer": "infer img/s, SAM2-UNet Hiera-L 352x352 forward"}
@@ -387,11 +390,11 @@ def run_b200(args):
         in_step = tfl * tcalls / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
         all_tf = fl / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the committed
-        # `ncu --set full` capture (profiles/r1_gemm_ws256_full.md); None when the shape differs from the captured one
+        # `ncu --set full` capture (profiles/r1_gemm_pair_full_raw.csv); None when the shape differs from the captured one
         traffic = NCU_TRAFFIC.get((tm, tn, tk))
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "traffic": traffic,
-                "kernel": f"gemm_umma_ws_kernel (persistent tcgen05 + TMA GEMM), dominant shape M={tm} N={tn} K={tk}",
+                "kernel": f"gemm_umma_pair_kernel (persistent CTA-pair tcgen05 + TMA GEMM), dominant shape M={tm} N={tn} K={tk}",
                 "algorithmic_flop_per_launch": tfl, "launches_of_shape_per_step": tcalls,
                 "us_per_launch": b2b_us, "variants": b2b_detail,
                 "us_per_launch_in_step": tms / tcalls * 1e3, "achieved_in_step": in_step,
