@@ -42,6 +42,14 @@ METRIC = {"train": "train img/s, SAM2-UNet Hiera-L 352x352 (fwd + 3x structure_l
           "infer": "infer img/s, SAM2-UNet Hiera-L 352x352 forward"}
 
 
+def metric_name(args):
+    """BASELINE.json's metric on the default configuration; other trunks / sizes are named as what they are."""
+    if args.cfg == "sam2_hiera_l.yaml" and args.size == 352:
+        return METRIC[args.mode]
+    trunk = args.cfg.replace("sam2_hiera_", "Hiera-").replace(".yaml", "").replace("Hiera-l", "Hiera-L")
+    return METRIC[args.mode].replace("Hiera-L 352x352", f"{trunk} {args.size}x{args.size}")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,7 +181,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = (f"{done} timed step(s) of {args.cpu_batch} images (of the 12-image batch), oracle port of the reference "
               f"on torch-CPU fp32, {cores} threads")
-    line = {"impl": "reference", "metric": METRIC[args.mode], "value": ips, "unit": "img/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args), "value": ips, "unit": "img/s", "n_gpus": args.gpus,
             "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "cpu_batch": args.cpu_batch},
@@ -422,7 +430,7 @@ def run_b200(args):
                            "gemm_shapes": {k: {"calls": v[0], "ms": v[1], "us_per_call": v[1] / v[0] * 1e3}
                                            for k, v in sorted(gs.items(), key=lambda kv: -kv[1][1])}}, f, indent=1)
     if rank == 0:
-        line = {"metric": METRIC[args.mode], "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(args), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm + 3, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
