@@ -1130,7 +1130,9 @@ __global__ void __launch_bounds__(128) wgrad_umma_kernel(const __grid_constant__
       const int y = c * 32 + j;
       if (y >= Y) continue;
       const int p = swap ? y : x, q = swap ? x : y;
-      atomicAdd(G + (long long)p * ldg + (long long)(q % q_inner) * q_taps + q / q_inner, __uint_as_float(r[j]));
+      // plain [P, Q] layout (adapters) needs no tap arithmetic: 64 integer divisions per thread otherwise
+      const long long off = q_taps == 1 ? (long long)q : (long long)(q % q_inner) * q_taps + q / q_inner;
+      atomicAdd(G + (long long)p * ldg + off, __uint_as_float(r[j]));
     }
   }
   tc_fence_before();
