@@ -407,7 +407,6 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
 #pragma unroll
     for (int t = 0; t < 4; ++t) o[j][t] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows lane/4 and lane/4 + 8 of this warp's 16
-  const bool warp_live = q0 + warp * 16 < w.nq;
   for (int k0 = 0, it = 0; k0 < nk; k0 += BN, ++it) {
     const bf16* Ks = KV + (it & 1) * 2 * BN * LD;
     const bf16* Vs = Ks + BN * LD;
@@ -418,10 +417,6 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const bf16* __restrict__ qkv, c
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (!warp_live) {                                           // all 16 query rows of this warp are beyond nq
-      __syncthreads();
-      continue;
-    }
     float s[8][4];
     mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
     float t0 = -INFINITY, t1 = -INFINITY;
@@ -554,7 +549,6 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
   for (int j = 0; j < HDP / 8; ++j)
 #pragma unroll
     for (int t = 0; t < 4; ++t) dq[j][t] = 0.f;
-  const bool warp_live = q0 + warp * 16 < w.nq;
   for (int k0 = 0, it = 0; k0 < nk; k0 += BN, ++it) {
     const bf16* Ks = KV + (it & 1) * 2 * BN * LD;
     const bf16* Vs = Ks + BN * LD;
@@ -565,10 +559,6 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const bf16* __restrict__ qkv
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (!warp_live) {
-      __syncthreads();
-      continue;
-    }
     float s[8][4], dp[8][4];
     mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
     mm_ab_t<HDP>(dp, dOs, Vs, warp, lane);
@@ -646,7 +636,6 @@ __global__ void __launch_bounds__(NT, 3) bwd_dkv_kernel(const bf16* __restrict__
 #pragma unroll
     for (int t = 0; t < 4; ++t) { dk[j][t] = 0.f; dv[j][t] = 0.f; }
   const int kr0 = k0 + warp * 16 + (lane >> 2);            // this thread's key rows: kr0, kr0 + 8
-  const bool warp_live = k0 + warp * 16 < nk;
   for (int q0 = 0, it = 0; q0 < nq; q0 += BM, ++it) {
     const bf16* Qs = QO + (it & 1) * 2 * BM * LD;
     const bf16* dOs = Qs + BM * LD;
@@ -656,10 +645,6 @@ __global__ void __launch_bounds__(NT, 3) bwd_dkv_kernel(const bf16* __restrict__
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (!warp_live) {                                       // all 16 keys of this warp are beyond n_real
-      __syncthreads();
-      continue;
-    }
     float st[8][4], dpt[8][4];                              // [16 keys x 64 queries]
     mm_ab_t<HDP>(st, Ks, Qs, warp, lane);
     mm_ab_t<HDP>(dpt, Vs, dOs, warp, lane);
