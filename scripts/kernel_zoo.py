@@ -124,6 +124,27 @@ bench("attn_fwd global 12x22x22 h8 d72", R * Cc * 8, mka,
 bench("attn_bwd global 12x22x22 h8 d72", R * Cc * 16, mka2,
       lambda s: ops.attn_bwd(s["qkv"], s["bias"], s["o"], s["lse"], s["do"], s["dqkv"], B, H, H, nh, hd, 0, False))
 print(f"(attention fwd algorithmic FLOPs, windowed: {flops_f / 1e9:.2f} GFLOP; bwd 2.5x)")
+# the same kernels on windows that fill their 64-row tiles exactly (16x16 = 256 tokens, 32x32 map): tile-waste reference
+H2 = 32
+R2 = B * H2 * H2
+
+
+def mkb_():
+    return dict(qkv=r(R2, 3 * Cc), bias=r(3 * Cc, dt=f32), o=torch.empty(R2, Cc, device=dev, dtype=bf),
+                lse=torch.empty(R2, nh, device=dev), do=r(R2, Cc), dqkv=torch.empty(R2, 3 * Cc, device=dev, dtype=bf))
+
+
+def mkb2_():
+    s = mkb_()
+    ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H2, H2, nh, hd, 16, False)
+    return s
+
+
+bench("attn_fwd win16 12x32x32 h8 d72 (full tiles)", R2 * Cc * 8, mkb_,
+      lambda s: ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H2, H2, nh, hd, 16, False))
+bench("attn_bwd win16 12x32x32 h8 d72 (full tiles)", R2 * Cc * 16, mkb2_,
+      lambda s: ops.attn_bwd(s["qkv"], s["bias"], s["o"], s["lse"], s["do"], s["dqkv"], B, H2, H2, nh, hd, 16, False))
+print(f"(win16 fwd FLOPs: {4.0 * B * 4 * nh * 256 * 256 * hd / 1e9:.2f} GFLOP)")
 
 for (M, P) in [(5808, 576), (5808, 32)]:
     def mkc():
