@@ -83,6 +83,48 @@ def cosine_lr(epoch: int, t_max: int, base_lr: float = 1e-3, eta_min: float = 1e
     return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * epoch / t_max)) / 2
 
 
+class _Prefetch:
+    """Host -> device copy of the NEXT batch on a copy stream, overlapped with the step that is running now.
+
+    `put(tensors)` starts the copies into staging buffers; `take(tensors, dsts)` (called by the step that consumes the
+    same host tensors) makes the compute stream wait for them and moves staging -> the step's static inputs with
+    device-to-device copies.  Returns False when nothing matching was prefetched (the caller then copies directly)."""
+
+    def __init__(self):
+        self.stream = None
+        self.stage = None
+        self.src = None
+        self.ready = None
+        self.free = None
+
+    def put(self, dev, tensors):
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(dev)
+        if self.stage is None or any(a.shape != b.shape for a, b in zip(self.stage, tensors)):
+            self.stage = [torch.empty_like(t, device=dev) for t in tensors]
+            self.free = None
+        with torch.cuda.stream(self.stream):
+            if self.free is not None:
+                self.stream.wait_event(self.free)          # the previous step has finished reading the staging buffers
+            for d, t in zip(self.stage, tensors):
+                d.copy_(t, non_blocking=True)
+            self.ready = torch.cuda.Event()
+            self.ready.record(self.stream)
+        self.src = tensors
+
+    def take(self, tensors, dsts) -> bool:
+        if self.src is None or len(self.src) != len(tensors) or any(a is not b for a, b in zip(self.src, tensors)):
+            return False
+        cur = torch.cuda.current_stream(dsts[0].device)
+        cur.wait_event(self.ready)
+        for d, st in zip(dsts, self.stage):
+            d.copy_(st, non_blocking=True)
+        self.free = torch.cuda.Event()
+        self.free.record(cur)
+        self.src = None
+        return True
+
+
 class TrainStep:
     """The whole step of train.py:66-86 — forward, three structure_loss terms, backward, (all-reduce,) AdamW —
     as one launch sequence without autograd, optionally captured in a CUDA graph.
@@ -104,6 +146,15 @@ class TrainStep:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static = None
         self._warm = 0
+        self._pre = _Prefetch()
+
+    def prefetch(self, x: torch.Tensor, mask: torch.Tensor) -> None:
+        """Start copying the NEXT (pinned) host batch to the device while the current step runs; the following
+        `step(x, mask)` with the same two tensors picks the copy up instead of copying again."""
+        dev = next(self.model.parameters()).device
+        if x.device.type == "cpu" and x.dtype == torch.float32 and mask.dtype == torch.float32 and \
+                x.is_contiguous() and mask.is_contiguous():
+            self._pre.put(dev, [x, mask])
 
     # the raw launch sequence (capturable: no host sync, no allocation outside torch's caching allocator)
     def _run(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -137,6 +188,7 @@ class TrainStep:
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise _lib.KernelError("TrainStep needs the model on a CUDA device (no CPU fallback)")
+        x0, m0 = x, mask
         x = x.contiguous().float()
         mask = mask.contiguous().float()
         model._engine(dev)
@@ -151,8 +203,9 @@ class TrainStep:
                 self._graph = None
                 self._warm = 0
             _, sx, sm, sl = self._static
-            sx.copy_(x, non_blocking=True)
-            sm.copy_(mask, non_blocking=True)
+            if not self._pre.take([x0, m0], [sx, sm]):  # prefetched by the previous iteration, else copy now
+                sx.copy_(x, non_blocking=True)
+                sm.copy_(mask, non_blocking=True)
             if self._graph is None and self._warm < 2:
                 loss = self._run(sx, sm)                # eager warm-up: allocator pools, smem attributes, tensor maps
                 self._warm += 1
@@ -188,6 +241,13 @@ class Predictor:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._sx = self._outs = None
         self._warm = 0
+        self._pre = _Prefetch()
+
+    def prefetch(self, x: torch.Tensor) -> None:
+        """Start copying the NEXT (pinned) host batch while the current forward runs (see TrainStep.prefetch)."""
+        dev = next(self.model.parameters()).device
+        if x.device.type == "cpu" and x.dtype == torch.float32 and x.is_contiguous():
+            self._pre.put(dev, [x])
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor):
@@ -198,6 +258,7 @@ class Predictor:
         if model.training:
             model.eval()
         eng = model._engine(dev)
+        x0 = x
         x = x.contiguous().float()
         if not self.use_graph:
             return eng.forward(x.to(dev, non_blocking=True), False, save=False)
@@ -205,7 +266,8 @@ class Predictor:
         if key != self._key:
             self._key, self._graph, self._warm = key, None, 0
             self._sx = torch.empty_like(x, device=dev)
-        self._sx.copy_(x, non_blocking=True)
+        if not self._pre.take([x0], [self._sx]):
+            self._sx.copy_(x, non_blocking=True)
         if self._graph is None and self._warm < 2:
             self._warm += 1
             return eng.forward(self._sx, False, save=False)
