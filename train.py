@@ -136,11 +136,17 @@ def main(args):
             sampler.set_epoch(epoch)
         step.optim.param_groups[0]["lr"] = cosine_lr(epoch, args.epoch, args.lr)      # train.py:54,87
         t0, seen, loss = time.time(), 0, None
-        for i, batch in enumerate(loader):
+        it = iter(loader)
+        batch, i = next(it, None), 0
+        while batch is not None:
             loss = step(batch["image"], batch["label"])
+            nxt = next(it, None)                             # the next (pinned) batch starts its H2D copy while this
+            if nxt is not None:                              # step's kernels run
+                step.prefetch(nxt["image"], nxt["label"])
             seen += batch["image"].shape[0]
             if i % 10 == 0 and rank == 0:
                 print("epoch-{}-{}: loss:{}".format(epoch + 1, i + 1, loss.sum().item()))
+            batch, i = nxt, i + 1
         torch.cuda.synchronize(device)
         epoch_loss = loss.sum().item() if loss is not None else float("nan")
         if rank == 0:
