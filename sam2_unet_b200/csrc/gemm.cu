@@ -476,14 +476,17 @@ __device__ __forceinline__ void gelu_dgelu2(float2 x, float2& g, float2& d) {
 constexpr int WS_EPI_WARPS = 8;
 constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
 constexpr int EPI_BUF_BYTES = 32 * 64;                 // one staging tile: 32 rows x 64 bytes, 16-byte chunks XOR-swizzled
-constexpr int EPI_WARP_BYTES = 5 * EPI_BUF_BYTES;      // per epilogue warp: side input [chunk parity][half] + one output tile
+// per epilogue warp: side-input slots [chunk parity] (one tile, or two for the fp32 halves of the stream epilogue)
+// + one output tile
+constexpr int epi_warp_bytes(bool f32s) { return (f32s ? 5 : 3) * EPI_BUF_BYTES; }
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;            // shared::cluster address of the same offset in the pair's even CTA
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F32S>
 struct CfgWS {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARP_BYTES = epi_warp_bytes(F32S);
   static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -493,11 +496,12 @@ struct CfgWS {
 };
 // CTA pair (cta_group::2): the pair owns a 256 x BN tile; each CTA stages its own 128 rows of A and BN/2 rows of B and
 // keeps its own 128 x BN half of the accumulator, so the operand bytes each SM pulls from L2 per FLOP drop by a third
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F32S>
 struct Cfg2 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARP_BYTES = epi_warp_bytes(F32S);
   static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
   static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // accumulator stride
@@ -623,7 +627,8 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   const float* side32 = resid_f32 ? reinterpret_cast<const float*>(epi.resid) : nullptr;
   const bool has_side = side16 != nullptr || side32 != nullptr;
   const int nch = (BN - half * 32 + 63) / 64;                               // this warp's chunks per tile (0 when BN == 32)
-  const uint32_t so = stg + 4 * EPI_BUF_BYTES;                              // output staging tile
+  constexpr uint32_t SLOT = (F32S ? 2 : 1) * EPI_BUF_BYTES;                 // one chunk's side input
+  const uint32_t so = stg + 2 * SLOT;                                       // output staging tile
 
   auto prefetch = [&](int tile, int ci, int par) {
     const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
@@ -631,7 +636,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
     const int rows_ok = (int)min((long long)32, (long long)M - row0);
     const int cols_ok = min(min(32, BN - half * 32 - ci * 64), N - col0);
     if (rows_ok <= 0 || cols_ok <= 0) return;
-    const uint32_t b = stg + (uint32_t)(par * 2 * EPI_BUF_BYTES);
+    const uint32_t b = stg + (uint32_t)par * SLOT;
     if (side16) {
       g2s_async(b, reinterpret_cast<const char*>(side16 + row0 * ld16 + col0), ld16 * 2, rows_ok, cols_ok * 2, lane);
     } else {
@@ -680,7 +685,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
       cp_async_wait<1>();                                                   // this chunk's side input has landed
       __syncwarp();
       if (!live) continue;
-      const uint32_t h0 = stg + (uint32_t)(par * 2 * EPI_BUF_BYTES), h1 = h0 + EPI_BUF_BYTES;
+      const uint32_t h0 = stg + (uint32_t)par * SLOT, h1 = h0 + EPI_BUF_BYTES;   // h1: F32S only
       if (epi.bias) {
         if (cols_ok == 32) {
 #pragma unroll
@@ -799,7 +804,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
                                                                    const __grid_constant__ CUtensorMap tma_b,
                                                                    bf16* __restrict__ C, int ldc, int M, int N, int K,
                                                                    EpiView<bf16> epi) {
-  using cfg = CfgWS<BN, STAGES>;
+  using cfg = CfgWS<BN, STAGES, F32S>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_holder;
@@ -890,7 +895,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     t.tile_rows = BM; t.row_off = 0;
     t.tmem_base = tmem_base; t.acc_cols = cfg::ACC_COLS;
     t.tfull0 = tfull_bar(0); t.tempty0 = tempty_bar(0);
-    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
+    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
                             ldc, M, N, epi);
   }
   tc_fence_before();
@@ -912,7 +917,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
                                                                      const __grid_constant__ CUtensorMap tma_b,
                                                                      bf16* __restrict__ C, int ldc, int M, int N,
                                                                      int K, EpiView<bf16> epi) {
-  using cfg = Cfg2<BN, STAGES>;
+  using cfg = Cfg2<BN, STAGES, F32S>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_holder;
@@ -1006,7 +1011,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
     t.tile_rows = 2 * BM; t.row_off = (int)rank * BM;
     t.tmem_base = tmem_base; t.acc_cols = cfg::ACC_COLS;
     t.tfull0 = tfull_bar(0); t.tempty0 = tempty_bar(0) & PEER_MASK;
-    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
+    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
                             ldc, M, N, epi);
   }
   tc_fence_before();
@@ -1240,7 +1245,7 @@ static int num_sms() {
 template <int BN, int STAGES>
 static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
                      const GemmEpi& e, cudaStream_t st) {
-  using cfg = CfgWS<BN, STAGES>;
+  using cfg = CfgWS<BN, STAGES, true>;            // the larger of the two footprints
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, BM);
   if (rc) return rc;
@@ -1271,10 +1276,13 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
 }
 
 // CTA-pair kernel: clusters of 2, one pair per TPC
-template <int BN, int STAGES>
+// STP / STS: operand stages of the compute-dtype and of the stream (fp32 side input: larger staging) instantiation
+template <int BN, int STP, int STS>
 static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
                        const GemmEpi& e, cudaStream_t st) {
-  using cfg = Cfg2<BN, STAGES>;
+  using cfgp = Cfg2<BN, STP, false>;
+  using cfgs = Cfg2<BN, STS, true>;
+  static_assert(cfgp::SMEM_BYTES <= 227 * 1024 - 512 && cfgs::SMEM_BYTES <= 227 * 1024 - 512, "shared memory budget");
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, BM);
   if (rc) return rc;
@@ -1282,11 +1290,11 @@ static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, 
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_pair_kernel<BN, STAGES, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES);
+    cudaError_t ce = cudaFuncSetAttribute(gemm_umma_pair_kernel<BN, STP, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cfgp::SMEM_BYTES);
     if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(gemm_umma_pair_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                cfg::SMEM_BYTES);
+      ce = cudaFuncSetAttribute(gemm_umma_pair_kernel<BN, STS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                cfgs::SMEM_BYTES);
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
@@ -1295,7 +1303,8 @@ static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, 
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(2 * pairs);
   lc.blockDim = dim3(WS_THREADS);
-  lc.dynamicSmemBytes = cfg::SMEM_BYTES;
+  const bool f32s = e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL);
+  lc.dynamicSmemBytes = f32s ? cfgs::SMEM_BYTES : cfgp::SMEM_BYTES;
   lc.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1306,11 +1315,10 @@ static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, 
   at[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = s2u_pdl_enabled() ? 2 : 1;
-  const bool f32s = e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL);
   if (f32s && (e.flags & (GEMM_DGELU | GEMM_MULAUX))) return S2U_EUNSUPPORTED;
-  cudaError_t ce = f32s ? cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STAGES, true>, ma, mb, C, ldc, M, N, K,
+  cudaError_t ce = f32s ? cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STS, true>, ma, mb, C, ldc, M, N, K,
                                              EpiView<bf16>(e))
-                        : cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STAGES, false>, ma, mb, C, ldc, M, N, K,
+                        : cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STP, false>, ma, mb, C, ldc, M, N, K,
                                              EpiView<bf16>(e));
   if (ce != cudaSuccess) return (int)ce;
   S2U_LAUNCH_CHECK();
@@ -1436,12 +1444,12 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     }
     if (pair) {
       switch (bn) {
-        case 32: return umma::launch_pair<32, 8>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 64: return umma::launch_pair<64, 7>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 128: return umma::launch_pair<128, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 144: return umma::launch_pair<144, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 192: return umma::launch_pair<192, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 256: return umma::launch_pair<256, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 32: return umma::launch_pair<32, 8, 8>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 64: return umma::launch_pair<64, 8, 7>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 128: return umma::launch_pair<128, 7, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 144: return umma::launch_pair<144, 7, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 192: return umma::launch_pair<192, 6, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 256: return umma::launch_pair<256, 5, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         default: return S2U_EINVAL;
       }
     }
