@@ -145,6 +145,14 @@ int s2u_structure_loss_bwd(const float* pred0, const float* pred1, const float* 
 int s2u_adamw(float* p, const float* g, float* m, float* v, long long n, float* hyper, float beta1,
               float beta2, float eps, float wd, void* stream);
 
+/* ---- inference tail (test.py:66-76, train.py:103-112) ---------------------------------------------------------
+ * One image: crop the letterbox padding off the [S,S] fp32 logit map, bilinear-resize to [out_h,out_w]
+ * (align_corners = False), sigmoid, min-max normalise over the image, quantise to uint8 (truncation, like numpy's
+ * astype).  ws: two ints of device scratch armed once with s2u_infer_tail_init; every call leaves them re-armed. */
+int s2u_infer_tail_init(int* ws, void* stream);
+int s2u_infer_tail(const float* logits, int S, int pad_left, int pad_top, int pad_right, int pad_bottom, int out_h,
+                   int out_w, int* ws, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

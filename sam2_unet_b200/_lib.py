@@ -49,6 +49,8 @@ SIGNATURES = {
     "s2u_head_bwd": [P, I, P, P, P, I, I, P, P, L, I, I, P],
     "s2u_structure_loss_fwd": [P, P, P, P, P, P, P, I, I, I, I, P],
     "s2u_structure_loss_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "s2u_infer_tail_init": [P, P],
+    "s2u_infer_tail": [P, I, I, I, I, I, I, I, P, P, P],
     "s2u_adamw": [P, P, P, P, L, P, F, F, F, F, P],
 }
 

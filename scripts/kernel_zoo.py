@@ -159,3 +159,33 @@ for (Bc, Hc, Cin, K) in [(12, 88, 64, 3), (12, 44, 64, 3), (12, 88, 64, 7)]:
     kh, kw = (3, 3) if K == 3 else (1, 7)
     bench(f"im2col {Bc}x{Hc}x{Hc}x{Cin} k{kh}x{kw}", M * Cin * 2 * (1 + taps), mki,
           lambda s: ops.im2col(s["x"], Cin, s["col"], Bc, Hc, Hc, Cin, kh, kw, 1, 1, kh // 2, kw // 2))
+
+# inference tail (test.py:66-76) on the device vs the reference's own CPU operators on this box
+if not only or "tail" in only:
+    import time
+    import torch.nn.functional as F
+    from oracle import port
+    from sam2_unet_b200 import infer_tail
+    for (S, pad, hw) in [(352, (0, 0, 0, 117), (480, 720)), (352, (0, 0, 0, 0), (1080, 1920)), (1024, (0, 0, 256, 0), (1536, 1152))]:
+        lg = F.interpolate(torch.randn(1, 1, S // 8, S // 8) * 3, size=(S, S), mode="bicubic").contiguous()
+        lgd = lg.to(dev)
+        for _ in range(3):
+            o = infer_tail(lgd, pad, hw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            o = infer_tail(lgd, pad, hw)
+        e1.record()
+        torch.cuda.synchronize()
+        t_dev = e0.elapsed_time(e1) / 20 * 1e3
+        t0 = time.perf_counter()
+        for _ in range(5):
+            o.cpu()
+        t_d2h = (time.perf_counter() - t0) / 5 * 1e6
+        t0 = time.perf_counter()
+        for _ in range(5):
+            port.infer_tail(lgd.cpu(), pad, hw)
+        t_cpu = (time.perf_counter() - t0) / 5 * 1e6
+        print(f"infer_tail {S}->{hw[0]}x{hw[1]}: device {t_dev:7.1f} us (3 launches, eager) + D2H of uint8 {t_d2h:7.1f} us"
+              f"   | reference path (D2H of fp32 map + torch/numpy on the host): {t_cpu:9.1f} us", flush=True)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from sam2_unet_b200 import SAM2UNet
+from sam2_unet_b200 import SAM2UNet, infer_tail
 
 if __name__ == "__main__":
     parser = argparse.ArgumentParser()
@@ -49,11 +49,10 @@ if __name__ == "__main__":
             e0.record()
             res, _, _ = model(x)
             e1.record()
-        res = res[:, :, :hw[0], :hw[1]]                                                # remove padding (test.py:66-70)
-        res = F.interpolate(res, size=tuple(gt_shape), mode="bilinear", align_corners=False).sigmoid()
-        res = res.squeeze().cpu().numpy()
-        res = (res - res.min()) / (res.max() - res.min() + 1e-8)
-        Image.fromarray((res * 255).astype(np.uint8)).save(os.path.join(args.save_path, name[:-4] + ".png"))
+        # remove padding, resize to the ground-truth size, sigmoid, min-max, uint8 (test.py:66-76): on the device,
+        # one byte per pixel comes back
+        res = infer_tail(res, (0, 0, args.size - hw[1], args.size - hw[0]), tuple(gt_shape))
+        Image.fromarray(res.cpu().numpy()).save(os.path.join(args.save_path, name[:-4] + ".png"))
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1) / 1e3)
         print("Saving " + name)

@@ -509,3 +509,30 @@ def test_adamw_kernel(cuda):
         _lib.call("s2u_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, hyper.data_ptr(), 0.9, 0.999,
                   1e-8, 5e-4, st)
     _close(p, ref_p.detach(), 1e-5, "adamw")
+
+
+# ------------------------------------------------------------------------------------------ inference tail
+
+@pytest.mark.parametrize("case", [(352, (0, 0, 0, 0), (352, 352)), (352, (0, 0, 0, 117), (480, 720)),
+                                  (352, (30, 0, 31, 0), (1001, 640)), (96, (5, 7, 0, 3), (50, 41)),
+                                  (1024, (0, 0, 256, 0), (1536, 1152))])
+def test_infer_tail(cuda, case):
+    """Device-side crop + bilinear resize + sigmoid + min-max + uint8 (test.py:66-76) against the reference's own
+    operators on the CPU (oracle.port.infer_tail).  Byte work: exact up to the last-ulp difference between the CPU's
+    and the GPU's expf, which can move a value across a quantisation step - at most one level, on a handful of pixels."""
+    from oracle import port
+    from sam2_unet_b200 import infer_tail
+    S, padding, hw = case
+    g = torch.Generator(device="cpu").manual_seed(S + hw[0])
+    logits = torch.randn(1, 1, S // 8, S // 8, generator=g) * 3
+    logits = F.interpolate(logits, size=(S, S), mode="bicubic", align_corners=False).contiguous()   # smooth map
+    ref = torch.from_numpy(port.infer_tail(logits, padding, hw))
+    for _ in range(2):                                    # twice: the min / max workspace must come back re-armed
+        got = infer_tail(logits.to(cuda), padding, hw).cpu()
+    assert got.dtype == torch.uint8 and tuple(got.shape) == tuple(hw)
+    diff = (got.int() - ref.int()).abs()
+    assert int(diff.max()) <= 1, int(diff.max())
+    assert float((diff > 0).float().mean()) <= 2e-3, float((diff > 0).float().mean())
+    assert int(got.min()) == 0 and int(got.max()) >= 254
+    with pytest.raises(Exception):
+        infer_tail(logits, padding, hw)                   # CPU tensor: no fallback
