@@ -153,6 +153,22 @@ int s2u_infer_tail_init(int* ws, void* stream);
 int s2u_infer_tail(const float* logits, int S, int pad_left, int pad_top, int pad_right, int pad_bottom, int out_h,
                    int out_w, int* ws, unsigned char* out, void* stream);
 
+/* ---- evaluation metrics (eval.py:55-171) --------------------------------------------------------------------------
+ * counts[4] (uint64, accumulated) += |P & G|, |P | G|, |P|, |G| with P = pred > threshold, G = gt > threshold
+ * (eval.py:81-101: semantic IoU and Dice). */
+int s2u_seg_counts(const unsigned char* pred, const unsigned char* gt, long long n, float threshold,
+                   unsigned long long* counts, void* stream);
+/* 8-connected components of (mask > threshold) (skimage.measure.label, eval.py:105-106): labels[H*W] = smallest
+ * raster index of the pixel's component, -1 for background; the component roots are appended to roots[cap] in no
+ * particular order and counted in *nroots (zero on entry). */
+int s2u_cc_label(const unsigned char* mask, float threshold, int H, int W, int* labels, int* roots, int* nroots,
+                 int cap, void* stream);
+/* Component areas (parea / garea [n], indexed by root, zero on entry) and the intersection counts of every
+ * overlapping (prediction root, ground-truth root) pair in an open-addressing table: keys[cap] = (proot << 32) |
+ * groot (all-ones = empty, on entry), vals[cap] (zero on entry), cap a power of two; *overflow = 1 if it filled up. */
+int s2u_cc_stats(const int* plabels, const int* glabels, long long n, int* parea, int* garea, unsigned long long* keys,
+                 int* vals, int cap, int* overflow, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ SIGNATURES = {
     "s2u_structure_loss_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     "s2u_infer_tail_init": [P, P],
     "s2u_infer_tail": [P, I, I, I, I, I, I, I, P, P, P],
+    "s2u_seg_counts": [P, P, L, F, P, P],
+    "s2u_cc_label": [P, F, I, I, P, P, P, I, P],
+    "s2u_cc_stats": [P, P, L, P, P, P, P, I, P, P],
     "s2u_adamw": [P, P, P, P, L, P, F, F, F, F, P],
 }
 

@@ -189,3 +189,31 @@ if not only or "tail" in only:
         t_cpu = (time.perf_counter() - t0) / 5 * 1e6
         print(f"infer_tail {S}->{hw[0]}x{hw[1]}: device {t_dev:7.1f} us (3 launches, eager) + D2H of uint8 {t_d2h:7.1f} us"
               f"   | reference path (D2H of fp32 map + torch/numpy on the host): {t_cpu:9.1f} us", flush=True)
+
+# evaluation metrics (eval.py:55-171) on the device vs the CPU restatement of the reference on this box
+if not only or "eval" in only:
+    import time
+    import numpy as np
+    from oracle import eval_port
+    from sam2_unet_b200 import evaluate_segmentation_performance
+    for (h, w, nb) in [(480, 720, 40), (1080, 1920, 80)]:
+        rng = np.random.default_rng(0)
+        yy, xx = np.mgrid[0:h, 0:w]
+        gt = np.zeros((h, w), np.uint8)
+        for _ in range(nb):
+            cy, cx, rr = rng.integers(0, h), rng.integers(0, w), rng.integers(4, 40)
+            gt[(yy - cy) ** 2 + (xx - cx) ** 2 <= rr * rr] = 255
+        pred = np.roll(gt, (3, -2), (0, 1))
+        pd, gd = torch.from_numpy(pred).to(dev), torch.from_numpy(gt).to(dev)
+        for _ in range(2):
+            evaluate_segmentation_performance(pd, gd)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            evaluate_segmentation_performance(pd, gd)
+        t_dev = (time.perf_counter() - t0) / 5 * 1e3
+        t0 = time.perf_counter()
+        ref = eval_port.evaluate_segmentation_performance(pred, gt)
+        t_cpu = (time.perf_counter() - t0) * 1e3
+        print(f"eval metrics {h}x{w}, {ref['count_gt']} components: device path {t_dev:7.2f} ms wall (kernels + host "
+              f"matching) | reference algorithm on the host: {t_cpu:9.1f} ms", flush=True)

@@ -277,3 +277,26 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsam2unet_b200.so")
     with pytest.raises(_lib.KernelError):
         _lib.call("s2u_add", 0, 0, 0, 8, 0, 0)
+
+
+# --------------------------------------------------------------------------- eval metrics oracle (eval.py:55-171)
+
+def test_eval_oracle_known_answers():
+    """Known-answer pins of the CPU restatement of eval.py's per-image metrics (skimage is absent from the image, so
+    these hand-computed cases are what anchors the labelling: 8-connectivity, raster label order, greedy matching)."""
+    import numpy as np
+    from oracle import eval_port
+    z = np.zeros((40, 60), np.uint8)
+    a = z.copy(); a[5:15, 5:15] = 255; a[20:30, 30:45] = 255           # two components
+    r = eval_port.evaluate_segmentation_performance(a, a)
+    assert r["semantic_iou"] == 1.0 and r["dice_coefficient"] == 1.0 and r["count_gt"] == 2 and r["count_pred"] == 2
+    assert r["instance_precision_50"] == r["instance_recall_75"] == r["instance_f1_75"] == 1.0
+    b = z.copy(); b[5:15, 7:17] = 255; b[20:30, 30:45] = 255           # first square shifted by 2: IoU 80 / 120
+    r = eval_port.evaluate_segmentation_performance(b, a)
+    assert r["semantic_iou"] == (80 + 150) / (120 + 150) and r["dice_coefficient"] == 2 * 230 / 500
+    assert r["instance_precision_50"] == 1.0 and r["instance_precision_75"] == 0.5 and r["instance_recall_75"] == 0.5
+    d = z.copy(); d[3, 3] = d[4, 4] = d[5, 5] = 255; d[10, 10] = 30    # diagonal chain = ONE component; 30 > 25.5 counts
+    r = eval_port.evaluate_segmentation_performance(d, z)
+    assert r["count_pred"] == 2 and r["count_gt"] == 0 and r["semantic_iou"] == 0.0 and r["instance_f1_50"] == 0.0
+    r = eval_port.evaluate_segmentation_performance(z, a)
+    assert r["count_pred"] == 0 and r["instance_precision_50"] == 0.0 and r["dice_coefficient"] == 0.0

@@ -536,3 +536,44 @@ def test_infer_tail(cuda, case):
     assert int(got.min()) == 0 and int(got.max()) >= 254
     with pytest.raises(Exception):
         infer_tail(logits, padding, hw)                   # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------------------ eval metrics
+
+def _blobs(h, w, n, seed, jitter=0):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    m = np.zeros((h, w), np.uint8)
+    for _ in range(n):
+        cy, cx, r = rng.integers(0, h), rng.integers(0, w), rng.integers(2, max(3, min(h, w) // 6))
+        cy, cx = cy + rng.integers(-jitter, jitter + 1), cx + rng.integers(-jitter, jitter + 1)
+        m[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = rng.integers(26, 256)
+    return m
+
+
+@pytest.mark.parametrize("case", [(64, 96, 6, 0), (353, 211, 25, 1), (480, 720, 60, 2), (32, 32, 0, 3), (128, 128, 300, 4)])
+def test_eval_metrics_vs_oracle(cuda, case):
+    """Device thresholding / counting / 8-connected labelling / overlap table + host matching against the CPU
+    restatement of eval.py:55-171: integer work, so every entry of the result dictionary must be identical."""
+    import numpy as np
+    from oracle import eval_port
+    from sam2_unet_b200 import evaluate_dataset, evaluate_segmentation_performance
+    h, w, n, seed = case
+    gt = _blobs(h, w, n, seed)
+    pred = _blobs(h, w, n, seed, jitter=3)                     # same blobs, displaced: partial overlaps, merges, splits
+    rng = np.random.default_rng(seed + 100)
+    pred[rng.random((h, w)) < 0.002] = 200                     # salt: single-pixel components, diagonal contacts
+    pred[rng.random((h, w)) < 0.01] = 20                       # below the 25.5 threshold: must not count
+    results = []
+    for p, g in ((pred, gt), (gt, gt), (np.zeros_like(gt), gt), (pred, np.zeros_like(gt))):
+        ref = eval_port.evaluate_segmentation_performance(p, g)
+        got = evaluate_segmentation_performance(torch.from_numpy(p).to(cuda), torch.from_numpy(g).to(cuda))
+        assert set(got) == set(ref)
+        for k in ref:
+            assert got[k] == ref[k], (k, got[k], ref[k])
+        results.append(got)
+    agg = evaluate_dataset(results)
+    assert agg["mIoU"] == sum(r["semantic_iou"] for r in results) / len(results)
+    with pytest.raises(Exception):
+        evaluate_segmentation_performance(torch.from_numpy(pred), torch.from_numpy(gt))      # CPU tensors: no fallback

@@ -21,7 +21,8 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from sam2_unet_b200 import SAM2UNet, TrainStep, cosine_lr
+from sam2_unet_b200 import (SAM2UNet, TrainStep, cosine_lr, evaluate_dataset, evaluate_segmentation_performance,
+                            infer_tail)
 
 
 def structure_loss(pred, mask):
@@ -93,19 +94,20 @@ def _datasets(args):
 
 @torch.no_grad()
 def evaluate(model, dataset, device, batch_size):
-    """Mean IoU of sigmoid(out) > 0.5 against the mask (stand-in for eval.py's semantic IoU, eval.py:55-90)."""
+    """Per-epoch evaluation of the reference (train.py:90-125): forward, inference tail (sigmoid, min-max, uint8),
+    eval.py's per-image metrics and their dataset aggregation - the pixel work of all three on the device.  Returns the
+    aggregated dictionary (mIoU, mDice, Precision/Recall/F1 at IoU 0.5 and 0.75)."""
     model.eval()
-    inter = union = 0.0
     loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
-    ious = []
+    results = []
     for batch in loader:
         res, _, _ = model(batch["image"].to(device))
-        pred = res.sigmoid() > 0.5
-        gt = batch["label"].to(device) > 0.5
-        inter = (pred & gt).flatten(1).sum(1).float()
-        union = (pred | gt).flatten(1).sum(1).float()
-        ious.append(((inter + 1e-6) / (union + 1e-6)).cpu())
-    return torch.cat(ious).mean().item() if ious else 0.0
+        gts = (batch["label"].to(device) * 255).round().clamp(0, 255).to(torch.uint8)
+        for i in range(res.shape[0]):
+            # datasets of this script are already square at the network size: no padding to remove, same size out
+            png = infer_tail(res[i:i + 1], (0, 0, 0, 0), tuple(res.shape[-2:]))
+            results.append(evaluate_segmentation_performance(png, gts[i, 0]))
+    return evaluate_dataset(results)
 
 
 def main(args):
@@ -152,9 +154,10 @@ def main(args):
         if rank == 0:
             print(f"epoch {epoch + 1}: {seen / max(time.time() - t0, 1e-9):.1f} img/s/rank")
             print("Evaluating", end="")
-            mean_iou = evaluate(model, test_ds, device, args.batch_size)
+            final = evaluate(model, test_ds, device, args.batch_size)
+            mean_iou = final.get("mIoU", 0.0)
             epoch_name = f"epoch-{epoch + 1}_loss-{epoch_loss:.3f}"
-            line = f"{epoch_name}: mIoU {mean_iou:.4f}"
+            line = f"{epoch_name}: " + ", ".join(f"{k} {v:.4f}" for k, v in final.items())
             print("\n" + line)
             with open(log_path, "a") as f:
                 f.write(line + "\n")
