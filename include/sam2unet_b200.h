@@ -169,6 +169,13 @@ int s2u_cc_label(const unsigned char* mask, float threshold, int H, int W, int* 
 int s2u_cc_stats(const int* plabels, const int* glabels, long long n, int* parea, int* garea, unsigned long long* keys,
                  int* vals, int cap, int* overflow, void* stream);
 
+/* ---- test-time input path (dataset.py:336-407: ImageToTensor, LongestMaxSizeAndPad, NormalizeImage) ------------
+ * img: uint8 [H,W,3] RGB on the device; out: fp32 [3,S,S] = normalise(pad(antialiased-bilinear-resize(img / 255)));
+ * new_h, new_w, pad_left, pad_top: the host integers of LongestMaxSizeAndPad; mean / std: 3 floats each in HOST
+ * memory; tmp: fp32 device scratch of 3 * H * new_w elements. */
+int s2u_preprocess(const unsigned char* img, int H, int W, int S, int new_h, int new_w, int pad_left, int pad_top,
+                   const float* mean3_host, const float* std3_host, float* tmp, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,7 @@ SIGNATURES = {
     "s2u_seg_counts": [P, P, L, F, P, P],
     "s2u_cc_label": [P, F, I, I, P, P, P, I, P],
     "s2u_cc_stats": [P, P, L, P, P, P, P, I, P, P],
+    "s2u_preprocess": [P, I, I, I, I, I, I, I, P, P, P, P, P],
     "s2u_adamw": [P, P, P, P, L, P, F, F, F, F, P],
 }
 

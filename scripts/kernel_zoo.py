@@ -217,3 +217,29 @@ if not only or "eval" in only:
         t_cpu = (time.perf_counter() - t0) * 1e3
         print(f"eval metrics {h}x{w}, {ref['count_gt']} components: device path {t_dev:7.2f} ms wall (kernels + host "
               f"matching) | reference algorithm on the host: {t_cpu:9.1f} ms", flush=True)
+
+# test-time input path (dataset.py:336-407) on the device vs the reference's torchvision transforms on this box
+if not only or "prep" in only:
+    import time
+    import numpy as np
+    from oracle import port
+    from sam2_unet_b200 import preprocess_image
+    for (h, w, S) in [(1080, 1920, 352), (2000, 1500, 1024)]:
+        img = np.random.default_rng(0).integers(0, 256, (h, w, 3)).astype(np.uint8)
+        imd = torch.from_numpy(img).to(dev)
+        for _ in range(3):
+            preprocess_image(imd, S)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            preprocess_image(imd, S)
+        e1.record()
+        torch.cuda.synchronize()
+        t_dev = e0.elapsed_time(e1) / 20 * 1e3
+        t0 = time.perf_counter()
+        for _ in range(3):
+            port.preprocess_image(img, S)
+        t_cpu = (time.perf_counter() - t0) / 3 * 1e3
+        print(f"preprocess {h}x{w} -> {S}: device {t_dev:7.1f} us (2 launches, eager; + H2D of the uint8 image) | "
+              f"reference transforms on the host: {t_cpu:7.2f} ms", flush=True)

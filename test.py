@@ -10,9 +10,8 @@ import os
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
-from sam2_unet_b200 import SAM2UNet, infer_tail
+from sam2_unet_b200 import SAM2UNet, infer_tail, preprocess_image
 
 if __name__ == "__main__":
     parser = argparse.ArgumentParser()
@@ -32,18 +31,14 @@ if __name__ == "__main__":
     model.eval()
     os.makedirs(args.save_path, exist_ok=True)
     names = sorted(f for f in os.listdir(args.test_image_path) if f.endswith((".jpg", ".png")))
-    mean = torch.tensor([0.485, 0.456, 0.406], device=device).view(1, 3, 1, 1)
-    std = torch.tensor([0.229, 0.224, 0.225], device=device).view(1, 3, 1, 1)
     times = []
     for name in names:
-        img = np.asarray(Image.open(os.path.join(args.test_image_path, name)).convert("RGB"), dtype=np.float32) / 255
+        img_u8 = np.ascontiguousarray(np.asarray(Image.open(os.path.join(args.test_image_path, name)).convert("RGB")))
         gt_path = os.path.join(args.test_gt_path, name[:-4] + ".png")
-        gt_shape = np.asarray(Image.open(gt_path)).shape[:2] if os.path.exists(gt_path) else img.shape[:2]
-        x = torch.from_numpy(img).permute(2, 0, 1)[None].to(device)
-        s = args.size / max(x.shape[2:])
-        hw = (max(1, round(x.shape[2] * s)), max(1, round(x.shape[3] * s)))
-        x = (F.interpolate(x, size=hw, mode="bilinear", align_corners=False) - mean) / std
-        x = F.pad(x, (0, args.size - hw[1], 0, args.size - hw[0]))
+        gt_shape = np.asarray(Image.open(gt_path)).shape[:2] if os.path.exists(gt_path) else img_u8.shape[:2]
+        # TestDataset's transforms (dataset.py:336-407) on the device: /255, antialiased resize of the longest side,
+        # centred zero padding, normalisation; `padding` = (left, top, right, bottom) like load_data's
+        x, padding = preprocess_image(torch.from_numpy(img_u8).to(device), args.size)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.no_grad():
             e0.record()
@@ -51,7 +46,7 @@ if __name__ == "__main__":
             e1.record()
         # remove padding, resize to the ground-truth size, sigmoid, min-max, uint8 (test.py:66-76): on the device,
         # one byte per pixel comes back
-        res = infer_tail(res, (0, 0, args.size - hw[1], args.size - hw[0]), tuple(gt_shape))
+        res = infer_tail(res, padding, tuple(gt_shape))
         Image.fromarray(res.cpu().numpy()).save(os.path.join(args.save_path, name[:-4] + ".png"))
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1) / 1e3)

@@ -577,3 +577,27 @@ def test_eval_metrics_vs_oracle(cuda, case):
     assert agg["mIoU"] == sum(r["semantic_iou"] for r in results) / len(results)
     with pytest.raises(Exception):
         evaluate_segmentation_performance(torch.from_numpy(pred), torch.from_numpy(gt))      # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------ test-time input path
+
+@pytest.mark.parametrize("case", [(300, 420, 352), (1080, 1920, 352), (352, 352, 352), (97, 41, 96), (200, 333, 1024),
+                                  (2000, 1500, 1024)])
+def test_preprocess_image(cuda, case):
+    """uint8 HWC image -> /255 -> antialiased bilinear resize (longest side) -> centred zero pad -> normalise, against
+    the reference's own torchvision transforms on the CPU (oracle.port.preprocess_image, dataset.py:336-407)."""
+    import numpy as np
+    from oracle import port
+    from sam2_unet_b200 import preprocess_image
+    H, W, S = case
+    rng = np.random.default_rng(H + W)
+    base = rng.integers(0, 256, (H // 8 + 2, W // 8 + 2, 3)).astype(np.float32)
+    img = np.kron(base, np.ones((8, 8, 1), np.float32))[:H, :W]                    # blocky image with sharp edges
+    img = np.clip(img + rng.normal(0, 12, img.shape), 0, 255).astype(np.uint8)
+    ref, pad_ref = port.preprocess_image(img, S)
+    got, pad = preprocess_image(torch.from_numpy(img).to(cuda), S)
+    assert list(pad) == list(pad_ref) and tuple(got.shape) == (1, 3, S, S)
+    err = (got[0].cpu() - ref).abs().max().item()
+    assert err <= 2e-5, err                                                        # fp32 path, values in [-2.2, 2.7]
+    with pytest.raises(Exception):
+        preprocess_image(torch.from_numpy(img), S)                                 # CPU tensor: no fallback
