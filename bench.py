@@ -440,7 +440,7 @@ def run_b200(args):
                 "warmup": warm + 3, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
-                           "cuda_graph": not args.no_graph and args.mode == "train",
+                           "cuda_graph": not args.no_graph,
                            "l2": "per-step working set (activations + im2col buffers, several GB) is far larger than "
                                  "the 126 MB L2, no explicit flush"},
                 "clocks": clocks,
