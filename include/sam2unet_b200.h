@@ -29,7 +29,8 @@ extern "C" {
  * conv forward / input gradient on im2col rows (SAM2UNet.py:83-86).  epi(v): v += bias[n]; pre_out = v;
  * flags&1: v = gelu(v); flags&2: v *= gelu'(aux); flags&4: v += resid; flags&16: C is fp32; flags&32: resid is
  * fp32; flags&64: pre_out receives the FINAL value (compute-dtype copy of C) instead of the pre-activation one;
- * flags&128: pre_out receives gelu'(v) instead of v (so the backward pass only multiplies); flags&256: v *= aux.
+ * flags&128: pre_out receives gelu'(v) instead of v (so the backward pass only multiplies); flags&256: v *= aux;
+ * flags&512: v = max(v, 0) last (eval-mode conv with folded BatchNorm, residual and ReLU in one call).
  * backend: 0 auto (tcgen05 + TMA for bf16: CTA-pair kernel when M > 128), 1 SIMT fp32-FMA, 2 tcgen05 required,
  * 16+bn one-CTA persistent tcgen05 kernel with N tile bn, 1024+bn CTA-pair (cta_group::2) kernel with N tile bn. */
 int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,

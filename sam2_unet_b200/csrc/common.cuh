@@ -150,8 +150,9 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // the pre-activation one.
 // GEMM_SAVE_DGELU: pre_out receives gelu'(pre-activation) instead of the pre-activation, so that the backward GEMM
 // only multiplies by it (GEMM_MULAUX: result *= aux) and the erf/exp are evaluated once, in the forward epilogue.
+// GEMM_RELU: max(v, 0) last (after the residual): eval-mode conv + folded BatchNorm (+ residual) + ReLU in one GEMM.
 enum GemmFlags { GEMM_GELU = 1, GEMM_DGELU = 2, GEMM_RESID = 4, GEMM_OUT_F32 = 16, GEMM_RESID_F32 = 32,
-                 GEMM_PRE_FINAL = 64, GEMM_SAVE_DGELU = 128, GEMM_MULAUX = 256 };
+                 GEMM_PRE_FINAL = 64, GEMM_SAVE_DGELU = 128, GEMM_MULAUX = 256, GEMM_RELU = 512 };
 struct GemmEpi {
   const float* bias;   // [N] or null
   void* pre_out;       // T [M, ld_pre]: value before the activation (saved for GELU'), or null

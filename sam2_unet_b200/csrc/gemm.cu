@@ -43,6 +43,7 @@ __device__ __forceinline__ float epi_scalar(const EpiView<T>& e, float v, long l
     if (e.flags & GEMM_RESID_F32) v += reinterpret_cast<const float*>(e.resid)[row * e.ld_res + col];
     else v += ldf(e.resid + row * e.ld_res + col);
   }
+  if (e.flags & GEMM_RELU) v = fmaxf(v, 0.f);
   if (e.pre_out && (e.flags & GEMM_PRE_FINAL)) stf(e.pre_out + row * e.ld_pre + col, v);
   return v;
 }
@@ -762,6 +763,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
           }
         }
       }
+      if (epi.flags & GEMM_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
       if (F32S && out_f32) {
         // 16 fp32 columns per staging tile; with an fp32 residual each thread overwrites exactly the row it just read
         char* cdst = reinterpret_cast<char*>(reinterpret_cast<float*>(C) + row0 * ldc + col0);
@@ -1433,7 +1438,7 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     const bf16 *a = (const bf16*)A, *w = (const bf16*)W;
     bf16* c = (bf16*)C;
     if (legacy) {
-      if (flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL | GEMM_SAVE_DGELU | GEMM_MULAUX)) return S2U_EUNSUPPORTED;
+      if (flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL | GEMM_SAVE_DGELU | GEMM_MULAUX | GEMM_RELU)) return S2U_EUNSUPPORTED;
       switch (bn) {
         case 32: return umma::launch<32, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         case 64: return umma::launch<64, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);

@@ -25,7 +25,7 @@ from . import _lib
 from .config import TrunkConfig
 from .resample_tables import ResampleTables
 
-GELU, DGELU, RESID, OUT_F32, RESID_F32, PRE_FINAL, SAVE_DGELU, MULAUX = 1, 2, 4, 16, 32, 64, 128, 256
+GELU, DGELU, RESID, OUT_F32, RESID_F32, PRE_FINAL, SAVE_DGELU, MULAUX, RELU = 1, 2, 4, 16, 32, 64, 128, 256, 512
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -214,6 +214,7 @@ class Engine:
         self._shadow: Dict[str, torch.Tensor] = {}
         self._pos_cache: Dict[int, torch.Tensor] = {}
         self._bn_ws: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._fold_cache: Dict[str, tuple] = {}
         self.tape: Optional[dict] = None
         self._units = {cs.name: cs for cs in model.conv_units}
         self._prepare_frozen()
@@ -444,6 +445,22 @@ class Engine:
                                        lse=lse, y=y, mean2=mean2, rstd2=rstd2, hid=hid, H=H, W=W, Ho=Ho, Wo=Wo))
         return z, zc, Ho, Wo
 
+    def _bn_folded(self, cs: "_ConvSpec"):
+        """Eval mode: conv weight x BN scale in the GEMM layout [64][(ky, kx, ci)] (compute dtype) and the BN shift as
+        the GEMM bias; rebuilt when the parameters change (setup, torch ops)."""
+        flat = self.model.flat
+        hit = self._fold_cache.get(cs.name)
+        if hit is not None and hit[0] == flat.version:
+            return hit[1], hit[2]
+        P, Bf = flat.views, flat.buffers
+        with torch.no_grad():
+            scale = P[cs.bn + ".weight"].float() / torch.sqrt(Bf[cs.bn + ".running_var"].float() + 1e-5)
+            shift = (P[cs.bn + ".bias"].float() - Bf[cs.bn + ".running_mean"].float() * scale).contiguous()
+            w = P[cs.name + ".weight"].float()                                  # [64, Cin, kh, kw]
+            wf = (w.permute(0, 2, 3, 1).reshape(w.shape[0], -1) * scale[:, None]).to(self.T).contiguous()
+        self._fold_cache[cs.name] = (flat.version, wf, shift)
+        return wf, shift
+
     # conv (+ BN (+ residual) (+ ReLU)) on NHWC rows.  `src`: (tensor, ld, channel offset) of the input map.
     def _conv_bn(self, cs: _ConvSpec, src, B, H, out, ld_out, out_off, relu, training, tape, resid=None, ld_res=0):
         ops, sh = self.ops, self._shadow
@@ -461,8 +478,16 @@ class Engine:
             xin = x.view(-1)[xoff:] if xoff else x
             ops.im2col(xin, ldx, col, B, H, H, cs.cin, cs.kh, cs.kw, cs.dil, cs.dil, ph, pw)
             ldcol, col_ptr_off = taps * cs.cin, 0
-        raw = ops.empty(M, 64)
         A = col.view(-1)[col_ptr_off:] if col_ptr_off else col
+        if not training and tape is None:
+            # inference: BatchNorm (running statistics) folded into the weights and a bias, residual and ReLU in the
+            # GEMM epilogue - one launch per conv instead of GEMM + finalize + apply
+            wf, shift = self._bn_folded(cs)
+            C = out.view(-1)[out_off:] if out_off else out
+            ops.gemm(A, wf, C, bias=shift, resid=resid, ld_res=ld_res, M=M, N=64, K=taps * cs.cin, lda=ldcol,
+                     ldw=taps * cs.cin, ldc=ld_out, flags=(RESID if resid is not None else 0) | (RELU if relu else 0))
+            return
+        raw = ops.empty(M, 64)
         ops.gemm(A, sh[cs.name + ".wf"], raw, M=M, N=64, K=taps * cs.cin, lda=ldcol, ldw=taps * cs.cin, ldc=64)
         ws = self._bn_workspace(cs.bn, 64)
         mean = rstd = None

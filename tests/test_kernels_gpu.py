@@ -42,7 +42,7 @@ GEMM_SHAPES = [(300, 96, 32), (1000, 432, 144), (484, 2304, 576), (777, 32, 144)
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
-@pytest.mark.parametrize("flags", [0, 1, 4, 5, 2, 256, 1 | 128])
+@pytest.mark.parametrize("flags", [0, 1, 4, 5, 2, 256, 1 | 128, 4 | 512])
 def test_gemm_simt(cuda, dtype, shape, flags):
     M, N, K = shape
     ops = _ops(dtype, cuda, backend=1)
@@ -67,6 +67,8 @@ def test_gemm_simt(cuda, dtype, shape, flags):
         ref = ref * dg
     if flags & 4:
         ref = ref + resid.float()
+    if flags & 512:
+        ref = F.relu(ref)
     _close(pre, ref_pre, _tol(dtype), "pre_out")
     _close(C, ref, _tol(dtype), "C")
 
@@ -124,6 +126,10 @@ def test_gemm_umma(cuda, shape, kernel):
     ops.gemm(A, W, C4, bias=bias, resid=resid, pre_out=h4, flags=1 | 4 | 16, backend=backend)     # bf16 resid, fp32 out
     _close(C4, F.gelu(ref_pre) + resid.float(), 1e-3, "gelu + bf16 resid, fp32 out")
     _close(h4, ref_pre, 1e-2, "pre-activation copy")
+    # eval-mode conv + folded BatchNorm: bias, residual, ReLU, written into a wider (concat) buffer
+    wide = ops.empty(M, N + 64)
+    ops.gemm(A, W, wide.view(-1)[8:], bias=bias, resid=resid, flags=4 | 512, ldc=N + 64, backend=backend)
+    _close(wide[:, 8:8 + N], F.relu(ref_pre + resid.float()), 1e-2, "bias + resid + relu into a strided buffer")
     # adapter layer 2 forward: gelu + fp32 residual in / out with the pre-activation saved
     C8, h8 = torch.empty(M, N, device=cuda), ops.empty(M, N)
     ops.gemm(A, W, C8, bias=bias, resid=r32, pre_out=h8, flags=1 | 4 | 16 | 32, backend=backend)
