@@ -40,6 +40,11 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
  * (SAM2UNet.py:72-80); q_inner/q_taps map q = tap*Cin+ci to the [Cout,Cin,kh,kw] parameter layout (0,0: plain). */
 int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int ldg, long long M, int P, int Q,
                    int q_inner, int q_taps, int dtype, void* stream);
+/* Two weight gradients sharing the row count M in one launch (an adapter's dW2 and dW1, SAM2UNet.py:57-59): G0 +=
+ * A0^T B0, G1 += A1^T B1, plain [P,Q] layouts. */
+int s2u_gemm_wgrad_pair(const void* A0, int lda0, const void* B0, int ldb0, float* G0, int ldg0, int P0, int Q0,
+                        const void* A1, int lda1, const void* B1, int ldb1, float* G1, int ldg1, int P1, int Q1,
+                        long long M, int dtype, void* stream);
 /* out[P] += column sums of A[M,P]: bias gradients. */
 int s2u_colsum(const void* A, int lda, float* out, long long M, int P, int dtype, void* stream);
 

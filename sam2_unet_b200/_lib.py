@@ -18,6 +18,7 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 SIGNATURES = {
     "s2u_gemm": [P, I, P, I, P, I, I, I, I, P, P, I, P, I, P, I, I, I, I, P],
     "s2u_gemm_wgrad": [P, I, P, I, P, I, L, I, I, I, I, I, P],
+    "s2u_gemm_wgrad_pair": [P, I, P, I, P, I, I, I, P, I, P, I, P, I, I, I, L, I, P],
     "s2u_colsum": [P, I, P, L, I, I, P],
     "s2u_layernorm_fwd": [P, P, P, P, P, P, L, I, F, I, I, P],
     "s2u_layernorm_ws_floats": [I],

@@ -1055,10 +1055,21 @@ constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024;
 constexpr uint32_t WG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                               ((uint32_t)(128 >> 4) << 24);
 
-__global__ void __launch_bounds__(128) wgrad_umma_kernel(const __grid_constant__ CUtensorMap tma_x,
-                                                        const __grid_constant__ CUtensorMap tma_y,
-                                                        float* __restrict__ G, int ldg, int M, int X, int Y, int swap,
-                                                        int q_inner, int q_taps, int kb_per_split) {
+// one weight-gradient problem; blockIdx.y selects between the (up to) two problems of a launch, which share M and the
+// row split (the two adapter weight gradients of a block: one launch, twice the CTAs)
+struct WgJob {
+  CUtensorMap tma_x, tma_y;
+  float* G;
+  int ldg, X, Y, swap, q_inner, q_taps;
+};
+__global__ void __launch_bounds__(128) wgrad_umma_kernel(const __grid_constant__ WgJob job0,
+                                                        const __grid_constant__ WgJob job1, int M, int kb_per_split) {
+  const WgJob& job = blockIdx.y ? job1 : job0;
+  if ((int)blockIdx.x * 128 >= job.X) return;              // the other problem has more column tiles
+  const CUtensorMap& tma_x = job.tma_x;
+  const CUtensorMap& tma_y = job.tma_y;
+  float* __restrict__ G = job.G;
+  const int ldg = job.ldg, X = job.X, Y = job.Y, swap = job.swap, q_inner = job.q_inner, q_taps = job.q_taps;
   pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
@@ -1360,17 +1371,35 @@ static int make_map_mn(CUtensorMap* out, const void* ptr, long long rows, long l
 }
 
 // G[P,Q] += A^T B on tcgen05; returns S2U_EUNSUPPORTED when the operands do not fit the kernel's assumptions
-static int launch_wgrad(const bf16* A, int lda, const bf16* B, int ldb, float* G, int ldg, long long M, int P, int Q,
-                        int q_inner, int q_taps, cudaStream_t st) {
-  if (!aligned16(A) || !aligned16(B) || (lda % 8) || (ldb % 8) || M > 0x7fffffffLL) return S2U_EUNSUPPORTED;
-  const int swap = Q > P;                         // the larger side is tiled by 128 (UMMA M), the smaller is UMMA N
-  const int X = swap ? Q : P, Y = swap ? P : Q;
-  if (Y > 64) return S2U_EUNSUPPORTED;
-  CUtensorMap mx, my;
-  int rc = make_map_mn(&mx, swap ? (const void*)B : (const void*)A, M, X, swap ? ldb : lda);
+struct WgProblem {
+  const bf16* A; int lda; const bf16* B; int ldb; float* G; int ldg; int P, Q, q_inner, q_taps;
+};
+static int make_wg_job(WgJob* j, const WgProblem& p, long long M) {
+  if (!aligned16(p.A) || !aligned16(p.B) || (p.lda % 8) || (p.ldb % 8)) return S2U_EUNSUPPORTED;
+  j->swap = p.Q > p.P;                           // the larger side is tiled by 128 (UMMA M), the smaller is UMMA N
+  j->X = j->swap ? p.Q : p.P;
+  j->Y = j->swap ? p.P : p.Q;
+  if (j->Y > 64) return S2U_EUNSUPPORTED;
+  int rc = make_map_mn(&j->tma_x, j->swap ? (const void*)p.B : (const void*)p.A, M, j->X, j->swap ? p.ldb : p.lda);
   if (rc) return rc;
-  rc = make_map_mn(&my, swap ? (const void*)A : (const void*)B, M, Y, swap ? lda : ldb);
+  rc = make_map_mn(&j->tma_y, j->swap ? (const void*)p.A : (const void*)p.B, M, j->Y, j->swap ? p.lda : p.ldb);
   if (rc) return rc;
+  j->G = p.G;
+  j->ldg = p.ldg;
+  j->q_inner = p.q_inner;
+  j->q_taps = p.q_taps;
+  return 0;
+}
+// G[P,Q] += A^T B on tcgen05 for one problem, or two that share M (nprob = 2); returns S2U_EUNSUPPORTED when the
+// operands do not fit the kernel's assumptions
+static int launch_wgrad(const WgProblem* probs, int nprob, long long M, cudaStream_t st) {
+  if (M > 0x7fffffffLL) return S2U_EUNSUPPORTED;
+  WgJob jobs[2];
+  for (int i = 0; i < nprob; ++i) {
+    const int rc = make_wg_job(&jobs[i], probs[i], M);
+    if (rc) return rc;
+  }
+  if (nprob == 1) jobs[1] = jobs[0];
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1378,15 +1407,16 @@ static int launch_wgrad(const bf16* A, int lda, const bf16* B, int ldb, float* G
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
-  const int x_tiles = ceil_div(X, 128);
+  int x_tiles = ceil_div(jobs[0].X, 128);
+  if (nprob == 2 && ceil_div(jobs[1].X, 128) > x_tiles) x_tiles = ceil_div(jobs[1].X, 128);
   const int total_kb = (int)((M + 63) / 64);
-  int splits = (2 * num_sms() + x_tiles - 1) / x_tiles;
+  int splits = (2 * num_sms() + x_tiles * nprob - 1) / (x_tiles * nprob);
   if (splits > total_kb / 4) splits = total_kb / 4;        // at least 4 k-blocks per CTA
   if (splits < 1) splits = 1;
   const int kb_per = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per - 1) / kb_per;
-  dim3 grid(x_tiles, 1, splits);
-  S2U_LAUNCH((wgrad_umma_kernel), grid, 128, WG_SMEM_BYTES, st, mx, my, G, ldg, (int)M, X, Y, swap, q_inner, q_taps, kb_per);
+  dim3 grid(x_tiles, nprob, splits);
+  S2U_LAUNCH((wgrad_umma_kernel), grid, 128, WG_SMEM_BYTES, st, jobs[0], jobs[1], (int)M, kb_per);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -1481,8 +1511,8 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
   if (M <= 0 || P <= 0 || Q <= 0) return S2U_EINVAL;
   if (q_inner <= 0) { q_inner = Q; q_taps = 1; }
   if (dtype == S2U_BF16) {
-    const int rc = umma::launch_wgrad((const bf16*)A, lda, (const bf16*)B, ldb, G, ldg, M, P, Q, q_inner, q_taps,
-                                      (cudaStream_t)stream);
+    const umma::WgProblem pr{(const bf16*)A, lda, (const bf16*)B, ldb, G, ldg, P, Q, q_inner, q_taps};
+    const int rc = umma::launch_wgrad(&pr, 1, M, (cudaStream_t)stream);
     if (rc != S2U_EUNSUPPORTED) return rc;
   }
   const int tiles = ceil_div(P, 64) * ceil_div(Q, 64);
@@ -1500,6 +1530,24 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
   })
   S2U_LAUNCH_CHECK();
   return 0;
+}
+
+// Two weight gradients that share the row count M in ONE launch (the adapter's dW2 = dh2^T u and dW1 = dh1^T x):
+// G0[P0,Q0] += A0^T B0, G1[P1,Q1] += A1^T B1, plain [P,Q] layouts.  Falls back to two s2u_gemm_wgrad calls when the
+// tcgen05 kernel cannot take the pair.
+int s2u_gemm_wgrad_pair(const void* A0, int lda0, const void* B0, int ldb0, float* G0, int ldg0, int P0, int Q0,
+                        const void* A1, int lda1, const void* B1, int ldb1, float* G1, int ldg1, int P1, int Q1,
+                        long long M, int dtype, void* stream) {
+  if (M <= 0 || P0 <= 0 || Q0 <= 0 || P1 <= 0 || Q1 <= 0) return S2U_EINVAL;
+  if (dtype == S2U_BF16) {
+    const umma::WgProblem pr[2] = {{(const bf16*)A0, lda0, (const bf16*)B0, ldb0, G0, ldg0, P0, Q0, Q0, 1},
+                                   {(const bf16*)A1, lda1, (const bf16*)B1, ldb1, G1, ldg1, P1, Q1, Q1, 1}};
+    const int rc = umma::launch_wgrad(pr, 2, M, (cudaStream_t)stream);
+    if (rc != S2U_EUNSUPPORTED) return rc;
+  }
+  const int rc = s2u_gemm_wgrad(A0, lda0, B0, ldb0, G0, ldg0, M, P0, Q0, 0, 0, dtype, stream);
+  if (rc) return rc;
+  return s2u_gemm_wgrad(A1, lda1, B1, ldb1, G1, ldg1, M, P1, Q1, 0, 0, dtype, stream);
 }
 
 // out[P] (fp32, accumulated) += column sums of A[M,P]

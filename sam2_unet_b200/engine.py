@@ -73,6 +73,12 @@ class Ops:
         _lib.call("s2u_gemm_wgrad", A.data_ptr(), lda or A.stride(0), B.data_ptr(), ldb or B.stride(0), G.data_ptr(),
                   ldg if ldg is not None else Q, M, P, Q, q_inner, q_taps, self.dt, self.stream)
 
+    def wgrad_pair(self, A0, B0, G0, ldg0, A1, B1, G1, ldg1):
+        """G0 += A0^T B0 and G1 += A1^T B1 (same row count) in one launch."""
+        _lib.call("s2u_gemm_wgrad_pair", A0.data_ptr(), A0.stride(0), B0.data_ptr(), B0.stride(0), G0.data_ptr(), ldg0,
+                  A0.shape[1], B0.shape[1], A1.data_ptr(), A1.stride(0), B1.data_ptr(), B1.stride(0), G1.data_ptr(),
+                  ldg1, A1.shape[1], B1.shape[1], A0.shape[0], self.dt, self.stream)
+
     def colsum(self, A, out, M=None, P=None, lda=None):
         _lib.call("s2u_colsum", A.data_ptr(), lda or A.stride(0), out.data_ptr(), A.shape[0] if M is None else M,
                   A.shape[1] if P is None else P, self.dt, self.stream)
@@ -656,10 +662,10 @@ class Engine:
         dxa, dh2 = ops.empty(R, C), ops.empty(R, C)
         ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C, pre=tp["h2"], dx2=dh2,
                    colsum=G[a + "2.bias"], pre_is_grad=True)         # h2 holds gelu'(pre-activation)
-        ops.wgrad(dh2, tp["u"], G[a + "2.weight"], ldg=32)              # [C, 32]
         dh1 = ops.empty(R, 32)
         ops.gemm(dh2, sh[a + "2.wt"], dh1, aux=tp["h1"], flags=MULAUX)  # (dh2 W2) * gelu'(h1)
-        ops.wgrad(dh1, tp["x"], G[a + "0.weight"], ldg=C)               # [32, C]
+        # dW2 [C, 32] = dh2^T u and dW1 [32, C] = dh1^T x in one launch
+        ops.wgrad_pair(dh2, tp["u"], G[a + "2.weight"], 32, dh1, tp["x"], G[a + "0.weight"], C)
         ops.colsum(dh1, G[a + "0.bias"])
         dx = ops.empty(R, C)
         ops.gemm(dh1, sh[a + "0.wt"], dx, resid=dxa, flags=RESID)

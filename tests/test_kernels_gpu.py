@@ -607,3 +607,18 @@ def test_preprocess_image(cuda, case):
     assert err <= 2e-5, err                                                        # fp32 path, values in [-2.2, 2.7]
     with pytest.raises(Exception):
         preprocess_image(torch.from_numpy(img), S)                                 # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(5808, 576, 32), (1452, 1152, 32), (3000, 144, 32), (777, 64, 64)])
+def test_wgrad_pair(cuda, dtype, shape):
+    """The two adapter weight gradients of a block in one launch: dW2 [C,32] += dh2^T u, dW1 [32,C] += dh1^T x."""
+    M, C, r = shape
+    ops = _ops(dtype, cuda)
+    dh2, u = _rand((M, C), dtype, cuda, 1), _rand((M, r), dtype, cuda, 2)
+    dh1, x = _rand((M, r), dtype, cuda, 3), _rand((M, C), dtype, cuda, 4)
+    G2, G1 = torch.zeros(C, r, device=cuda), torch.ones(r, C, device=cuda)       # accumulates into what is there
+    ops.wgrad_pair(dh2, u, G2, r, dh1, x, G1, C)
+    tol = 1e-4 if dtype == "fp32" else 2e-3
+    _close(G2, dh2.float().t() @ u.float(), tol, "pair: dW2")
+    _close(G1, 1 + dh1.float().t() @ x.float(), tol, "pair: dW1")
