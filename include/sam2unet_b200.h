@@ -82,6 +82,10 @@ int s2u_refresh_shadows(const void* entries, const void* blocks, int nblocks, in
  * dws = fp32 workspace [B,Ho,Wo,nh] of the backward.  bf16 runs on tensor cores, fp32 on an exact FFMA kernel. */
 int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
                      int window, int pool, int dtype, void* stream);
+/* bf16 kernel family: 0 = auto (tcgen05 + TMEM + TMA kernels of attention_tc.cu where they apply - no q-pool, window of
+ * 65..256 tokens or global, head dim 72..96 - else the mma.sync kernels), 1 = never tcgen05, 2 = tcgen05 or
+ * S2U_EUNSUPPORTED (tests / A-B measurements).  Environment S2U_ATTN_BACKEND sets the initial value. */
+int s2u_set_attn_backend(int backend);
 int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
                      void* dqkv, float* dws, int B, int H, int W, int nh, int hd, int window, int pool, int dtype,
                      void* stream);

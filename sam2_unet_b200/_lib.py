@@ -30,6 +30,7 @@ SIGNATURES = {
     "s2u_cast": [P, P, I, I, I, I, P],
     "s2u_refresh_shadows": [P, P, I, I, P],
     "s2u_win_attn_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, P],
+    "s2u_set_attn_backend": [I],
     "s2u_win_attn_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     "s2u_patch_embed": [P, P, P, P, P, I, P, I, I, I, I, P],
     "s2u_patch_im2col": [P, P, I, I, P],

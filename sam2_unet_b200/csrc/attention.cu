@@ -424,10 +424,39 @@ int s2u_attn_mma_bwd(const void* qkv, const float* bias, const void* out, const 
                      void* dqkv, float* Dws, int B, int H, int W, int nh, int hd, int window, int pool,
                      cudaStream_t st);
 
+// tcgen05 / TMEM / TMA variants (attention_tc.cu), bf16 only, same convention
+int s2u_attn_tc_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
+                    int window, int pool, cudaStream_t st);
+
+int s2u_attn_tc_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
+                    void* dqkv, float* dws, int B, int H, int W, int nh, int hd, int window, int pool,
+                    cudaStream_t st);
+
+// 0 = auto (tcgen05 kernels where they apply, else mma.sync, else fp32 SIMT), 1 = never tcgen05, 2 = tcgen05 or fail
+static int g_attn_backend = -1;
+static int attn_backend() {
+  if (g_attn_backend < 0) {
+    const char* e = getenv("S2U_ATTN_BACKEND");
+    g_attn_backend = e ? atoi(e) : 0;
+  }
+  return g_attn_backend;
+}
+
 extern "C" {
+
+int s2u_set_attn_backend(int backend) {
+  if (backend < 0 || backend > 2) return S2U_EINVAL;
+  g_attn_backend = backend;
+  return 0;
+}
 
 int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, int B, int H, int W, int nh, int hd,
                      int window, int pool, int dtype, void* stream) {
+  if (dtype == S2U_BF16 && attn_backend() != 1) {
+    const int rc3 = s2u_attn_tc_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, pool, (cudaStream_t)stream);
+    if (rc3 != S2U_EUNSUPPORTED) return rc3;
+    if (attn_backend() == 2) return rc3;
+  }
   if (dtype == S2U_BF16) {
     const int rc2 = s2u_attn_mma_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, pool, (cudaStream_t)stream);
     if (rc2 != S2U_EUNSUPPORTED) return rc2;
@@ -450,6 +479,12 @@ int s2u_win_attn_fwd(const void* qkv, const float* bias, void* out, float* lse, 
 int s2u_win_attn_bwd(const void* qkv, const float* bias, const void* out, const float* lse, const void* dout,
                      void* dqkv, float* dws, int B, int H, int W, int nh, int hd, int window, int pool, int dtype,
                      void* stream) {
+  if (dtype == S2U_BF16 && dws && attn_backend() != 1) {
+    const int rc3 = s2u_attn_tc_bwd(qkv, bias, out, lse, dout, dqkv, dws, B, H, W, nh, hd, window, pool,
+                                    (cudaStream_t)stream);
+    if (rc3 != S2U_EUNSUPPORTED) return rc3;
+    if (attn_backend() == 2) return rc3;
+  }
   if (dtype == S2U_BF16 && dws) {
     const int rc2 = s2u_attn_mma_bwd(qkv, bias, out, lse, dout, dqkv, dws, B, H, W, nh, hd, window, pool,
                                      (cudaStream_t)stream);
