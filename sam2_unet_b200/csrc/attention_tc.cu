@@ -853,8 +853,10 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
         pp[e >> 1] = pack2(p0, p1);
         pd[e >> 1] = pack2(g0, g1);
       }
-      tc_st16(t_row + (uint32_t)(col0 >> 1), pp);
-      tc_st16(t_row + 128u + (uint32_t)(col0 >> 1), pd);
+      // packed bf16 pairs go INSIDE this warp's own (already read) column range - the other warp of the lane quarter
+      // may still be reading its 64 columns: queries [64h + 32cc, +32) -> columns [64h + 16cc, +16)
+      tc_st16(t_row + (uint32_t)(half * 64 + cc * 16), pp);
+      tc_st16(t_row + 128u + (uint32_t)(half * 64 + cc * 16), pd);
     }
     tc_wait_st();
     tc_fence_before();
@@ -867,10 +869,11 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
       for (int ks = 0; ks < nq_mma / 16; ++ks) {
         const uint32_t accf = (i > 0 || ks > 0) ? 1u : 0u;
         const uint64_t o0 = (uint64_t)(ks * (2048 >> 4)), o1 = (uint64_t)(ks * ((16 * s1::C1B) >> 4));
-        tc_mma_bf16_ts(tV, tmem + (uint32_t)(8 * ks), bd0 + o0, id0, accf);            // dV += P^T dO
-        if (C1) tc_mma_bf16_ts(tV + 64, tmem + (uint32_t)(8 * ks), bd1 + o1, id1, accf);
-        tc_mma_bf16_ts(tK, tmem + 128 + (uint32_t)(8 * ks), bq0 + o0, id0, accf);      // dK += dS^T Q
-        if (C1) tc_mma_bf16_ts(tK + 64, tmem + 128 + (uint32_t)(8 * ks), bq1 + o1, id1, accf);
+        const uint32_t acol = (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8);              // 16 queries = 8 packed columns
+        tc_mma_bf16_ts(tV, tmem + acol, bd0 + o0, id0, accf);                           // dV += P^T dO
+        if (C1) tc_mma_bf16_ts(tV + 64, tmem + acol, bd1 + o1, id1, accf);
+        tc_mma_bf16_ts(tK, tmem + 128 + acol, bq0 + o0, id0, accf);                     // dK += dS^T Q
+        if (C1) tc_mma_bf16_ts(tK + 64, tmem + 128 + acol, bq1 + o1, id1, accf);
       }
       tc_commit(bar_d);
     }
@@ -1068,7 +1071,9 @@ static int launch_fwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
 
 template <int C1>
 static int launch_bwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
-  {
+  static int skip = -1;                                      // S2U_ATC_SKIP=1 / 2: leave out the dQ / dK-dV kernel (timing)
+  if (skip < 0) { const char* e = getenv("S2U_ATC_SKIP"); skip = e ? atoi(e) : 0; }
+  if (skip != 1) {
     dim3 grid(pl.total_items, p.nh);
     if (pl.stream) {
       S2U_ALLOW_SMEM((bwd_dq_kernel<C1, true>));
@@ -1079,7 +1084,7 @@ static int launch_bwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
     }
     S2U_LAUNCH_CHECK();
   }
-  {
+  if (skip != 2) {
     dim3 grid(pl.total_kitems, p.nh);
     if (pl.stream) {
       S2U_ALLOW_SMEM((bwd_dkv_kernel<C1, true>));

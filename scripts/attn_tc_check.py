@@ -47,17 +47,28 @@ def err(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
 
 
-def timeit(fn, iters=30):
-    for _ in range(3):
-        fn()
+def timeit(fn, iters=24, reps=5):
+    """us per call: `iters` calls captured in one CUDA graph (no Python / launch latency in the number), replayed."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(reps):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3
+    return e0.elapsed_time(e1) / (iters * reps) * 1e3
 
 
 def main():
@@ -92,7 +103,6 @@ def main():
                      (4, 64, 64, 8, 72, 0)]:
             B, H, W, nh, hd, window = case
             C = nh * hd
-            ops = Ops(torch.bfloat16, cuda, 0)
             sets = []
             for i in range(6):                        # rotate through > L2 worth of operands
                 qkv = _rand((B, H, W, 3 * C), "bf16", cuda, 10 + i)
@@ -100,6 +110,10 @@ def main():
                              torch.empty(B, H, W, nh, device=cuda), _rand((B, H, W, C), "bf16", cuda, 20 + i),
                              torch.empty(B, H, W, 3 * C, device=cuda, dtype=torch.bfloat16)))
             bias = _rand((3 * C,), "fp32", cuda, 2)
+            dws = torch.empty(B, H, W, nh, device=cuda)
+            for q, o, l, d, dq in sets:               # valid out / lse for the backward
+                _lib.call("s2u_set_attn_backend", 1)
+                Ops(torch.bfloat16, cuda, 0).attn_fwd(q, bias, o, l, B, H, W, nh, hd, window, False)
             for backend, name in ((1, "mma.sync"), (2, "tcgen05 ")):
                 _lib.call("s2u_set_attn_backend", backend)
                 k = [0]
@@ -107,12 +121,14 @@ def main():
                 def f():
                     q, o, l, d, dq = sets[k[0] % len(sets)]
                     k[0] += 1
-                    ops.attn_fwd(q, bias, o, l, B, H, W, nh, hd, window, False)
+                    Ops(torch.bfloat16, cuda, 0).attn_fwd(q, bias, o, l, B, H, W, nh, hd, window, False)
 
                 def g():
                     q, o, l, d, dq = sets[k[0] % len(sets)]
                     k[0] += 1
-                    ops.attn_bwd(q, bias, o, l, d, dq, B, H, W, nh, hd, window, False)
+                    _lib.call("s2u_win_attn_bwd", q.data_ptr(), bias.data_ptr(), o.data_ptr(), l.data_ptr(), d.data_ptr(),
+                              dq.data_ptr(), dws.data_ptr(), B, H, W, nh, hd, window, 0, 1,
+                              torch.cuda.current_stream().cuda_stream)
                 t_f = timeit(f)
                 msg = f"{case} {name}: fwd {t_f:7.1f} us"
                 if args.bwd:
