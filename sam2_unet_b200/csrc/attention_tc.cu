@@ -32,6 +32,14 @@ namespace atc {
 
 using namespace umma;
 
+// -DS2U_ATC_TIMING: thread 0 of every forward CTA stamps its phases (globaltimer ns) into dws[8 * cta] (tuning only)
+#ifdef S2U_ATC_TIMING
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ATC_STAMP(i) do { if (threadIdx.x == 0 && p.dws) reinterpret_cast<long long*>(p.dws)[8LL * (blockIdx.y * gridDim.x + blockIdx.x) + (i)] = gtime(); } while (0)
+#else
+#define ATC_STAMP(i) do {} while (0)
+#endif
+
 constexpr int NTHR = 128;
 constexpr int MAXCLS = 4;
 
@@ -147,254 +155,6 @@ __device__ __forceinline__ long long query_token(const TcParams& p, const Item& 
   return ((long long)it.b * p.H + it.yq0 + ry) * p.W + it.x0 + rx;
 }
 
-// the virtual pad key (row n_real: k = v = bias of this head) and zero rows up to the MMA's key count, written with
-// st.shared into the swizzled K / V tiles (window mode only; streaming tiles get their tail from TMA zero fill)
-template <int C1>
-__device__ __forceinline__ void write_pad_rows(uint32_t k0, uint32_t k1, uint32_t v0, uint32_t v1, const TcParams& p,
-                                               const Item& it, int head, int n_mma) {
-  constexpr int NCH = 8 + C1 / 8;
-  const int C = p.nh * p.hd;
-  const int first = it.n_real, rows = n_mma - it.n_real;
-  for (int e = threadIdx.x; e < rows * NCH * 2; e += NTHR) {
-    const int which = e & 1;                        // 0: K, 1: V
-    const int rc = e >> 1;
-    const int row = first + rc / NCH, c16 = rc % NCH;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (row == it.n_real && it.n_pad > 0) {
-      const float* bsrc = p.bias + (which + 1) * C + head * p.hd;
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = c16 * 8 + 2 * i;
-        w[i] = pack2(d < p.hd ? bsrc[d] : 0.f, d + 1 < p.hd ? bsrc[d + 1] : 0.f);
-      }
-      val = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    const uint32_t b0 = which ? v0 : k0, b1 = which ? v1 : k1;
-    sts16(c16 < 8 ? tile0_addr(b0, row, c16) : tile1_addr<C1>(b1, row, c16 - 8), val);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------- forward
-template <int C1, bool STREAM>
-__global__ void __launch_bounds__(NTHR, C1 == 16 ? 2 : 1) fwd_kernel(const __grid_constant__ TcParams p) {
-  using sm = Smem<C1>;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[6];
-  __shared__ uint32_t tmem_holder;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int head = blockIdx.y;
-  const Item it = decode_item<STREAM>(p, blockIdx.x);
-  const TcClass& cl = p.cls[it.c];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar0 = smem_u32(bars);
-  const uint32_t bar_k[2] = {bar0, bar0 + 8}, bar_v[2] = {bar0 + 16, bar0 + 24}, bar_s = bar0 + 32, bar_o = bar0 + 40;
-  constexpr int KBCAP = STREAM ? 128 : 256;                  // keys per block
-  const int nblk = STREAM ? (it.n_keys + 127) / 128 : 1;
-  const int C = p.nh * p.hd;
-
-  pdl_launch_dependents();
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.q0[it.c]);
-      tma_prefetch_desc(&p.k0[it.c]);
-      if (C1) { tma_prefetch_desc(&p.q1[it.c]); tma_prefetch_desc(&p.k1[it.c]); }
-      for (int i = 0; i < 6; ++i) mbar_init(bar0 + 8u * i, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (!STREAM) {                                            // pad key / zero tail rows (no dependency on the producer kernel)
-    const int n_mma = max(16, (it.n_keys + 15) & ~15);
-    write_pad_rows<C1>(base + sm::K0, base + sm::K1, base + sm::V0, base + sm::V1, p, it, head, n_mma);
-    fence_proxy_async();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_holder;
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter
-  pdl_wait();                                               // qkv of the producer GEMM is complete
-
-  const int q_box_rows = STREAM ? 128 : cl.qbh * cl.rw;
-  const int k_box_rows = STREAM ? 128 : cl.rh * cl.rw;
-  auto load_kv = [&](int j) {                               // key / value block j -> buffer j & 1
-    const int buf = j & 1;
-    const uint32_t kb0 = base + sm::K0 + buf * (128 * 128), kb1 = base + sm::K1 + buf * (128 * sm::C1B);
-    const uint32_t vb0 = base + sm::V0 + buf * (128 * 128), vb1 = base + sm::V1 + buf * (128 * sm::C1B);
-    const int x = STREAM ? j * 128 : it.x0;
-    const uint32_t bytes = (uint32_t)k_box_rows * (128 + sm::C1B);
-    mbar_expect_tx(bar_k[buf], bytes + (j == 0 ? (uint32_t)q_box_rows * (128 + sm::C1B) : 0u));
-    tma_load_5d(kb0, &p.k0[it.c], bar_k[buf], 0, p.nh + head, x, it.yk0, it.b);
-    if (C1) tma_load_5d(kb1, &p.k1[it.c], bar_k[buf], 64, p.nh + head, x, it.yk0, it.b);
-    mbar_expect_tx(bar_v[buf], bytes);
-    tma_load_5d(vb0, &p.k0[it.c], bar_v[buf], 0, 2 * p.nh + head, x, it.yk0, it.b);
-    if (C1) tma_load_5d(vb1, &p.k1[it.c], bar_v[buf], 64, 2 * p.nh + head, x, it.yk0, it.b);
-  };
-  if (tid == 0) {
-    load_kv(0);
-    tma_load_5d(base + sm::Q0, &p.q0[it.c], bar_k[0], 0, head, it.x0, it.yq0, it.b);
-    if (C1) tma_load_5d(base + sm::Q1, &p.q1[it.c], bar_k[0], 64, head, it.x0, it.yq0, it.b);
-    if (nblk > 1) load_kv(1);
-  }
-
-  const float sl2 = p.scale * 1.4426950408889634f;
-  const float bonus = it.n_pad > 0 ? __logf((float)it.n_pad) / p.scale : 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  const uint32_t tS = tmem, tO = tmem + 128;
-
-  for (int j = 0; j < nblk; ++j) {
-    const int buf = j & 1;
-    const int keys_here = min(KBCAP, it.n_keys - j * KBCAP);
-    const int n_mma = max(16, (keys_here + 15) & ~15);
-    if (tid == 0) {
-      if (j > 0) mbar_wait(bar_o, (uint32_t)(j - 1) & 1u);  // P of block j-1 (aliases S) has been consumed
-      mbar_wait(bar_k[buf], (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t kb0 = base + sm::K0 + buf * (128 * 128), kb1 = base + sm::K1 + buf * (128 * sm::C1B);
-      const uint64_t dq0 = smem_desc_sw128(base + sm::Q0), dk0 = smem_desc_sw128(kb0);
-      const uint32_t id = idesc_n(n_mma, false);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, dq0 + 2 * k, dk0 + 2 * k, id, k > 0 ? 1u : 0u);
-      if (C1) {
-        const uint64_t dq1 = smem_desc(base + sm::Q1, 16, sm::SBO1, sm::LAYOUT1);
-        const uint64_t dk1 = smem_desc(kb1, 16, sm::SBO1, sm::LAYOUT1);
-#pragma unroll
-        for (int k = 0; k < C1 / 16; ++k) tc_mma_bf16(tS, dq1 + 2 * k, dk1 + 2 * k, id, 1u);
-      }
-      tc_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_s, (uint32_t)j & 1u);
-    tc_fence_after();
-
-    // ---- pass 1: row maximum
-    const int nch = (n_mma + 31) >> 5;
-    const int key0 = j * KBCAP;
-    float mx = -INFINITY;
-    for (int c = 0; c < nch; ++c) {
-      uint32_t r[32];
-      tc_ld32(t_row + (uint32_t)(c * 32), r);
-      tc_wait_ld();
-      const int col0 = key0 + c * 32;
-      if (col0 + 32 <= it.n_real) {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float v = __uint_as_float(r[e]);
-          if (col0 + e == it.n_real) v += bonus;
-          if (col0 + e < it.n_keys) mx = fmaxf(mx, v);
-        }
-      }
-    }
-    const float m_new = fmaxf(m_run, mx);
-    const float alpha = ex2((m_run - m_new) * sl2);         // 0 for the first block (m_run = -inf)
-    const float mb = -m_new * sl2;
-    if (STREAM && j > 0) {
-      // O holds blocks 0..j-1 (their PV product is complete): rescale it to the new maximum
-      mbar_wait(bar_o, (uint32_t)(j - 1) & 1u);
-      tc_fence_after();
-      if (tid == 0 && j + 1 < nblk) load_kv(j + 1);         // both buffers (j+1)&1 are free now
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < (64 + C1) / 16; ++c) {
-        uint32_t r[16];
-        tc_ld16(t_row + 128u + (uint32_t)(c * 16), r);
-        tc_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-        tc_st16(t_row + 128u + (uint32_t)(c * 16), r);
-      }
-    }
-    // ---- pass 2: P = exp(S * scale - max) as bf16 over S, row sum
-    float sum = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      uint32_t r[32], pk[16];
-      tc_ld32(t_row + (uint32_t)(c * 32), r);
-      tc_wait_ld();
-      const int col0 = key0 + c * 32;
-      if (col0 + 32 <= it.n_real) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float a = ex2(fmaf(__uint_as_float(r[e]), sl2, mb)), b = ex2(fmaf(__uint_as_float(r[e + 1]), sl2, mb));
-          sum += a + b;
-          pk[e >> 1] = pack2(a, b);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]);
-          if (col0 + e == it.n_real) v0 += bonus;
-          if (col0 + e + 1 == it.n_real) v1 += bonus;
-          const float a = col0 + e < it.n_keys ? ex2(fmaf(v0, sl2, mb)) : 0.f;
-          const float b = col0 + e + 1 < it.n_keys ? ex2(fmaf(v1, sl2, mb)) : 0.f;
-          sum += a + b;
-          pk[e >> 1] = pack2(a, b);
-        }
-      }
-      tc_st16(t_row + (uint32_t)(c * 16), pk);
-    }
-    l_run = l_run * alpha + sum;
-    m_run = m_new;
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(bar_v[buf], (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t vb0 = base + sm::V0 + buf * (128 * 128), vb1 = base + sm::V1 + buf * (128 * sm::C1B);
-      const uint64_t dv0 = smem_desc(vb0, 1024, 1024, 2), dv1 = smem_desc(vb1, sm::SBO1, sm::SBO1, sm::LAYOUT1);
-      const uint32_t id0 = idesc_n(64, true), id1 = idesc_n(C1 ? C1 : 16, true);
-      for (int ks = 0; ks < n_mma / 16; ++ks) {
-        const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-        tc_mma_bf16_ts(tO, tS + (uint32_t)(8 * ks), dv0 + (uint64_t)(ks * (2048 >> 4)), id0, acc);
-        if (C1) tc_mma_bf16_ts(tO + 64, tS + (uint32_t)(8 * ks), dv1 + (uint64_t)(ks * ((16 * sm::C1B) >> 4)), id1, acc);
-      }
-      tc_commit(bar_o);
-    }
-    __syncwarp();
-  }
-  mbar_wait(bar_o, (uint32_t)(nblk - 1) & 1u);
-  tc_fence_after();
-
-  // ---- epilogue: O / l -> bf16 rows of `out` (16-byte stores), lse
-  const bool live = tid < it.q_rows;
-  const long long tok = live ? query_token<STREAM>(p, it, tid) : 0;
-  const float inv = 1.f / l_run;
-  bf16* orow = p.out + tok * C + head * p.hd;
-#pragma unroll
-  for (int c = 0; c < (64 + C1) / 16; ++c) {
-    uint32_t r[16];
-    tc_ld16(t_row + 128u + (uint32_t)(c * 16), r);
-    tc_wait_ld();
-    if (live) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int d = c * 16 + h * 8;
-        if (d < p.hd) {
-          uint4 u;
-          u.x = pack2(__uint_as_float(r[h * 8 + 0]) * inv, __uint_as_float(r[h * 8 + 1]) * inv);
-          u.y = pack2(__uint_as_float(r[h * 8 + 2]) * inv, __uint_as_float(r[h * 8 + 3]) * inv);
-          u.z = pack2(__uint_as_float(r[h * 8 + 4]) * inv, __uint_as_float(r[h * 8 + 5]) * inv);
-          u.w = pack2(__uint_as_float(r[h * 8 + 6]) * inv, __uint_as_float(r[h * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + d) = u;
-        }
-      }
-    }
-  }
-  if (live) p.lse[tok * p.nh + head] = m_run * p.scale + __logf(l_run);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
-}
-
-
 // ------------------------------------------------------------------------------------------------ backward
 // Shared by the two backward kernels: keys are visited in blocks of <= 128 (window mode: the same row boxes as the
 // query tiles, i.e. qbh window rows; streaming: 128 tokens).
@@ -445,6 +205,255 @@ __device__ __forceinline__ void write_tail_rows(uint32_t k0, uint32_t k1, uint32
   }
 }
 
+// ------------------------------------------------------------------------------------------------- forward
+// 256 threads: the two warps of a TMEM lane quarter (warp w and w + 4) share 32 query rows and split the key columns
+// of each row in two contiguous ranges; row maximum and row sum are exchanged through shared memory.  Each thread
+// writes its bf16 P INSIDE the column range it has already read (the partner may still be reading its own), so the
+// packed A operand sits at columns [0, 16*h0) and [32*h0, ...): the MMA issuer steps its tensor-memory address
+// accordingly.  O: columns [64,128) + [192,208) (windows: S is dead by then), [128,208) when streaming.
+constexpr int NTHR_F = 256;
+template <int C1, bool STREAM>
+__global__ void __launch_bounds__(NTHR_F, C1 == 16 ? 2 : 1) fwd_kernel(const __grid_constant__ TcParams p) {
+  using sm = Smem<C1>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[6];
+  __shared__ uint32_t tmem_holder;
+  __shared__ float red[2][2][128];                          // [max | sum][column half][row]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;
+  const int head = blockIdx.y;
+  const Item it = decode_item<STREAM>(p, blockIdx.x);
+  const TcClass& cl = p.cls[it.c];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_k[2] = {bar0, bar0 + 8}, bar_v[2] = {bar0 + 16, bar0 + 24}, bar_s = bar0 + 32, bar_o = bar0 + 40;
+  constexpr int KBCAP = STREAM ? 128 : 256;                  // keys per block
+  const int nblk = STREAM ? (it.n_keys + 127) / 128 : 1;
+  const int C = p.nh * p.hd;
+  const int q_box_rows = STREAM ? 128 : cl.qbh * cl.rw;
+  const int k_box_rows = STREAM ? 128 : cl.rh * cl.rw;
+  ATC_STAMP(0);
+
+  auto load_kv = [&](int j) {                               // key / value block j -> buffer j & 1
+    const int buf = j & 1;
+    const uint32_t kb0 = base + sm::K0 + buf * (128 * 128), kb1 = base + sm::K1 + buf * (128 * sm::C1B);
+    const uint32_t vb0 = base + sm::V0 + buf * (128 * 128), vb1 = base + sm::V1 + buf * (128 * sm::C1B);
+    const int x = STREAM ? j * 128 : it.x0;
+    const uint32_t bytes = (uint32_t)k_box_rows * (128 + sm::C1B);
+    mbar_expect_tx(bar_k[buf], bytes + (j == 0 ? (uint32_t)q_box_rows * (128 + sm::C1B) : 0u));
+    tma_load_5d(kb0, &p.k0[it.c], bar_k[buf], 0, p.nh + head, x, it.yk0, it.b);
+    if (C1) tma_load_5d(kb1, &p.k1[it.c], bar_k[buf], 64, p.nh + head, x, it.yk0, it.b);
+    mbar_expect_tx(bar_v[buf], bytes);
+    tma_load_5d(vb0, &p.k0[it.c], bar_v[buf], 0, 2 * p.nh + head, x, it.yk0, it.b);
+    if (C1) tma_load_5d(vb1, &p.k1[it.c], bar_v[buf], 64, 2 * p.nh + head, x, it.yk0, it.b);
+  };
+
+  pdl_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      // barriers, then straight to the TMA loads: their latency overlaps the TMEM allocation and the pad rows
+      for (int i = 0; i < 6; ++i) mbar_init(bar0 + 8u * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      pdl_wait();                                           // qkv of the producer GEMM is complete
+      load_kv(0);
+      tma_load_5d(base + sm::Q0, &p.q0[it.c], bar_k[0], 0, head, it.x0, it.yq0, it.b);
+      if (C1) tma_load_5d(base + sm::Q1, &p.q1[it.c], bar_k[0], 64, head, it.x0, it.yq0, it.b);
+      if (nblk > 1) load_kv(1);
+    }
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (!STREAM) {                                            // pad key / zero tail rows (rows the TMA boxes never touch)
+    const int n_mma = max(16, (it.n_keys + 15) & ~15);
+    write_tail_rows<C1>(base + sm::K0, base + sm::K1, base + sm::V0, base + sm::V1, p, head, it.n_real, n_mma,
+                        it.n_pad > 0 ? it.n_real : -1);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);   // this warp's lane quarter
+  ATC_STAMP(1);
+  pdl_wait();
+  ATC_STAMP(2);
+
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const float bonus = it.n_pad > 0 ? __logf((float)it.n_pad) / p.scale : 0.f;
+  float m_run = -INFINITY, l_run = 0.f;                     // l_run: this thread's column half only
+  const uint32_t tS = tmem;
+  // O: 64 + C1 columns that neither the packed P ranges nor (when streaming) the next S touch
+  const bool o_high = STREAM || it.n_keys <= 128;
+  const uint32_t o0col = o_high ? 128u : 64u;
+  const uint32_t tO0 = tmem + o0col, tO1 = tmem + 192u;
+
+  for (int j = 0; j < nblk; ++j) {
+    const int buf = j & 1;
+    const int keys_here = min(KBCAP, it.n_keys - j * KBCAP);
+    const int n_mma = max(16, (keys_here + 15) & ~15);
+    if (tid == 0) {
+      if (j > 0) mbar_wait(bar_o, (uint32_t)(j - 1) & 1u);  // P of block j-1 (aliases S) has been consumed
+      mbar_wait(bar_k[buf], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t kb0 = base + sm::K0 + buf * (128 * 128), kb1 = base + sm::K1 + buf * (128 * sm::C1B);
+      const uint64_t dq0 = smem_desc_sw128(base + sm::Q0), dk0 = smem_desc_sw128(kb0);
+      const uint32_t id = idesc_n(n_mma, false);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, dq0 + 2 * k, dk0 + 2 * k, id, k > 0 ? 1u : 0u);
+      if (C1) {
+        const uint64_t dq1 = smem_desc(base + sm::Q1, 16, sm::SBO1, sm::LAYOUT1);
+        const uint64_t dk1 = smem_desc(kb1, 16, sm::SBO1, sm::LAYOUT1);
+#pragma unroll
+        for (int k = 0; k < C1 / 16; ++k) tc_mma_bf16(tS, dq1 + 2 * k, dk1 + 2 * k, id, 1u);
+      }
+      tc_commit(bar_s);
+      ATC_STAMP(3);
+    }
+    __syncwarp();
+    mbar_wait(bar_s, (uint32_t)j & 1u);
+    tc_fence_after();
+    ATC_STAMP(4);
+
+    // this thread's 32-column chunks of the row: [c_beg, c_end)
+    const int nch = (n_mma + 31) >> 5;
+    const int h0 = nch > 4 ? 4 : (nch + 1) >> 1;            // > 128 keys: P ranges [0,64) and [128,..), O in between
+    const int c_beg = half ? h0 : 0, c_end = half ? nch : h0;
+    const int key0 = j * KBCAP;
+    // ---- pass 1: row maximum
+    float mx = -INFINITY;
+    for (int c = c_beg; c < c_end; ++c) {
+      uint32_t r[32];
+      tc_ld32(t_row + (uint32_t)(c * 32), r);
+      tc_wait_ld();
+      const int col0 = key0 + c * 32;
+      if (col0 + 32 <= it.n_real) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float v = __uint_as_float(r[e]);
+          if (col0 + e == it.n_real) v += bonus;
+          if (col0 + e < it.n_keys) mx = fmaxf(mx, v);
+        }
+      }
+    }
+    red[0][half][row] = mx;
+    if (STREAM && j > 0) {
+      // O holds blocks 0..j-1 once their PV product is complete
+      mbar_wait(bar_o, (uint32_t)(j - 1) & 1u);
+      tc_fence_after();
+      if (tid == 0 && j + 1 < nblk) load_kv(j + 1);         // both buffers (j+1)&1 are free now
+    }
+    __syncthreads();
+    const float m_new = fmaxf(m_run, fmaxf(red[0][0][row], red[0][1][row]));
+    const float alpha = ex2((m_run - m_new) * sl2);         // 0 for the first block (m_run = -inf)
+    const float mb = -m_new * sl2;
+    if (STREAM && j > 0) {
+      // rescale O to the new maximum; the two threads of a row take 48 and 16 + C1 of its columns
+      for (int c = half ? 3 : 0; c < (half ? (64 + C1) / 16 : 3); ++c) {
+        uint32_t r[16];
+        const uint32_t a = t_row + (c < 4 ? 128u + (uint32_t)(c * 16) : 192u + (uint32_t)((c - 4) * 16));
+        tc_ld16(a, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+        tc_st16(a, r);
+      }
+    }
+    // ---- pass 2: P = exp(S * scale - max) as bf16 inside this thread's column range, partial row sum
+    float sum = 0.f;
+    for (int c = c_beg; c < c_end; ++c) {
+      uint32_t r[32], pk[16];
+      tc_ld32(t_row + (uint32_t)(c * 32), r);
+      tc_wait_ld();
+      const int col0 = key0 + c * 32;
+      if (col0 + 32 <= it.n_real) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float a = ex2(fmaf(__uint_as_float(r[e]), sl2, mb)), b = ex2(fmaf(__uint_as_float(r[e + 1]), sl2, mb));
+          sum += a + b;
+          pk[e >> 1] = pack2(a, b);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]);
+          if (col0 + e == it.n_real) v0 += bonus;
+          if (col0 + e + 1 == it.n_real) v1 += bonus;
+          const float a = col0 + e < it.n_keys ? ex2(fmaf(v0, sl2, mb)) : 0.f;
+          const float b = col0 + e + 1 < it.n_keys ? ex2(fmaf(v1, sl2, mb)) : 0.f;
+          sum += a + b;
+          pk[e >> 1] = pack2(a, b);
+        }
+      }
+      tc_st16(t_row + (uint32_t)(half ? 32 * h0 + 16 * (c - h0) : 16 * c), pk);
+    }
+    l_run = l_run * alpha + sum;
+    m_run = m_new;
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    ATC_STAMP(5);
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v[buf], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t vb0 = base + sm::V0 + buf * (128 * 128), vb1 = base + sm::V1 + buf * (128 * sm::C1B);
+      const uint64_t dv0 = smem_desc(vb0, 1024, 1024, 2), dv1 = smem_desc(vb1, sm::SBO1, sm::SBO1, sm::LAYOUT1);
+      const uint32_t id0 = idesc_n(64, true), id1 = idesc_n(C1 ? C1 : 16, true);
+      for (int ks = 0; ks < n_mma / 16; ++ks) {
+        const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+        const int c = ks >> 1;                              // 16 keys = 8 packed columns of chunk c
+        const uint32_t acol = (uint32_t)((c < h0 ? 16 * c : 32 * h0 + 16 * (c - h0)) + 8 * (ks & 1));
+        tc_mma_bf16_ts(tO0, tS + acol, dv0 + (uint64_t)(ks * (2048 >> 4)), id0, acc);
+        if (C1) tc_mma_bf16_ts(tO1, tS + acol, dv1 + (uint64_t)(ks * ((16 * sm::C1B) >> 4)), id1, acc);
+      }
+      tc_commit(bar_o);
+    }
+    __syncwarp();
+  }
+  red[1][half][row] = l_run;
+  mbar_wait(bar_o, (uint32_t)(nblk - 1) & 1u);
+  tc_fence_after();
+  __syncthreads();
+  ATC_STAMP(6);
+
+  // ---- epilogue: O / l -> bf16 rows of `out` (16-byte stores), lse.  Column half 0: d 0..47, half 1: d 48..hd-1
+  const bool live = row < it.q_rows;
+  const long long tok = live ? query_token<STREAM>(p, it, row) : 0;
+  const float l_tot = red[1][0][row] + red[1][1][row];
+  const float inv = 1.f / l_tot;
+  bf16* orow = p.out + tok * C + head * p.hd;
+  for (int c = half ? 3 : 0; c < (half ? (64 + C1) / 16 : 3); ++c) {
+    uint32_t r[16];
+    tc_ld16(t_row + (c < 4 ? o0col + (uint32_t)(c * 16) : 192u + (uint32_t)((c - 4) * 16)), r);
+    tc_wait_ld();
+    if (live) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int d = c * 16 + h * 8;
+        if (d < p.hd) {
+          uint4 u;
+          u.x = pack2(__uint_as_float(r[h * 8 + 0]) * inv, __uint_as_float(r[h * 8 + 1]) * inv);
+          u.y = pack2(__uint_as_float(r[h * 8 + 2]) * inv, __uint_as_float(r[h * 8 + 3]) * inv);
+          u.z = pack2(__uint_as_float(r[h * 8 + 4]) * inv, __uint_as_float(r[h * 8 + 5]) * inv);
+          u.w = pack2(__uint_as_float(r[h * 8 + 6]) * inv, __uint_as_float(r[h * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + d) = u;
+        }
+      }
+    }
+  }
+  if (live && half == 0) p.lse[tok * p.nh + head] = m_run * p.scale + __logf(l_tot);
+  tc_fence_before();
+  __syncthreads();
+  ATC_STAMP(7);
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
 template <int C1>
 struct SmemDq {
   static constexpr int C1B = C1 * 2;
@@ -478,26 +487,6 @@ __global__ void __launch_bounds__(NTHR, C1 == 16 ? 2 : 1) bwd_dq_kernel(const __
   const int nblk = cl.n_kb;
   const int C = p.nh * p.hd;
 
-  pdl_launch_dependents();
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.q0[it.c]);
-      tma_prefetch_desc(&p.o0[it.c]);
-      if (C1) { tma_prefetch_desc(&p.q1[it.c]); tma_prefetch_desc(&p.o1[it.c]); }
-      for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8u * i, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_holder;
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
-  pdl_wait();
-
   const uint32_t tile_bytes = (uint32_t)(STREAM ? 128 : cl.qbh * cl.rw) * (128 + s1::C1B);
   auto load_k = [&](int j) {
     const KeyBlock kb = key_block<STREAM>(p, cl, it, j);
@@ -512,15 +501,30 @@ __global__ void __launch_bounds__(NTHR, C1 == 16 ? 2 : 1) bwd_dq_kernel(const __
     tma_load_5d(base + sm::V0, &p.q0[it.c], bar_v, 0, 2 * p.nh + head, kb.x, kb.y, it.b);
     if (C1) tma_load_5d(base + sm::V1, &p.q1[it.c], bar_v, 64, 2 * p.nh + head, kb.x, kb.y, it.b);
   };
-  if (tid == 0) {
-    load_k(0);
-    tma_load_5d(base + sm::Q0, &p.q0[it.c], bar_k[0], 0, head, it.x0, it.yq0, it.b);
-    if (C1) tma_load_5d(base + sm::Q1, &p.q1[it.c], bar_k[0], 64, head, it.x0, it.yq0, it.b);
-    tma_load_5d(base + sm::D0, &p.o0[it.c], bar_k[0], 0, head, it.x0, it.yq0, it.b);
-    if (C1) tma_load_5d(base + sm::D1, &p.o1[it.c], bar_k[0], 64, head, it.x0, it.yq0, it.b);
-    load_v(0);
-    if (nblk > 1) load_k(1);
+  pdl_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8u * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      pdl_wait();
+      load_k(0);
+      tma_load_5d(base + sm::Q0, &p.q0[it.c], bar_k[0], 0, head, it.x0, it.yq0, it.b);
+      if (C1) tma_load_5d(base + sm::Q1, &p.q1[it.c], bar_k[0], 64, head, it.x0, it.yq0, it.b);
+      tma_load_5d(base + sm::D0, &p.o0[it.c], bar_k[0], 0, head, it.x0, it.yq0, it.b);
+      if (C1) tma_load_5d(base + sm::D1, &p.o1[it.c], bar_k[0], 64, head, it.x0, it.yq0, it.b);
+      load_v(0);
+      if (nblk > 1) load_k(1);
+    }
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  pdl_wait();
 
   // this thread's query row: lse, D = sum_d dO * O (also written out for the dK/dV kernel)
   const bool live = tid < it.q_rows;
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(NTHR, C1 == 16 ? 2 : 1) bwd_dq_kernel(const __
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0)
+  if (warp == 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
@@ -713,16 +717,34 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
   const int C = p.nh * p.hd;
   const int q_box_rows = STREAM ? 128 : cl.qbh * cl.rw;
 
+  const uint32_t tile_bytes = (uint32_t)q_box_rows * (128 + s1::C1B);
+  auto q_origin = [&](int i, int& x, int& y) {
+    x = STREAM ? i * 128 : it.x0;
+    y = STREAM ? 0 : it.yk0 + i * cl.qbh;
+  };
+  auto load_q = [&](int i) {
+    const int buf = i & 1;
+    int x, y;
+    q_origin(i, x, y);
+    mbar_expect_tx(bar_in[buf], tile_bytes * (i == 0 ? 4u : 2u));      // tile 0 also carries K and V
+    tma_load_5d(base + sm::Q0 + buf * sm::T0, &p.q0[c], bar_in[buf], 0, head, x, y, it.b);
+    if (C1) tma_load_5d(base + sm::Q1 + buf * sm::T1, &p.q1[c], bar_in[buf], 64, head, x, y, it.b);
+    tma_load_5d(base + sm::D0 + buf * sm::T0, &p.o0[c], bar_in[buf], 0, head, x, y, it.b);
+    if (C1) tma_load_5d(base + sm::D1 + buf * sm::T1, &p.o1[c], bar_in[buf], 64, head, x, y, it.b);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_wait();                                              // dws from the dQ kernel, lse, dout
+    load_q(0);
+    tma_load_5d(base + sm::K0, &p.q0[c], bar_in[0], 0, p.nh + head, kb.x, kb.y, it.b);
+    if (C1) tma_load_5d(base + sm::K1, &p.q1[c], bar_in[0], 64, p.nh + head, kb.x, kb.y, it.b);
+    tma_load_5d(base + sm::V0, &p.q0[c], bar_in[0], 0, 2 * p.nh + head, kb.x, kb.y, it.b);
+    if (C1) tma_load_5d(base + sm::V1, &p.q1[c], bar_in[0], 64, 2 * p.nh + head, kb.x, kb.y, it.b);
+    if (n_qt > 1) load_q(1);
+  }
   pdl_launch_dependents();
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.q0[c]);
-      tma_prefetch_desc(&p.o0[c]);
-      if (C1) { tma_prefetch_desc(&p.q1[c]); tma_prefetch_desc(&p.o1[c]); }
-      for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8u * i, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -748,29 +770,6 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
   const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
   pdl_wait();                                                // dws / dqkv's q third from the dQ kernel, lse, dout
 
-  const uint32_t tile_bytes = (uint32_t)q_box_rows * (128 + s1::C1B);
-  auto q_origin = [&](int i, int& x, int& y) {
-    x = STREAM ? i * 128 : it.x0;
-    y = STREAM ? 0 : it.yk0 + i * cl.qbh;
-  };
-  auto load_q = [&](int i) {
-    const int buf = i & 1;
-    int x, y;
-    q_origin(i, x, y);
-    mbar_expect_tx(bar_in[buf], tile_bytes * (i == 0 ? 4u : 2u));      // tile 0 also carries K and V
-    tma_load_5d(base + sm::Q0 + buf * sm::T0, &p.q0[c], bar_in[buf], 0, head, x, y, it.b);
-    if (C1) tma_load_5d(base + sm::Q1 + buf * sm::T1, &p.q1[c], bar_in[buf], 64, head, x, y, it.b);
-    tma_load_5d(base + sm::D0 + buf * sm::T0, &p.o0[c], bar_in[buf], 0, head, x, y, it.b);
-    if (C1) tma_load_5d(base + sm::D1 + buf * sm::T1, &p.o1[c], bar_in[buf], 64, head, x, y, it.b);
-  };
-  if (tid == 0) {
-    load_q(0);
-    tma_load_5d(base + sm::K0, &p.q0[c], bar_in[0], 0, p.nh + head, kb.x, kb.y, it.b);
-    if (C1) tma_load_5d(base + sm::K1, &p.q1[c], bar_in[0], 64, p.nh + head, kb.x, kb.y, it.b);
-    tma_load_5d(base + sm::V0, &p.q0[c], bar_in[0], 0, 2 * p.nh + head, kb.x, kb.y, it.b);
-    if (C1) tma_load_5d(base + sm::V1, &p.q1[c], bar_in[0], 64, 2 * p.nh + head, kb.x, kb.y, it.b);
-    if (n_qt > 1) load_q(1);
-  }
   // valid queries of tile i and their tokens
   auto q_rows_of = [&](int i) { return STREAM ? min(128, it.rw - i * 128) : min(cl.qbh, cl.rh - i * cl.qbh) * cl.rw; };
   auto fill_ld = [&](int i) {                                 // lse * log2e and D of tile i's queries -> LDs[i & 1]
@@ -916,7 +915,7 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0)
+  if (warp == 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
@@ -1060,10 +1059,10 @@ static int launch_fwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
   dim3 grid(pl.total_items, p.nh);
   if (pl.stream) {
     S2U_ALLOW_SMEM((fwd_kernel<C1, true>));
-    S2U_LAUNCH((fwd_kernel<C1, true>), grid, NTHR, sm::FWD_BYTES, st, p);
+    S2U_LAUNCH((fwd_kernel<C1, true>), grid, NTHR_F, sm::FWD_BYTES, st, p);
   } else {
     S2U_ALLOW_SMEM((fwd_kernel<C1, false>));
-    S2U_LAUNCH((fwd_kernel<C1, false>), grid, NTHR, sm::FWD_BYTES, st, p);
+    S2U_LAUNCH((fwd_kernel<C1, false>), grid, NTHR_F, sm::FWD_BYTES, st, p);
   }
   S2U_LAUNCH_CHECK();
   return 0;
@@ -1109,6 +1108,9 @@ int s2u_attn_tc_fwd(const void* qkv, const float* bias, void* out, float* lse, i
   if (rc) return rc;
   atc::TcParams p = pl->p;
   p.bias = bias; p.qkv = (const bf16*)qkv; p.out = (bf16*)out; p.lse = lse;
+#ifdef S2U_ATC_TIMING
+  { const char* e = getenv("S2U_ATC_TIMING_BUF"); p.dws = e ? (float*)strtoull(e, nullptr, 0) : nullptr; }
+#endif
   if (hd - 64 <= 16) return atc::launch_fwd<16>(*pl, p, st);
   return atc::launch_fwd<32>(*pl, p, st);
 }

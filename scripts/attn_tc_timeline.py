@@ -1,0 +1,35 @@
+"""Per-CTA phase timeline of the tcgen05 attention forward (library built with -DS2U_ATC_TIMING)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from sam2_unet_b200 import _lib
+from sam2_unet_b200.engine import Ops
+
+B, H, W, nh, hd, window = 12, 22, 22, 8, 72, int(os.environ.get("WIN", "16"))
+C = nh * hd
+cuda = torch.device("cuda:0")
+ops = Ops(torch.bfloat16, cuda, 0)
+g = torch.Generator().manual_seed(0)
+qkv = torch.randn(B, H, W, 3 * C, generator=g).to(cuda).bfloat16()
+bias = torch.randn(3 * C, generator=g).to(cuda)
+out, lse = torch.empty(B, H, W, C, device=cuda, dtype=torch.bfloat16), torch.empty(B, H, W, nh, device=cuda)
+buf = torch.zeros(8 * 8192, dtype=torch.int64, device=cuda)
+os.environ["S2U_ATC_TIMING_BUF"] = str(buf.data_ptr())
+_lib.call("s2u_set_attn_backend", 2)
+for _ in range(3):
+    ops.attn_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, False)
+torch.cuda.synchronize()
+t = buf.view(-1, 8).cpu()
+t = t[t[:, 0] > 0].double()
+t0 = t[:, 0].min()
+print("CTAs", t.shape[0], "kernel span us", (t[:, 7].max() - t0).item() / 1e3)
+names = ["start->alloc", "pdl_wait", "->S issued(TMA)", "S mma done", "softmax", "PV done", "epilogue"]
+d = t[:, 1:] - t[:, :-1]
+for i, n in enumerate(names):
+    print(f"{n:18s} mean {d[:, i].mean().item() / 1e3:6.2f} us  max {d[:, i].max().item() / 1e3:6.2f}")
+print("CTA life mean us", ((t[:, 7] - t[:, 0]).mean() / 1e3).item())
+start = (t[:, 0] - t0) / 1e3
+print("CTA start offsets us: quantiles", [round(float(torch.quantile(start, q)), 2) for q in (0.1, 0.5, 0.62, 0.9, 1.0)])
