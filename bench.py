@@ -12,10 +12,14 @@ One JSON line on rank 0:
   value         device-resident throughput (inputs already in HBM), whole job, CUDA-event timed, max over ranks
   e2e           same metric through the public TrainStep call with HOST (pinned) batches: H2D of the batch and a
                 D2H read of the loss inside the timed region, every step
-  roofline      tcgen05 GEMM family (the dominant kernel): algorithmic FLOPs of its launches / their summed
-                CUDA-event duration in an instrumented eager step, against the measured bf16 peak
-  cpu_baseline  the oracle port (oracle/port.py, torch-CPU restatement of the reference) timed on this box's
-                host cores on a bounded sample of the same workload
+  infer         the other half of BASELINE.json's metric in the same run: inference forward img/s (device-resident and
+                end to end from pinned host batches) of the same model at the same batch
+  roofline      the dominant tcgen05 GEMM shape: algorithmic FLOPs / CUDA-event duration, both ways the recipe names -
+                launched alone back to back against the BURST bf16 peak (`achieved`, `frac`), and inside the step
+                against the SUSTAINED peak (`achieved_in_step`, `frac_in_step`)
+  cpu_baseline  N = 1 only: the reference's own modules (staged under baseline/_ref by scripts/stage_reference.py,
+                imported through oracle/ref_shim.py; kind "reference") - or the oracle port when they are absent (kind
+                "port") - timed on this box's host cores on a bounded sample (one 12-image step) of the same workload
 `--impl reference` times that CPU path alone and prints the same line shape with "impl": "reference".
 """
 from __future__ import annotations
@@ -63,7 +67,10 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=4, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="images per CPU-baseline step (0 = --batch: the same config)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: total images per step, split evenly over the ranks (0 = weak: --batch per GPU)")
+    ap.add_argument("--no-infer", action="store_true", help="skip the inference half of the line")
     ap.add_argument("--profile-out", default="", help="write the per-op CUDA-event breakdown of one eager step here")
     ap.add_argument("--ncu-range", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
@@ -121,20 +128,58 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
 
+def _reference_root():
+    """Where the unmodified reference can be imported from: the build container's checkout or the staged copy."""
+    for root in (os.environ.get("SAM2UNET_REFERENCE", ""), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if root and os.path.isfile(os.path.join(root, "SAM2UNet.py")):
+            return root
+    return None
+
+
+_VARIANT = {"sam2_hiera_l.yaml": "l", "sam2_hiera_s.yaml": "s", "sam2_hiera_t.yaml": "t", "sam2_hiera_b+.yaml": "b+",
+            "tiny_test.yaml": "test"}
+
+
 def cpu_step_fn(cfg_key: str, batch: int, size: int, mode: str):
-    """One step of the oracle port on the host cores (test infrastructure used as the reported CPU baseline)."""
+    """-> (step, kind).  One step of the reference on the host cores: its own SAM2UNet / Hiera modules, its
+    structure_loss and torch.optim.AdamW exactly as train.py:48-52,74-83 drives them (kind "reference"); when the
+    reference files are not on this box, the oracle port of the same path (kind "port")."""
     import torch
+    from sam2_unet_b200.params import fill_deterministic_
+    from sam2_unet_b200.synthetic import synthetic_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, mask = synthetic_batch(batch, size, seed=0)
+    root = _reference_root()
+    if root is not None and cfg_key != "tiny_test.yaml":
+        os.environ["SAM2UNET_REFERENCE"] = root
+        from oracle import ref_shim
+        model = ref_shim.build_reference(_VARIANT[cfg_key])
+        fill_deterministic_(model, 0)
+        loss_fn = ref_shim.reference_structure_loss()
+        optim = torch.optim.AdamW([{"params": model.parameters(), "initial_lr": 1e-3}], lr=1e-3, weight_decay=5e-4)
+
+        def step():
+            if mode == "infer":
+                model.eval()
+                with torch.no_grad():
+                    model(x)
+                return
+            model.train()
+            optim.zero_grad()                              # train.py:74-83
+            pred0, pred1, pred2 = model(x)
+            loss = loss_fn(pred0, mask) + loss_fn(pred1, mask) + loss_fn(pred2, mask)
+            loss.item()
+            loss.backward()
+            optim.step()
+        return step, "reference"
+
     from oracle import port
     from sam2_unet_b200 import SAM2UNet
-    from sam2_unet_b200.params import fill_deterministic_
-    torch.set_num_threads(os.cpu_count() or 1)
     m = SAM2UNet(model_cfg=cfg_key)                     # parameter container only (never run on the CPU)
     fill_deterministic_(m, 0)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     del m
-    trunk = port.TRUNKS[{"sam2_hiera_l.yaml": "l", "sam2_hiera_s.yaml": "s", "sam2_hiera_t.yaml": "t",
-                         "sam2_hiera_b+.yaml": "b+", "tiny_test.yaml": "test"}[cfg_key]]
-    x, mask = port.synthetic_batch(batch, size, seed=0)
+    trunk = port.TRUNKS[_VARIANT[cfg_key]]
     keys = port.trainable_keys(sd)
     mom = {k: torch.zeros_like(sd[k]) for k in keys}
     var = {k: torch.zeros_like(sd[k]) for k in keys}
@@ -153,14 +198,18 @@ def cpu_step_fn(cfg_key: str, batch: int, size: int, mode: str):
                 port.adamw_step(sd[k], grads[k], mom[k], var[k], state["t"])
         sd.update(bn.updates)
 
-    return step
+    return step, "port"
 
 
 def time_cpu(args, steps: int, warmup: int, budget_s: float):
     from sam2_unet_b200.config import canonical_name
-    step = cpu_step_fn(canonical_name(args.cfg), args.cpu_batch, args.size, args.mode)
+    batch = args.cpu_batch or args.batch
+    step, kind = cpu_step_fn(canonical_name(args.cfg), batch, args.size, args.mode)
+    t_begin = time.perf_counter()
     for _ in range(max(1, warmup)):
         step()
+        if time.perf_counter() - t_begin > budget_s / 3:  # bounded: one warm-up step is enough on a slow host
+            break
     times = []
     t_begin = time.perf_counter()
     for _ in range(steps):
@@ -170,22 +219,24 @@ def time_cpu(args, steps: int, warmup: int, budget_s: float):
         if time.perf_counter() - t_begin > budget_s:
             break
     total = sum(times)
-    return args.cpu_batch * len(times) / total, total / len(times), len(times)
+    return batch * len(times) / total, total / len(times), len(times), kind, batch
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ips, sec, done = time_cpu(args, args.steps, min(args.warmup, 1), 150.0)
+    ips, sec, done, kind, batch = time_cpu(args, args.steps, min(args.warmup, 1), 150.0)
     cores = os.cpu_count() or 1
-    sample = (f"{done} timed step(s) of {args.cpu_batch} images (of the 12-image batch), oracle port of the reference "
-              f"on torch-CPU fp32, {cores} threads")
+    what = "the reference's own modules (SAM2UNet.py, hieradet.py, train.py:structure_loss, torch.optim.AdamW)" \
+        if kind == "reference" else "oracle port of the reference"
+    sample = (f"{done} timed step(s) of {batch} images after 1 warm-up (bounded to 150 s of the requested {args.steps}), "
+              f"{what} on torch-CPU fp32, {cores} threads")
     line = {"impl": "reference", "metric": metric_name(args), "value": ips, "unit": "img/s", "n_gpus": args.gpus,
             "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "cpu_batch": args.cpu_batch},
-            "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(args), "cpu_batch": batch},
+            "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -286,24 +337,28 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 
-    from oracle import port  # synthetic inputs only (seeded discs); no oracle compute on this arm
-    from sam2_unet_b200 import SAM2UNet, TrainStep, _lib
+    from sam2_unet_b200 import Predictor, SAM2UNet, TrainStep, _lib
     from sam2_unet_b200.params import fill_deterministic_
+    from sam2_unet_b200.synthetic import synthetic_batch
 
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        ips, sec, done = time_cpu(args, 1, 1, 60.0)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:       # N = 1 only (torchrun pins OMP_NUM_THREADS=1)
+        ips, sec, done, kind, batch = time_cpu(args, 1, 1, 60.0)
         cores = os.cpu_count() or 1
-        cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-               "sample": f"{done} timed step of {args.cpu_batch} images after 1 warm-up, oracle port (torch-CPU fp32), "
-                         f"{cores} threads"}
+        cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": kind,
+               "sample": f"{done} timed step of {batch} images after 1 warm-up, "
+                         f"{'the reference modules' if kind == 'reference' else 'oracle port'} (torch-CPU fp32), {cores} threads"}
 
     torch.manual_seed(0)
     model = SAM2UNet(model_cfg=args.cfg, dtype=args.dtype)
     fill_deterministic_(model, 0)
     model = model.to(dev)
     B, S = args.batch, args.size
-    xh, mh = port.synthetic_batch(B, S, seed=100 + rank)
+    xh, mh = synthetic_batch(B, S, seed=100 + rank)
     xh, mh = xh.pin_memory(), mh.pin_memory()
     xd, md = xh.to(dev), mh.to(dev)
 
@@ -322,7 +377,6 @@ def run_b200(args):
             return loss.cpu()
         d2h = 12
     else:
-        from sam2_unet_b200 import Predictor
         model.eval()
         pred = Predictor(model, use_graph=not args.no_graph)
         run_dev = lambda: pred(xd)                              # noqa: E731
@@ -368,6 +422,26 @@ def run_b200(args):
     ms_e2e, _, _ = timed(run_e2e, args.steps, 2)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
+    # the other half of the metric: inference forward of the same model at the same batch (graph-replayed Predictor)
+    infer = None
+    if args.mode == "train" and not args.no_infer:
+        model.eval()
+        pred = Predictor(model, use_graph=not args.no_graph)
+
+        def infer_e2e():
+            out = pred(xh)[0]
+            pred.prefetch(xh)
+            return out.cpu()
+        ms_i, _, _ = timed(lambda: pred(xd), args.steps, warm + 3)
+        ms_ie, _, _ = timed(infer_e2e, args.steps, 2)
+        infer = {"metric": METRIC["infer"] if metric_name(args) == METRIC["train"] else metric_name(args).replace("train", "infer"),
+                 "value": B * world * args.steps / (ms_i / 1e3), "unit": "img/s", "ms_per_step": ms_i / args.steps,
+                 "e2e": {"value": B * world * args.steps / (ms_ie / 1e3), "unit": "img/s",
+                         "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": B * S * S * 4,
+                         "ms_per_step": ms_ie / args.steps}}
+        del pred
+        model.train()
+
     # instrumented eager step: per-op CUDA-event durations (kernel shares, roofline of the GEMM family)
     roof = None
     launches_per_step = None
@@ -406,18 +480,20 @@ def run_b200(args):
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the committed
         # `ncu --set full` capture (profiles/r1_gemm_pair_full_raw.csv); None when the shape differs from the captured one
         traffic = NCU_TRAFFIC.get((tm, tn, tk))
-        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_burst"], "traffic": traffic,
+                "frac_in_step": in_step / pk["tf_sustained"], "peak_in_step": pk["tf_sustained"],
                 "kernel": f"gemm_umma_pair_kernel (persistent CTA-pair tcgen05 + TMA GEMM), dominant shape M={tm} N={tn} K={tk}",
                 "algorithmic_flop_per_launch": tfl, "launches_of_shape_per_step": tcalls,
                 "us_per_launch": b2b_us, "variants": b2b_detail,
                 "us_per_launch_in_step": tms / tcalls * 1e3, "achieved_in_step": in_step,
                 "all_gemm_launches": ng, "all_gemm_tflops": all_tf, "gemm_ms_per_step": gms,
                 "gemm_share_of_step": gms / total_ms if total_ms else None,
-                "timing": "achieved: CUDA events around 40 back-to-back launches per epilogue variant on the launching "
-                          "stream, operands rotating through 4 buffer sets (> L2); *_in_step: CUDA events around each "
-                          "launch of one eager step (adds ~5 us idle-GPU launch latency per call)",
-                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"}
+                "timing": "achieved / frac: the kernel timed ALONE - CUDA events around 40 back-to-back launches per epilogue "
+                          "variant on the launching stream, operands rotating through 4 buffer sets (> L2) - against the "
+                          "BURST bf16 peak; achieved_in_step / frac_in_step: CUDA events around each launch of one eager "
+                          "step (adds ~5 us idle-GPU launch latency per call) against the SUSTAINED peak",
+                "peak_source": pk["source"] + ": burst figure for the isolated timing, sustained for the in-step one"}
         if args.profile_out:
             by = {}
             for name, t, _ in rec:
@@ -437,17 +513,19 @@ def run_b200(args):
                                            for k, v in sorted(gs.items(), key=lambda kv: -kv[1][1])}}, f, indent=1)
     if rank == 0:
         line = {"metric": metric_name(args), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-                "warmup": warm + 3, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.global_batch else "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
                            "cuda_graph": not args.no_graph,
+                           "untimed_steps_before_the_timed_region": warm + 3,
                            "l2": "per-step working set (activations + im2col buffers, several GB) is far larger than "
                                  "the 126 MB L2, no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": (launches_per_step or 0) * args.steps,
-                "roofline": roof, "cpu_baseline": cpu}
+                "infer": infer, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         # leave without tearing NCCL down: destroying a communicator whose collectives were captured in a live CUDA

@@ -374,8 +374,9 @@ __global__ void __launch_bounds__(NTHR_F, C1 == 16 ? 2 : 1) fwd_kernel(const __g
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float a = ex2(fmaf(__uint_as_float(r[e]), sl2, mb)), b = ex2(fmaf(__uint_as_float(r[e + 1]), sl2, mb));
-          sum += a + b;
-          pk[e >> 1] = pack2(a, b);
+          const uint32_t w = pack2(a, b);
+          pk[e >> 1] = w;
+          sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);   // the ROUNDED P: O is a convex combination
         }
       } else {
 #pragma unroll
@@ -385,8 +386,9 @@ __global__ void __launch_bounds__(NTHR_F, C1 == 16 ? 2 : 1) fwd_kernel(const __g
           if (col0 + e + 1 == it.n_real) v1 += bonus;
           const float a = col0 + e < it.n_keys ? ex2(fmaf(v0, sl2, mb)) : 0.f;
           const float b = col0 + e + 1 < it.n_keys ? ex2(fmaf(v1, sl2, mb)) : 0.f;
-          sum += a + b;
-          pk[e >> 1] = pack2(a, b);
+          const uint32_t w = pack2(a, b);
+          pk[e >> 1] = w;
+          sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
         }
       }
       tc_st16(t_row + (uint32_t)(half ? 32 * h0 + 16 * (c - h0) : 16 * c), pk);

@@ -385,6 +385,8 @@ class Engine:
         outs = self._up_fwd(rfb_out, B, S, training, tape)
         if save:
             self.tape = tape
+        if training:
+            self.model.flat.bump()       # our kernels updated the BatchNorm running statistics through raw pointers
         return outs
 
     def _side_streams(self):

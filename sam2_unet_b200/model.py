@@ -73,6 +73,8 @@ class FlatParams:
                 self.params[n] = p
                 self.offsets[n] = o
         self.buffers: Dict[str, torch.Tensor] = {n: b for n, b in model.named_buffers()}
+        self._active_params = [p for n, p in self.params.items() if self.offsets[n] < self.n_active]
+        self._float_buffers = [b for b in self.buffers.values() if b.dtype.is_floating_point]
         self._manual = 0
         # bucket boundaries for the gradient all-reduce: decoder side first, then ~8 blocks of adapters each
         self.buckets = self._buckets(named, offs)
@@ -98,7 +100,16 @@ class FlatParams:
 
     @property
     def version(self):
-        return (self.master._version, self._manual)
+        """Changes whenever a trainable parameter or a BatchNorm buffer may have changed.  The parameters alias the
+        flat master buffer through `p.data`, so an in-place update by a stock optimizer (torch.optim.AdamW, EMA,
+        `p.copy_`) bumps `p._version` but NOT `master._version`: the counter is therefore derived from the parameters
+        and buffers themselves; writes by our own kernels (raw pointers) are announced with bump()."""
+        v = self._manual + self.master._version
+        for p in self._active_params:
+            v += p._version
+        for b in self._float_buffers:
+            v += b._version
+        return v
 
     def bump(self):
         self._manual += 1

@@ -146,6 +146,7 @@ class TrainStep:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static = None
         self._warm = 0
+        self._cache = {}
         self._pre = _Prefetch()
 
     def prefetch(self, x: torch.Tensor, mask: torch.Tensor) -> None:
@@ -197,11 +198,23 @@ class TrainStep:
             # host batches (pinned or pageable) are copied to the device here: this is the H2D leg of the step
             loss = self._run(x.to(dev, non_blocking=True), mask.to(dev, non_blocking=True))
         else:
-            key = (tuple(x.shape), dev)
+            # the captured graph holds raw pointers into the flat parameter / gradient / shadow buffers: a rebuild of
+            # those (load_state_dict, .to(), .float()) must re-capture, and the optimizer moments start over
+            key = (tuple(x.shape), dev, id(model.flat), model.flat.master.data_ptr())
             if self._static is None or self._static[0] != key:
-                self._static = (key, torch.empty_like(x, device=dev), torch.empty_like(mask, device=dev), None)
-                self._graph = None
-                self._warm = 0
+                # one captured graph per batch shape (a smaller last batch of an epoch alternates with the full one)
+                if self._static is not None:
+                    self._cache[self._static[0]] = (self._static, self._graph, self._warm)
+                hit = self._cache.pop(key, None)
+                if hit is not None:
+                    self._static, self._graph, self._warm = hit
+                else:
+                    self._static = (key, torch.empty_like(x, device=dev), torch.empty_like(mask, device=dev), None)
+                    self._graph = None
+                    self._warm = 0
+                stale = [k for k in self._cache if k[2:] != key[2:]]      # graphs of a rebuilt parameter buffer
+                for k in stale:
+                    del self._cache[k]
             _, sx, sm, sl = self._static
             if not self._pre.take([x0, m0], [sx, sm]):  # prefetched by the previous iteration, else copy now
                 sx.copy_(x, non_blocking=True)
@@ -262,7 +275,7 @@ class Predictor:
         x = x.contiguous().float()
         if not self.use_graph:
             return eng.forward(x.to(dev, non_blocking=True), False, save=False)
-        key = (tuple(x.shape), dev, model.flat.version)
+        key = (tuple(x.shape), dev, id(model.flat), model.flat.master.data_ptr(), model.flat.version)
         if key != self._key:
             self._key, self._graph, self._warm = key, None, 0
             self._sx = torch.empty_like(x, device=dev)

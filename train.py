@@ -22,7 +22,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from sam2_unet_b200 import (SAM2UNet, TrainStep, cosine_lr, evaluate_dataset, evaluate_segmentation_performance,
-                            infer_tail)
+                            infer_tail, preprocess_image)
 
 
 def structure_loss(pred, mask):
@@ -79,35 +79,64 @@ class _Synthetic(torch.utils.data.Dataset):
         return self.items[i]
 
 
+class _TestFiles:
+    """The evaluation set of the reference (TestDataset, dataset.py:405-447): sorted image / ground-truth FILES, no
+    augmentation.  Every item is decoded on the host and goes through the deterministic test-time transforms on the
+    device (`preprocess_image` = dataset.py:336-407), exactly like test.py."""
+
+    def __init__(self, image_root, gt_root):
+        self.images = sorted(os.path.join(image_root, f) for f in os.listdir(image_root) if f.endswith((".jpg", ".png")))
+        self.gts = sorted(os.path.join(gt_root, f) for f in os.listdir(gt_root) if f.endswith(".png"))
+        if len(self.images) != len(self.gts):
+            raise ValueError(f"{len(self.images)} test images but {len(self.gts)} ground-truth masks")
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        import numpy as np
+        from PIL import Image
+        img = np.ascontiguousarray(np.asarray(Image.open(self.images[i]).convert("RGB")))
+        gt = np.ascontiguousarray(np.asarray(Image.open(self.gts[i]).convert("L")))
+        return torch.from_numpy(img), torch.from_numpy(gt)
+
+
 def _datasets(args):
     if args.synthetic > 0:
         ds = _Synthetic(args.synthetic, args.size)
         return ds, ds
+    test = _TestFiles(args.test_image_path, args.test_gt_path)
     try:                                             # the reference's own pipeline, unchanged, when it is on the path
         from dataset import FullDataset
-        return (FullDataset(args.train_image_path, args.train_mask_path, args.size, mode="train"),
-                FullDataset(args.test_image_path, args.test_gt_path, args.size, mode="test"))
+        return FullDataset(args.train_image_path, args.train_mask_path, args.size, mode="train"), test
     except ImportError:
-        return (_FolderData(args.train_image_path, args.train_mask_path, args.size),
-                _FolderData(args.test_image_path, args.test_gt_path, args.size))
+        return _FolderData(args.train_image_path, args.train_mask_path, args.size), test
 
 
 @torch.no_grad()
-def evaluate(model, dataset, device, batch_size):
-    """Per-epoch evaluation of the reference (train.py:90-125): forward, inference tail (sigmoid, min-max, uint8),
-    eval.py's per-image metrics and their dataset aggregation - the pixel work of all three on the device.  Returns the
-    aggregated dictionary (mIoU, mDice, Precision/Recall/F1 at IoU 0.5 and 0.75)."""
+def evaluate(model, dataset, device, size, rank=0, world=1):
+    """Per-epoch evaluation of the reference (train.py:90-125), image by image: test-time transforms, forward, padding
+    removed, bilinear resize to the ground-truth size, sigmoid, min-max, uint8, eval.py's per-image metrics - the pixel
+    work of all of it on the device.  Under DDP every rank scores its stride of the file list; -> list of per-image
+    result dictionaries of this rank (aggregate with evaluate_dataset after gathering)."""
     model.eval()
-    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
     results = []
-    for batch in loader:
-        res, _, _ = model(batch["image"].to(device))
-        gts = (batch["label"].to(device) * 255).round().clamp(0, 255).to(torch.uint8)
-        for i in range(res.shape[0]):
-            # datasets of this script are already square at the network size: no padding to remove, same size out
-            png = infer_tail(res[i:i + 1], (0, 0, 0, 0), tuple(res.shape[-2:]))
-            results.append(evaluate_segmentation_performance(png, gts[i, 0]))
-    return evaluate_dataset(results)
+    for i in range(rank, len(dataset), world):
+        item = dataset[i]
+        if isinstance(item, dict):                   # --synthetic: already at the network size, no padding
+            res, _, _ = model(item["image"][None].to(device))
+            gt = (item["label"][0].to(device) * 255).round().clamp(0, 255).to(torch.uint8)
+            png = infer_tail(res, (0, 0, 0, 0), tuple(gt.shape))
+        else:
+            img_u8, gt = item
+            x, padding = preprocess_image(img_u8.to(device), size)
+            res, _, _ = model(x)
+            gt = gt.to(device)
+            png = infer_tail(res, padding, tuple(gt.shape))           # train.py:103-112 on the device
+        results.append(evaluate_segmentation_performance(png, gt))
+        if i % 10 == 0 and rank == 0:
+            print(".", end="", flush=True)
+    return results
 
 
 def main(args):
@@ -121,11 +150,25 @@ def main(args):
     train_ds, test_ds = _datasets(args)
     sampler = torch.utils.data.distributed.DistributedSampler(train_ds, shuffle=True) if ddp else None
     loader = torch.utils.data.DataLoader(train_ds, batch_size=args.batch_size, shuffle=sampler is None, sampler=sampler,
-                                         num_workers=0 if args.synthetic else 8, drop_last=True, pin_memory=True)
-    model = SAM2UNet(checkpoint_path=args.hiera_path if os.path.exists(args.hiera_path) else "",
-                     model_cfg=args.model_cfg, dtype=args.dtype).to(device)
+                                         num_workers=0 if args.synthetic else 8, drop_last=ddp, pin_memory=True)
+    if os.path.exists(args.hiera_path):
+        hiera = args.hiera_path
+    elif args.synthetic > 0 or args.random_trunk or len(args.checkpoint) > 0:
+        hiera = ""                                   # smoke runs / full SAM2-UNet checkpoint: no pretrained trunk needed
+        if rank == 0 and not len(args.checkpoint):
+            print(f"WARNING: {args.hiera_path} not found - the frozen Hiera trunk keeps its RANDOM initialisation")
+    else:                                            # the reference fails in build_sam2 (build_sam.py:79-89): so do we
+        raise FileNotFoundError(f"--hiera_path {args.hiera_path} does not exist: the trunk is frozen, training on a random "
+                                "encoder is never what you want (pass --random_trunk to do it anyway)")
+    model = SAM2UNet(checkpoint_path=hiera, model_cfg=args.model_cfg, dtype=args.dtype).to(device)
     if len(args.checkpoint) > 0:
         model.load_state_dict(torch.load(args.checkpoint, map_location=device), strict=True)
+    if ddp:                                          # one set of initial weights / BN buffers: rank 0's
+        model._engine(device)
+        dist.broadcast(model.flat.master, 0)
+        for b in model.buffers():
+            dist.broadcast(b, 0)
+        model.flat.bump()
     step = TrainStep(model, lr=args.lr, weight_decay=args.weight_decay, use_graph=not args.no_graph)
     os.makedirs(args.save_path, exist_ok=True)
     log_path = os.path.join(args.save_path, "log.txt")
@@ -154,7 +197,14 @@ def main(args):
         if rank == 0:
             print(f"epoch {epoch + 1}: {seen / max(time.time() - t0, 1e-9):.1f} img/s/rank")
             print("Evaluating", end="")
-            final = evaluate(model, test_ds, device, args.batch_size)
+        # every rank scores its share of the test files (no rank idles in an NCCL barrier while rank 0 evaluates)
+        mine = evaluate(model, test_ds, device, args.size, rank, dist.get_world_size() if ddp else 1)
+        if ddp:
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, mine)
+            mine = [r for part in parts for r in part]
+        if rank == 0:
+            final = evaluate_dataset(mine)
             mean_iou = final.get("mIoU", 0.0)
             epoch_name = f"epoch-{epoch + 1}_loss-{epoch_loss:.3f}"
             line = f"{epoch_name}: " + ", ".join(f"{k} {v:.4f}" for k, v in final.items())
@@ -197,4 +247,5 @@ if __name__ == "__main__":
     parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     parser.add_argument("--synthetic", type=int, default=0, help="train on N seeded synthetic images (no files needed)")
+    parser.add_argument("--random_trunk", action="store_true", help="allow training without the pretrained Hiera weights")
     main(parser.parse_args())
