@@ -107,14 +107,27 @@ def mka():
 
 
 flops_f = 4.0 * B * 4 * nh * 196 * 196 * hd
-bench("attn_fwd win14 12x22x22 h8 d72", R * Cc * 8, mka,
-      lambda s: ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H, H, nh, hd, win, False))
 
 
 def mka2():
     s = mka()
-    ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H, H, nh, hd, win, False)
+    ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H, H, nh, hd, 16, False)
     return s
+
+
+for _be, _nm in ((1, "mma.sync"), (2, "tcgen05")):
+    _lib.call("s2u_set_attn_backend", _be)
+    bench(f"attn_fwd win16 12x22x22 h8 d72 [{_nm}]", R * Cc * 8, mka,
+          lambda s: ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H, H, nh, hd, 16, False))
+    bench(f"attn_bwd win16 12x22x22 h8 d72 [{_nm}]", R * Cc * 16, mka2,
+          lambda s: ops.attn_bwd(s["qkv"], s["bias"], s["o"], s["lse"], s["do"], s["dqkv"], B, H, H, nh, hd, 16, False))
+    bench(f"attn_fwd global 12x22x22 h8 d72 [{_nm}]", R * Cc * 8, mka,
+          lambda s: ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H, H, nh, hd, 0, False))
+    bench(f"attn_bwd global 12x22x22 h8 d72 [{_nm}]", R * Cc * 16, mka2,
+          lambda s: ops.attn_bwd(s["qkv"], s["bias"], s["o"], s["lse"], s["do"], s["dqkv"], B, H, H, nh, hd, 0, False))
+_lib.call("s2u_set_attn_backend", 0)
+bench("attn_fwd win14 12x22x22 h8 d72", R * Cc * 8, mka,
+      lambda s: ops.attn_fwd(s["qkv"], s["bias"], s["o"], s["lse"], B, H, H, nh, hd, win, False))
 
 
 bench("attn_bwd win14 12x22x22 h8 d72", R * Cc * 16, mka2,
@@ -145,6 +158,34 @@ bench("attn_fwd win16 12x32x32 h8 d72 (full tiles)", R2 * Cc * 8, mkb_,
 bench("attn_bwd win16 12x32x32 h8 d72 (full tiles)", R2 * Cc * 16, mkb2_,
       lambda s: ops.attn_bwd(s["qkv"], s["bias"], s["o"], s["lse"], s["do"], s["dqkv"], B, H2, H2, nh, hd, 16, False))
 print(f"(win16 fwd FLOPs: {4.0 * B * 4 * nh * 256 * 256 * hd / 1e9:.2f} GFLOP)")
+
+
+# structure_loss forward + backward, three heads sharing one mask (train.py:21-29,76-79): algorithmic bytes =
+# forward: 3 logit maps + mask read, weit written (20 B/pixel); backward: 3 logits + mask + weit read, 3 gradients
+# written (32 B/pixel)
+for (Bl, Sl) in [(12, 352), (4, 1024)]:
+    npx = Bl * Sl * Sl
+
+    def mkl():
+        return dict(p=[r(Bl, 1, Sl, Sl, dt=f32) for _ in range(3)], m=(torch.rand(Bl, 1, Sl, Sl, device=dev) > 0.7).float(),
+                    w=torch.empty(Bl, Sl, Sl, device=dev), sums=torch.zeros(3 * Bl * 2 + 3, device=dev, dtype=torch.float64),
+                    loss=torch.empty(3, device=dev), g=[torch.empty(Bl, 1, Sl, Sl, device=dev) for _ in range(3)])
+
+    def lfwd(s):
+        _lib.call("s2u_structure_loss_fwd", s["p"][0].data_ptr(), s["p"][1].data_ptr(), s["p"][2].data_ptr(), s["m"].data_ptr(),
+                  s["w"].data_ptr(), s["sums"].data_ptr(), s["loss"].data_ptr(), Bl, Sl, Sl, 3, ops.stream)
+
+    def lbwd(s):
+        _lib.call("s2u_structure_loss_bwd", s["p"][0].data_ptr(), s["p"][1].data_ptr(), s["p"][2].data_ptr(), s["m"].data_ptr(),
+                  s["w"].data_ptr(), s["sums"].data_ptr(), 0, s["g"][0].data_ptr(), s["g"][1].data_ptr(), s["g"][2].data_ptr(),
+                  Bl, Sl, Sl, 3, ops.stream)
+
+    def mkl2():
+        s = mkl()
+        lfwd(s)
+        return s
+    bench(f"structure_loss fwd 3 heads {Bl}x{Sl}x{Sl} (+memset, finalize)", npx * 20, mkl, lfwd)
+    bench(f"structure_loss bwd 3 heads {Bl}x{Sl}x{Sl}", npx * 32, mkl2, lbwd)
 
 for (M, P) in [(5808, 576), (5808, 32)]:
     def mkc():

@@ -477,7 +477,7 @@ def test_resample_and_heads(cuda, dtype):
 
 # ------------------------------------------------------------------------------------------ loss / optimizer
 
-@pytest.mark.parametrize("shape", [(2, 96), (3, 352), (1, 64)])
+@pytest.mark.parametrize("shape", [(2, 96), (3, 352), (1, 64), (2, 50), (1, 130), (1, 132)])
 def test_structure_loss(cuda, shape):
     from oracle import port
     from sam2_unet_b200.loss import structure_loss, structure_loss3
