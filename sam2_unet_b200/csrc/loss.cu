@@ -83,12 +83,15 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(LossPtrs p, const float* 
 
 // ---- vectorised path (W % 4 == 0: every row starts 16-byte aligned) ------------------------------------------------
 // Forward: one CTA = 16 rows x 128 columns.  The 31x31 box sum is separable AND sliding: a thread starts a 31-tap sum
-// once and then slides it (one add, one subtract per pixel), horizontally over a 16-pixel run of a halo row and
-// vertically over an 8-pixel run of a column: ~4 shared-memory adds per pixel instead of 62.  The last phase is a pure
-// row-major stream: float4 loads of the (up to) three logit maps, float4 store of weit, one exp2 / rcp / log2 per head
-// and pixel (sigmoid and softplus share exp(-|p|)), per-image sums by warp shuffles and one fp64 atomic per CTA.
+// once and then slides it (one add, one subtract per pixel) - first vertically (lanes = consecutive columns), then
+// horizontally over 16-pixel runs with lanes = rows of an array whose pitch is 1 (mod 32), so both passes are free of
+// bank conflicts: ~5 shared-memory adds per pixel instead of 62.  The last phase is a pure row-major stream: float4
+// loads of the (up to) three logit maps, float4 store of weit, one exp / rcp / log per head and pixel (sigmoid and
+// softplus share exp(-|p|)), per-image sums by warp shuffles and one fp64 atomic per CTA and quantity.
 constexpr int VT_H = 16, VT_W = 128, VHALO_H = VT_H + 2 * LR, VHALO_W = VT_W + 2 * LR;
-constexpr int VPITCH = VHALO_W + 2;                                  // 160 floats: rows stay 16-byte aligned
+constexpr int VPITCH = VHALO_W + 2;                                  // 160 floats: halo rows stay 16-byte aligned
+constexpr int VS_PITCH = 161, BX_PITCH = 129;                        // 1 (mod 32): lanes = rows hit distinct banks
+constexpr size_t VEC_SMEM = sizeof(float) * (VHALO_H * VPITCH + VT_H * VS_PITCH + VT_H * BX_PITCH);
 
 __device__ __forceinline__ void sig_softplus(float pv, float& sg, float& sp) {
   // e = exp(-|p|): sigmoid(p) = p >= 0 ? 1/(1+e) : e/(1+e); softplus(-|p|) = log(1+e)
@@ -102,54 +105,49 @@ __global__ void __launch_bounds__(256) loss_fwd_vec_kernel(LossPtrs p, const flo
                                                           float* __restrict__ weit, double* __restrict__ sums, int B,
                                                           int H, int W, int nheads) {
   pdl_sync();
-  extern __shared__ __align__(16) uint8_t vsm[];            // 61 KB: opted in by the launcher
-  float (*tile)[VPITCH] = reinterpret_cast<float (*)[VPITCH]>(vsm);                                   // mask + 15-pixel halo
-  float (*hsum)[VT_W] = reinterpret_cast<float (*)[VT_W]>(vsm + sizeof(float) * VHALO_H * VPITCH);     // horizontal sums
-  float (*box)[VT_W] = reinterpret_cast<float (*)[VT_W]>(vsm + sizeof(float) * VHALO_H * (VPITCH + VT_W));   // 31x31 sums
+  extern __shared__ __align__(16) uint8_t vsm[];            // 48 KB: opted in by the launcher
+  float (*tile)[VPITCH] = reinterpret_cast<float (*)[VPITCH]>(vsm);                        // mask + 15-pixel halo
+  float* vsum = reinterpret_cast<float*>(vsm) + VHALO_H * VPITCH;                          // [16][VS_PITCH] column sums
+  float* box = vsum + VT_H * VS_PITCH;                                                     // [16][BX_PITCH] 31x31 sums
   __shared__ float red[8][MAXH * 3];
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * VT_H, x0 = blockIdx.x * VT_W;
   const float* mb = mask + (long long)b * H * W;
-  // halo tile: columns x0-15 .. x0+142 in 4-pixel groups starting at x0-16 (16-byte aligned since x0 % 4 == 0)
+  // halo tile: tile column c = image column x0 - 16 + c, in 4-pixel groups (16-byte aligned since x0 % 4 == 0)
   for (int i = threadIdx.x; i < VHALO_H * (VPITCH / 4); i += 256) {
     const int ty = i / (VPITCH / 4), g = i - ty * (VPITCH / 4);
     const int y = y0 + ty - LR, x = x0 - 16 + 4 * g;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = *reinterpret_cast<const float4*>(mb + (long long)y * W + x);
-    else if (y >= 0 && y < H) {
-      if (x >= 0 && x < W) v.x = mb[(long long)y * W + x];
-      if (x + 1 >= 0 && x + 1 < W) v.y = mb[(long long)y * W + x + 1];
-      if (x + 2 >= 0 && x + 2 < W) v.z = mb[(long long)y * W + x + 2];
-      if (x + 3 >= 0 && x + 3 < W) v.w = mb[(long long)y * W + x + 3];
-    }
-    // tile column c holds image column x0 - 16 + c: the window of output column tx is tile[.][tx + 1 .. tx + 31]
-    *reinterpret_cast<float4*>(&tile[ty][4 * g]) = v;
+    if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = __ldg(reinterpret_cast<const float4*>(mb + (long long)y * W + x));
+    *reinterpret_cast<float4*>(&tile[ty][4 * g]) = v;       // W % 4 == 0 and x % 4 == 0: a group is all in or all out
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < VHALO_H * (VT_W / 16); i += 256) {     // (halo row, 16-column run)
-    const int ty = i / (VT_W / 16), tx0 = (i - ty * (VT_W / 16)) * 16;
-    const float* r = &tile[ty][tx0 + 1];
+  // vertical 31-tap sums of every halo column for the 16 output rows: (column, 8-row run), lanes = consecutive columns
+  for (int i = threadIdx.x; i < VPITCH * 2; i += 256) {
+    const int c = i % VPITCH, r0 = (i / VPITCH) * 8;
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k <= 2 * LR; ++k) s += r[k];
-    hsum[ty][tx0] = s;
-#pragma unroll
-    for (int j = 1; j < 16; ++j) {
-      s += r[j + 2 * LR] - r[j - 1];
-      hsum[ty][tx0 + j] = s;
-    }
-  }
-  __syncthreads();
-  {                                                                     // (column, 8-row run): 128 x 2 = 256 threads
-    const int tx = threadIdx.x & (VT_W - 1), ty0 = (threadIdx.x >> 7) * 8;
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k <= 2 * LR; ++k) s += hsum[ty0 + k][tx];
-    box[ty0][tx] = s;
+    for (int k = 0; k <= 2 * LR; ++k) s += tile[r0 + k][c];
+    vsum[r0 * VS_PITCH + c] = s;
 #pragma unroll
     for (int j = 1; j < 8; ++j) {
-      s += hsum[ty0 + j + 2 * LR][tx] - hsum[ty0 + j - 1][tx];
-      box[ty0 + j][tx] = s;
+      s += tile[r0 + j + 2 * LR][c] - tile[r0 + j - 1][c];
+      vsum[(r0 + j) * VS_PITCH + c] = s;
+    }
+  }
+  __syncthreads();
+  // horizontal 31-tap sums: (row, 16-column run); a warp = 16 rows x 2 adjacent runs -> banks r + 16 * run + k, distinct
+  if (threadIdx.x < VT_H * (VT_W / 16)) {
+    const int r = threadIdx.x & 15, tx0 = (threadIdx.x >> 4) * 16;
+    const float* v = vsum + r * VS_PITCH + tx0 + 1;         // window of output column tx: tile columns tx + 1 .. tx + 31
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k <= 2 * LR; ++k) s += v[k];
+    box[r * BX_PITCH + tx0] = s;
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+      s += v[j + 2 * LR] - v[j - 1];
+      box[r * BX_PITCH + tx0 + j] = s;
     }
   }
   __syncthreads();
@@ -162,12 +160,11 @@ __global__ void __launch_bounds__(256) loss_fwd_vec_kernel(LossPtrs p, const flo
     const int ty = i / (VT_W / 4), tx = (i - ty * (VT_W / 4)) * 4;
     const int y = y0 + ty, x = x0 + tx;
     if (y >= H || x >= W) continue;                                    // W % 4 == 0: a group is all in or all out
-    const float4 s4 = *reinterpret_cast<const float4*>(&box[ty][tx]);
     const float4 m4 = *reinterpret_cast<const float4*>(&tile[ty + LR][tx + 16]);
-    const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
+    const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
     float wv[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) wv[e] = 1.f + 5.f * fabsf(sv[e] * (1.f / 961.f) - mv[e]);
+    for (int e = 0; e < 4; ++e) wv[e] = 1.f + 5.f * fabsf(box[ty * BX_PITCH + tx + e] * (1.f / 961.f) - mv[e]);
     const long long o = ((long long)b * H + y) * W + x;
     *reinterpret_cast<float4*>(weit + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
 #pragma unroll
@@ -321,7 +318,7 @@ int s2u_structure_loss_fwd(const float* pred0, const float* pred1, const float* 
                                     (uintptr_t)weit) % 16 == 0);
   if (vec) {
     dim3 grid(ceil_div(W, VT_W), ceil_div(H, VT_H), B);
-    constexpr size_t smem = sizeof(float) * (VHALO_H * (VPITCH + VT_W) + VT_H * VT_W);
+    constexpr size_t smem = VEC_SMEM;
     S2U_ALLOW_SMEM(loss_fwd_vec_kernel);
     S2U_LAUNCH((loss_fwd_vec_kernel), grid, 256, smem, st, p, mask, weit, sums, B, H, W, nheads);
   } else {
