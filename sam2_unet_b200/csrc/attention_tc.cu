@@ -50,6 +50,7 @@ struct TcClass {
   int qbh, n_qt;           // window rows per query tile, query tiles per window
   int item0, n_items;      // work items (window, query tile) of the class: [item0, item0 + n_items)
   int n_kb, kitem0;        // backward: 128-key blocks per window, first (window, key block) work item of the class
+  int witem0;              // fused backward: first window index of the class
 };
 
 struct TcParams {
@@ -222,8 +223,8 @@ __global__ void __launch_bounds__(NTHR_F, C1 == 16 ? 2 : 1) fwd_kernel(const __g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
   const int row = quarter * 32 + lane;
-  const int head = blockIdx.y;
-  const Item it = decode_item<STREAM>(p, blockIdx.x);
+  const int head = blockIdx.x;                               // fast dimension: the heavy (full-window) items of ALL heads first
+  const Item it = decode_item<STREAM>(p, blockIdx.y);
   const TcClass& cl = p.cls[it.c];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
@@ -456,6 +457,53 @@ __global__ void __launch_bounds__(NTHR_F, C1 == 16 ? 2 : 1) fwd_kernel(const __g
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
+
+// D = sum_d dO[d] * O[d] of one query row (hd <= 64 + C1 bf16 values each): every 16-byte load is issued before the
+// first use - with a runtime trip count the loads serialise behind the FMA chain (~0.5 us of L2 latency each)
+template <int C1>
+__device__ __forceinline__ float row_dot(const bf16* __restrict__ a, const bf16* __restrict__ b, int hd) {
+  constexpr int NCH = (64 + C1) / 8;
+  uint4 ua[NCH], ub[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    ua[c] = make_uint4(0, 0, 0, 0);
+    ub[c] = make_uint4(0, 0, 0, 0);
+    if (c * 8 < hd) {
+      ua[c] = __ldg(reinterpret_cast<const uint4*>(a) + c);
+      ub[c] = __ldg(reinterpret_cast<const uint4*>(b) + c);
+    }
+  }
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua[c]);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub[c]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+      d0 = fmaf(fa.x, fb.x, d0);
+      d1 = fmaf(fa.y, fb.y, d1);
+    }
+  }
+  return d0 + d1;
+}
+
+// rows of <= 64 + C1 head-dim values, one thread per row in shared memory (pitch 16 * NCH bytes), written out with
+// CONSECUTIVE lanes on consecutive 16-byte chunks: a thread-per-row global store touches 32 cache lines per
+// instruction (~1.2 us per [128 x 72] tile), this one ~4.  off[r] = element offset of row r's destination, < 0: skip
+template <int C1>
+__device__ __forceinline__ void copy_rows_out(const uint8_t* stage, const long long* off, bf16* __restrict__ dst,
+                                              int hd, int t, int nthreads) {
+  constexpr int NCH = (64 + C1) / 8;
+  const int live = hd / 8;
+  for (int f = t; f < 128 * live; f += nthreads) {
+    const int r = f / live, c = f - r * live;
+    const long long o = off[r];
+    if (o >= 0)
+      *reinterpret_cast<uint4*>(dst + o + c * 8) = *reinterpret_cast<const uint4*>(stage + r * (NCH * 16) + c * 16);
+  }
+}
+
 template <int C1>
 struct SmemDq {
   static constexpr int C1B = C1 * 2;
@@ -480,8 +528,8 @@ __global__ void __launch_bounds__(NTHR, C1 == 16 ? 2 : 1) bwd_dq_kernel(const __
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int head = blockIdx.y;
-  const Item it = decode_item<STREAM>(p, blockIdx.x);
+  const int head = blockIdx.x;                               // fast dimension: the heavy (full-window) items of ALL heads first
+  const Item it = decode_item<STREAM>(p, blockIdx.y);
   const TcClass& cl = p.cls[it.c];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
@@ -534,18 +582,7 @@ __global__ void __launch_bounds__(NTHR, C1 == 16 ? 2 : 1) bwd_dq_kernel(const __
   float Lrow = INFINITY, Drow = 0.f;
   if (live) {
     Lrow = p.lse[tok * p.nh + head] * 1.4426950408889634f;
-    const uint4* a = reinterpret_cast<const uint4*>(p.dout + tok * C + head * p.hd);
-    const uint4* b = reinterpret_cast<const uint4*>(p.o_in + tok * C + head * p.hd);
-    for (int c = 0; c < p.hd / 8; ++c) {
-      const uint4 ua = a[c], ub = b[c];
-      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
-      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
-        Drow = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, Drow));
-      }
-    }
+    Drow = row_dot<C1>(p.dout + tok * C + head * p.hd, p.o_in + tok * C + head * p.hd, p.hd);
     p.dws[tok * p.nh + head] = Drow;
   }
   const float sl2 = p.scale * 1.4426950408889634f;
@@ -699,14 +736,14 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int head = blockIdx.y;
+  const int head = blockIdx.x;
   // work item -> (class, window, key block)
   int c = 0;
 #pragma unroll
   for (int i = 1; i < MAXCLS; ++i)
-    if (i < p.n_cls && (int)blockIdx.x >= p.cls[i].kitem0) c = i;
+    if (i < p.n_cls && (int)blockIdx.y >= p.cls[i].kitem0) c = i;
   const TcClass& cl = p.cls[c];
-  const int local = blockIdx.x - cl.kitem0;
+  const int local = blockIdx.y - cl.kitem0;
   const int jb = local % cl.n_kb;
   // decode_item on the window's first query tile gives the window coordinates
   const Item it = decode_item<STREAM>(p, cl.item0 + (local / cl.n_kb) * cl.n_qt);
@@ -921,6 +958,331 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_dkv_kernel(const __grid_consta
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fused backward for windows (<= 256 tokens, head dim <= 80): ONE CTA = (window, head) computes dQ, dK and dV, so the
+// scores are recomputed once (the two-kernel path above recomputes them in each kernel) and no D workspace travels
+// through HBM.  All eight operand tiles of the window (Q, dO per query tile; K, V per key block) are TMA-loaded once.
+// Keys sit on the TMEM lanes.  Per (key block j, query tile i):
+//   S^T = K_j Q_i^T, dP^T = V_j dO_i^T                     two accumulators, 256 TMEM columns
+//   P^T, dS^T (bf16) over them (tcgen05.st), and dS^T also into a 128-byte-swizzled shared-memory tile [key][query]
+//   dV_j += P^T dO_i,  dK_j += dS^T Q_i                    A from tensor memory, accumulated in TMEM over i
+//   dQ_i part = dS K_j                                     A = the shared dS^T tile read MN-major (M = queries), B = K_j
+//                                                          read MN-major; the [128 x hd'] result is added to fp32
+//                                                          registers (queries on lanes), accumulated over j
+// TMEM: 128 + 128 + 3 x (64 + C1) = 496 columns; shared memory: 8 tiles + dS^T tile = 195 KB; 256 threads.
+template <int C1>
+struct SmemWin {
+  static constexpr int C1B = C1 * 2;
+  static constexpr int T0 = 128 * 128, T1 = ((128 * C1B) + 1023) / 1024 * 1024, TILE = T0 + T1;
+  static constexpr int Q = 0, DO = 2 * TILE, K = 4 * TILE, V = 6 * TILE;     // [2 tiles or blocks][chunk 0 | remainder]
+  static constexpr int DS = 8 * TILE;                                        // dS^T: two [128 x 64] chunks
+  static constexpr int LD = DS + 2 * T0;                                     // [2 tiles][lse*log2e (128) | D (128)]
+  static constexpr int BYTES = LD + 2 * 256 * 4 + 1024;
+};
+
+template <int C1>
+__global__ void __launch_bounds__(NTHR_KV, 1) bwd_win_kernel(const __grid_constant__ TcParams p) {
+  using sm = SmemWin<C1>;
+  using s1 = Smem<C1>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[6];
+  __shared__ uint32_t tmem_holder;
+  __shared__ long long offs[2][128];                         // destination rows of the staged stores
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;
+  const int head = blockIdx.x;
+  int c = 0;
+#pragma unroll
+  for (int i = 1; i < MAXCLS; ++i)
+    if (i < p.n_cls && (int)blockIdx.y >= p.cls[i].witem0) c = i;
+  const TcClass& cl = p.cls[c];
+  const Item it = decode_item<false>(p, cl.item0 + ((int)blockIdx.y - cl.witem0) * cl.n_qt);
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_q[2] = {bar0, bar0 + 8}, bar_k[2] = {bar0 + 16, bar0 + 24}, bar_s = bar0 + 32, bar_d = bar0 + 40;
+  float* LDs = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + sm::LD);
+  const int n_qt = cl.n_qt;                                  // <= 2 query tiles = key blocks
+  const int C = p.nh * p.hd;
+  const int box_rows = cl.qbh * cl.rw;
+  const uint32_t tile_bytes = (uint32_t)box_rows * (128 + s1::C1B);
+  auto tile0 = [&](int what, int i) { return base + (uint32_t)(what + i * sm::TILE); };
+  auto tile1 = [&](int what, int i) { return base + (uint32_t)(what + i * sm::TILE + sm::T0); };
+  auto q_rows_of = [&](int i) { return min(cl.qbh, cl.rh - i * cl.qbh) * cl.rw; };
+  ATC_STAMP(0);
+
+  pdl_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8u * i, 1);
+      mbar_init(bar_s, 2);                                   // one commit per MMA-issuing thread, see below
+      mbar_init(bar_d, 3);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      pdl_wait();
+      for (int i = 0; i < n_qt; ++i) {                       // tile i of the queries == block i of the keys (same boxes)
+        const int y = it.yk0 + i * cl.qbh;
+        mbar_expect_tx(bar_k[i], 2 * tile_bytes);
+        tma_load_5d(tile0(sm::K, i), &p.q0[c], bar_k[i], 0, p.nh + head, it.x0, y, it.b);
+        if (C1) tma_load_5d(tile1(sm::K, i), &p.q1[c], bar_k[i], 64, p.nh + head, it.x0, y, it.b);
+        tma_load_5d(tile0(sm::V, i), &p.q0[c], bar_k[i], 0, 2 * p.nh + head, it.x0, y, it.b);
+        if (C1) tma_load_5d(tile1(sm::V, i), &p.q1[c], bar_k[i], 64, 2 * p.nh + head, it.x0, y, it.b);
+        mbar_expect_tx(bar_q[i], 2 * tile_bytes);
+        tma_load_5d(tile0(sm::Q, i), &p.q0[c], bar_q[i], 0, head, it.x0, y, it.b);
+        if (C1) tma_load_5d(tile1(sm::Q, i), &p.q1[c], bar_q[i], 64, head, it.x0, y, it.b);
+        tma_load_5d(tile0(sm::DO, i), &p.o0[c], bar_q[i], 0, head, it.x0, y, it.b);
+        if (C1) tma_load_5d(tile1(sm::DO, i), &p.o1[c], bar_q[i], 64, head, it.x0, y, it.b);
+      }
+    }
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // query rows the TMA boxes never write but the (rounded-up) dV / dK products read as their K dimension: zero
+  {
+    constexpr int NCH = 8 + C1 / 8;
+    const int rows = min(128, (box_rows + 15) & ~15) - box_rows;
+    for (int e = tid; e < rows * NCH * 4; e += NTHR_KV) {
+      const int which = e & 3;                               // Q tile 0/1, dO tile 0/1
+      const int rc = e >> 2;
+      const int r = box_rows + rc / NCH, c16 = rc % NCH;
+      const int what = (which & 2) ? sm::DO : sm::Q;
+      sts16(c16 < 8 ? tile0_addr(tile0(what, which & 1), r, c16) : tile1_addr<C1>(tile1(what, which & 1), r, c16 - 8),
+            make_uint4(0, 0, 0, 0));
+    }
+  }
+  pdl_wait();
+  // lse and D = sum_d dO * O of the window's queries: thread t owns query (t / 128, t % 128)
+  {
+    const int i = tid >> 7, r = tid & 127;
+    float L = INFINITY, D = 0.f;
+    if (i < n_qt && r < q_rows_of(i)) {
+      const int ry = r / cl.rw, rx = r - ry * cl.rw;
+      const long long tk = ((long long)it.b * p.H + it.yk0 + i * cl.qbh + ry) * p.W + it.x0 + rx;
+      L = p.lse[tk * p.nh + head] * 1.4426950408889634f;
+      D = row_dot<C1>(p.dout + tk * C + head * p.hd, p.o_in + tk * C + head * p.hd, p.hd);
+    }
+    LDs[i * 256 + r] = L;
+    LDs[i * 256 + 128 + r] = D;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  ATC_STAMP(1);
+  const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t tK = tmem + 256, tV = tmem + 256 + 64 + C1, tQ = tmem + 256 + 2 * (64 + C1);
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const float bonus = it.n_pad > 0 ? __logf((float)it.n_pad) / p.scale : 0.f;
+  constexpr int NACC = 48;                                   // dQ row: column half 0 keeps d [0,48), half 1 [48, 64 + C1)
+  const int a_beg = half ? 3 : 0, a_end = half ? (64 + C1) / 16 : 3;
+  float acc[2][NACC];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int e = 0; e < NACC; ++e) acc[i][e] = 0.f;
+  const uint32_t ds_base = base + sm::DS;
+  uint32_t step = 0;
+
+  for (int j = 0; j < n_qt; ++j) {
+    const KeyBlock kb = key_block<false>(p, cl, it, j);
+    if (kb.real_here < kb.n_mma) {
+      // rows beyond the real keys of this block: pad key (k = v = bias) / zeros, after the TMA box (which may cover them)
+      mbar_wait(bar_k[j], 0);
+      write_tail_rows<C1>(tile0(sm::K, j), tile1(sm::K, j), tile0(sm::V, j), tile1(sm::V, j), p, head, kb.real_here, kb.n_mma,
+                          kb.keys_here > kb.real_here ? kb.real_here : -1);
+      fence_proxy_async();
+      __syncthreads();
+    }
+    const bool key_live = row < kb.keys_here;                // this thread's key takes part in the softmax
+    const float row_bonus = (kb.keys_here > kb.real_here && row == kb.real_here) ? bonus : 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i >= n_qt) break;
+      const int q_rows = q_rows_of(i);
+      const int nq_mma = max(16, (q_rows + 15) & ~15);
+      if (tid == 0 || tid == 32) {
+        // the tensor core is driven by several threads (one per product): a single thread issues a tcgen05.mma
+        // every ~35 ns, which made the 48 instructions of a step the longest part of it
+        mbar_wait(bar_k[j], 0);
+        mbar_wait(bar_q[i], 0);
+        tc_fence_after();
+        const uint32_t id = idesc_n(nq_mma, false);
+        const int a_what = tid == 0 ? sm::K : sm::V, b_what = tid == 0 ? sm::Q : sm::DO;
+        const uint32_t td = tmem + (tid == 0 ? 0u : 128u);
+        const uint64_t da0 = smem_desc_sw128(tile0(a_what, j)), db0 = smem_desc_sw128(tile0(b_what, i));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(td, da0 + 2 * k, db0 + 2 * k, id, k > 0 ? 1u : 0u);
+        if (C1) {
+          const uint64_t da1 = smem_desc(tile1(a_what, j), 16, s1::SBO1, s1::LAYOUT1), db1 = smem_desc(tile1(b_what, i), 16, s1::SBO1, s1::LAYOUT1);
+#pragma unroll
+          for (int k = 0; k < C1 / 16; ++k) tc_mma_bf16(td, da1 + 2 * k, db1 + 2 * k, id, 1u);
+        }
+        tc_commit(bar_s);
+      }
+      __syncwarp();
+      mbar_wait(bar_s, step & 1u);
+      tc_fence_after();
+      const float* Ls = LDs + i * 256;
+      const float* Ds = Ls + 128;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = half * 64 + cc * 32;
+        if (col0 >= nq_mma) break;
+        uint32_t s[32], d[32], pp[16], pd[16];
+        tc_ld32(t_row + (uint32_t)col0, s);
+        tc_ld32(t_row + 128u + (uint32_t)col0, d);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float2 L2 = *reinterpret_cast<const float2*>(Ls + col0 + e);
+          const float2 D2 = *reinterpret_cast<const float2*>(Ds + col0 + e);
+          float p0 = ex2(fmaf(__uint_as_float(s[e]) + row_bonus, sl2, -L2.x));
+          float p1 = ex2(fmaf(__uint_as_float(s[e + 1]) + row_bonus, sl2, -L2.y));
+          float g0 = p0 * (__uint_as_float(d[e]) - D2.x) * p.scale, g1 = p1 * (__uint_as_float(d[e + 1]) - D2.y) * p.scale;
+          if (!key_live || col0 + e >= q_rows) { p0 = 0.f; g0 = 0.f; }
+          if (!key_live || col0 + e + 1 >= q_rows) { p1 = 0.f; g1 = 0.f; }
+          pp[e >> 1] = pack2(p0, p1);
+          pd[e >> 1] = pack2(g0, g1);
+        }
+        // packed pairs inside this warp's own (already read) column range, see bwd_dkv_kernel
+        tc_st16(t_row + (uint32_t)(half * 64 + cc * 16), pp);
+        tc_st16(t_row + 128u + (uint32_t)(half * 64 + cc * 16), pd);
+        // dS^T row of this key, queries col0 .. col0 + 31, into the [key][query] tile (A operand of the dQ product)
+        const uint32_t chunk = ds_base + (uint32_t)((col0 >> 6) * sm::T0);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          sts16(tile0_addr(chunk, row, ((col0 & 63) >> 3) + m), make_uint4(pd[4 * m], pd[4 * m + 1], pd[4 * m + 2], pd[4 * m + 3]));
+      }
+      tc_wait_st();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0 || tid == 32) {
+        // dV_j += P^T dO_i (thread 0), dK_j += dS^T Q_i (thread 32): A from tensor memory
+        tc_fence_after();
+        const int b_what = tid == 0 ? sm::DO : sm::Q;
+        const uint32_t td = tid == 0 ? tV : tK, ta = tmem + (tid == 0 ? 0u : 128u);
+        const uint64_t b0 = smem_desc(tile0(b_what, i), 1024, 1024, 2), b1 = smem_desc(tile1(b_what, i), s1::SBO1, s1::SBO1, s1::LAYOUT1);
+        const uint32_t id0 = idesc_n(64, true), id1 = idesc_n(C1 ? C1 : 16, true);
+        for (int ks = 0; ks < nq_mma / 16; ++ks) {
+          const uint32_t accf = (i > 0 || ks > 0) ? 1u : 0u;
+          const uint32_t acol = (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8);
+          tc_mma_bf16_ts(td, ta + acol, b0 + (uint64_t)(ks * (2048 >> 4)), id0, accf);
+          if (C1) tc_mma_bf16_ts(td + 64, ta + acol, b1 + (uint64_t)(ks * ((16 * s1::C1B) >> 4)), id1, accf);
+        }
+        tc_commit(bar_d);
+      } else if (tid == 64) {
+        // dQ_i part = dS K_j: both operands MN-major (A: queries contiguous in the dS^T tile, B: head dim contiguous)
+        tc_fence_after();
+        const uint64_t bk0 = smem_desc(tile0(sm::K, j), 1024, 1024, 2), bk1 = smem_desc(tile1(sm::K, j), s1::SBO1, s1::SBO1, s1::LAYOUT1);
+        const uint32_t iq0 = idesc_n(64, true) | (1u << 15), iq1 = idesc_n(C1 ? C1 : 16, true) | (1u << 15);
+        for (int ks = 0; ks < kb.n_mma / 16; ++ks) {
+          const uint64_t a = smem_desc(ds_base + (uint32_t)(ks * 2048), sm::T0, 1024, 2);
+          tc_mma_bf16(tQ, a, bk0 + (uint64_t)(ks * (2048 >> 4)), iq0, ks > 0 ? 1u : 0u);
+          if (C1) tc_mma_bf16(tQ + 64, a, bk1 + (uint64_t)(ks * ((16 * s1::C1B) >> 4)), iq1, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_d);
+      }
+      __syncwarp();
+      mbar_wait(bar_d, step & 1u);
+      tc_fence_after();
+      ++step;
+      // dQ part: queries on the lanes now
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        if (a_beg + cc < a_end) {
+          uint32_t r[16];
+          tc_ld16(t_row + 256u + 2 * (64 + C1) + (uint32_t)((a_beg + cc) * 16), r);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[i][cc * 16 + e] += __uint_as_float(r[e]);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();                                       // the next step overwrites S^T / dP^T, the dS^T tile and dQ part
+      tc_fence_after();
+      if (step == 1) ATC_STAMP(2);
+      if (step == 2) ATC_STAMP(3);
+      if (step == 3) ATC_STAMP(5);
+      if (step == 4) ATC_STAMP(6);
+    }
+    // dK_j (column half 0) and dV_j (half 1) are complete: rows = keys.  Their tiles K_j / V_j are dead now and stage
+    // the bf16 rows for a coalesced copy-out
+    {
+      constexpr int RB = (64 + C1) / 8 * 16;                 // bytes per staged row
+      uint8_t* stage = smem_raw + (base - smem_u32(smem_raw)) + (half ? sm::V : sm::K) + j * sm::TILE;
+      const uint32_t t_src = t_row + (half ? (256u + 64u + C1) : 256u);
+#pragma unroll
+      for (int cc = 0; cc < (64 + C1) / 16; ++cc) {
+        uint32_t r[16];
+        tc_ld16(t_src + (uint32_t)(cc * 16), r);
+        tc_wait_ld();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 u;
+          u.x = pack2(__uint_as_float(r[h * 8 + 0]), __uint_as_float(r[h * 8 + 1]));
+          u.y = pack2(__uint_as_float(r[h * 8 + 2]), __uint_as_float(r[h * 8 + 3]));
+          u.z = pack2(__uint_as_float(r[h * 8 + 4]), __uint_as_float(r[h * 8 + 5]));
+          u.w = pack2(__uint_as_float(r[h * 8 + 6]), __uint_as_float(r[h * 8 + 7]));
+          *reinterpret_cast<uint4*>(stage + row * RB + cc * 32 + h * 16) = u;
+        }
+      }
+      if (half == 0) {
+        long long o = -1;
+        if (row < kb.real_here) {
+          const int kidx = kb.key0 + row;
+          const int ky = kidx / cl.rw, kx = kidx - ky * cl.rw;
+          o = (((long long)it.b * p.H + it.yk0 + ky) * p.W + it.x0 + kx) * (3LL * C);
+        }
+        offs[0][row] = o;
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      copy_rows_out<C1>(stage, offs[0], p.dqkv + (half ? 2 : 1) * C + head * p.hd, p.hd, tid & 127, 128);
+      __syncthreads();                                       // offs / the next key block's accumulators
+    }
+  }
+  // dQ: thread = (query row, column half) of both query tiles -> staged in the (dead) Q tiles, copied out coalesced
+  {
+    constexpr int RB = (64 + C1) / 8 * 16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i >= n_qt) break;
+      uint8_t* stage = smem_raw + (base - smem_u32(smem_raw)) + sm::Q + i * sm::TILE;
+#pragma unroll
+      for (int cc = 0; cc < NACC / 8; ++cc) {
+        if (a_beg * 16 + cc * 8 < a_end * 16) {
+          uint4 u;
+          u.x = pack2(acc[i][cc * 8 + 0], acc[i][cc * 8 + 1]); u.y = pack2(acc[i][cc * 8 + 2], acc[i][cc * 8 + 3]);
+          u.z = pack2(acc[i][cc * 8 + 4], acc[i][cc * 8 + 5]); u.w = pack2(acc[i][cc * 8 + 6], acc[i][cc * 8 + 7]);
+          *reinterpret_cast<uint4*>(stage + row * RB + (a_beg * 2 + cc) * 16) = u;
+        }
+      }
+      if (half == 0) {
+        long long o = -1;
+        if (row < q_rows_of(i)) {
+          const int ry = row / cl.rw, rx = row - ry * cl.rw;
+          o = (((long long)it.b * p.H + it.yk0 + i * cl.qbh + ry) * p.W + it.x0 + rx) * (3LL * C);
+        }
+        offs[i][row] = o;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i >= n_qt) break;
+      copy_rows_out<C1>(smem_raw + (base - smem_u32(smem_raw)) + sm::Q + i * sm::TILE, offs[i], p.dqkv + head * p.hd, p.hd, tid, NTHR_KV);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  ATC_STAMP(7);
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------- host side
 
 // 5-D view (d, part*nh + head, x, y, b) of a [B, H, W, parts*nh*hd] bf16 tensor; stream mode: x = H*W, y = 1
@@ -968,6 +1330,8 @@ struct Plan {
   TcParams p;
   int total_items;          // query-tile work items
   int total_kitems;         // key-block work items (dK/dV kernel)
+  int total_windows;        // window work items (fused backward)
+  bool fused_ok;            // every window has <= 2 query tiles
   bool bwd_ok;              // every key block has room for the virtual pad key
   bool stream;
 };
@@ -999,7 +1363,8 @@ static int get_plan(Plan** out, const void* qkv, const void* dout, int B, int H,
   p.scale = 1.0f / sqrtf((float)hd);
   pl.stream = window == 0;
   pl.bwd_ok = true;
-  int items = 0, kitems = 0;
+  pl.fused_ok = !pl.stream;
+  int items = 0, kitems = 0, witems = 0;
   auto add_class = [&](int rw, int rh, int wx0, int wy0, int cnx, int cny, int n_pad) -> int {
     const int c = p.n_cls++;
     TcClass& k = p.cls[c];
@@ -1023,6 +1388,9 @@ static int get_plan(Plan** out, const void* qkv, const void* dout, int B, int H,
     items += k.n_items;
     k.kitem0 = kitems;
     kitems += cnx * cny * B * k.n_kb;
+    k.witem0 = witems;
+    witems += cnx * cny * B;
+    if (k.n_qt > 2) pl.fused_ok = false;
     int rc = make_map5(&p.q0[c], qkv, B, H, W, 3 * nh, hd, pl.stream, 64, qbx, qby, CU_TENSOR_MAP_SWIZZLE_128B);
     if (!rc) rc = make_map5(&p.q1[c], qkv, B, H, W, 3 * nh, hd, pl.stream, box1, qbx, qby, swz1);
     if (!rc) rc = make_map5(&p.k0[c], qkv, B, H, W, 3 * nh, hd, pl.stream, 64, kbx, kby, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1049,6 +1417,7 @@ static int get_plan(Plan** out, const void* qkv, const void* dout, int B, int H,
   if (rc) return rc;
   pl.total_items = items;
   pl.total_kitems = kitems;
+  pl.total_windows = witems;
   if (cache.size() > 4096) cache.clear();
   auto ins = cache.emplace(key, pl);
   *out = &ins.first->second;
@@ -1058,7 +1427,7 @@ static int get_plan(Plan** out, const void* qkv, const void* dout, int B, int H,
 template <int C1>
 static int launch_fwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
   using sm = Smem<C1>;
-  dim3 grid(pl.total_items, p.nh);
+  dim3 grid(p.nh, pl.total_items);
   if (pl.stream) {
     S2U_ALLOW_SMEM((fwd_kernel<C1, true>));
     S2U_LAUNCH((fwd_kernel<C1, true>), grid, NTHR_F, sm::FWD_BYTES, st, p);
@@ -1073,9 +1442,18 @@ static int launch_fwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
 template <int C1>
 static int launch_bwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
   static int skip = -1;                                      // S2U_ATC_SKIP=1 / 2: leave out the dQ / dK-dV kernel (timing)
-  if (skip < 0) { const char* e = getenv("S2U_ATC_SKIP"); skip = e ? atoi(e) : 0; }
+  if (skip < 0) { const char* e = getenv("S2U_ATC_SKIP"); skip = e ? atoi(e) : 0; }   // 3: never the fused kernel
+  if (C1 == 16 && pl.fused_ok && skip != 3) {
+    if constexpr (C1 == 16) {
+      dim3 grid(p.nh, pl.total_windows);
+      S2U_ALLOW_SMEM((bwd_win_kernel<16>));
+      S2U_LAUNCH((bwd_win_kernel<16>), grid, NTHR_KV, SmemWin<16>::BYTES, st, p);
+      S2U_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   if (skip != 1) {
-    dim3 grid(pl.total_items, p.nh);
+    dim3 grid(p.nh, pl.total_items);
     if (pl.stream) {
       S2U_ALLOW_SMEM((bwd_dq_kernel<C1, true>));
       S2U_LAUNCH((bwd_dq_kernel<C1, true>), grid, NTHR, SmemDq<C1>::BYTES, st, p);
@@ -1086,7 +1464,7 @@ static int launch_bwd(const Plan& pl, const TcParams& p, cudaStream_t st) {
     S2U_LAUNCH_CHECK();
   }
   if (skip != 2) {
-    dim3 grid(pl.total_kitems, p.nh);
+    dim3 grid(p.nh, pl.total_kitems);
     if (pl.stream) {
       S2U_ALLOW_SMEM((bwd_dkv_kernel<C1, true>));
       S2U_LAUNCH((bwd_dkv_kernel<C1, true>), grid, NTHR_KV, SmemKv<C1>::BYTES, st, p);
@@ -1128,6 +1506,9 @@ int s2u_attn_tc_bwd(const void* qkv, const float* bias, const void* out, const f
   atc::TcParams p = pl->p;
   p.bias = bias; p.qkv = (const bf16*)qkv; p.lse = const_cast<float*>(lse);
   p.o_in = (const bf16*)out; p.dout = (const bf16*)dout; p.dqkv = (bf16*)dqkv; p.dws = dws;
+#ifdef S2U_ATC_TIMING
+  { const char* e = getenv("S2U_ATC_TIMING_BUF"); if (e) p.dws = (float*)strtoull(e, nullptr, 0); }
+#endif
   if (hd - 64 <= 16) return atc::launch_bwd<16>(*pl, p, st);
   return atc::launch_bwd<32>(*pl, p, st);
 }

@@ -113,6 +113,19 @@ __global__ void __launch_bounds__(256) loss_fwd_vec_kernel(LossPtrs p, const flo
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * VT_H, x0 = blockIdx.x * VT_W;
   const float* mb = mask + (long long)b * H * W;
+  // this thread's two 4-pixel groups of the last phase: issue their logit loads now, consume them after the filter
+  constexpr int NG = VT_H * (VT_W / 4) / 256;
+  float4 pre[NG][MAXH];
+#pragma unroll
+  for (int it = 0; it < NG; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int ty = i / (VT_W / 4), tx = (i - ty * (VT_W / 4)) * 4;
+    const bool ok = y0 + ty < H && x0 + tx < W;
+    const long long o = ((long long)b * H + y0 + ty) * W + x0 + tx;
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h)
+      pre[it][h] = (ok && h < nheads) ? __ldg(reinterpret_cast<const float4*>(p.pred[h] + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   // halo tile: tile column c = image column x0 - 16 + c, in 4-pixel groups (16-byte aligned since x0 % 4 == 0)
   for (int i = threadIdx.x; i < VHALO_H * (VPITCH / 4); i += 256) {
     const int ty = i / (VPITCH / 4), g = i - ty * (VPITCH / 4);
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(256) loss_fwd_vec_kernel(LossPtrs p, const flo
 #pragma unroll
   for (int k = 0; k < MAXH * 3; ++k) acc[k] = 0.f;
 #pragma unroll
-  for (int it = 0; it < VT_H * (VT_W / 4) / 256; ++it) {                // 2 float4 groups per thread, row-major
+  for (int it = 0; it < NG; ++it) {                                     // 2 float4 groups per thread, row-major
     const int i = threadIdx.x + it * 256;
     const int ty = i / (VT_W / 4), tx = (i - ty * (VT_W / 4)) * 4;
     const int y = y0 + ty, x = x0 + tx;
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(256) loss_fwd_vec_kernel(LossPtrs p, const flo
 #pragma unroll
     for (int h = 0; h < MAXH; ++h) {
       if (h >= nheads) break;
-      const float4 p4 = __ldg(reinterpret_cast<const float4*>(p.pred[h] + o));
+      const float4 p4 = pre[it][h];
       const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {

@@ -19,17 +19,39 @@ out, lse = torch.empty(B, H, W, C, device=cuda, dtype=torch.bfloat16), torch.emp
 buf = torch.zeros(8 * 8192, dtype=torch.int64, device=cuda)
 os.environ["S2U_ATC_TIMING_BUF"] = str(buf.data_ptr())
 _lib.call("s2u_set_attn_backend", 2)
-for _ in range(3):
+BWD = os.environ.get("BWD", "0") == "1"
+dout = torch.randn(B, H, W, C, generator=g).to(cuda).bfloat16()
+dqkv = torch.empty_like(qkv)
+if BWD:
+    del os.environ["S2U_ATC_TIMING_BUF"]
     ops.attn_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, False)
+    torch.cuda.synchronize()
+    os.environ["S2U_ATC_TIMING_BUF"] = str(buf.data_ptr())
+for _ in range(3):
+    torch.cuda.synchronize()                      # isolated launches: no programmatic overlap with a predecessor
+    if BWD:
+        ops.attn_bwd(qkv, bias, out, lse, dout, dqkv, B, H, W, nh, hd, window, False)
+    else:
+        ops.attn_fwd(qkv, bias, out, lse, B, H, W, nh, hd, window, False)
 torch.cuda.synchronize()
 t = buf.view(-1, 8).cpu()
 t = t[t[:, 0] > 0].double()
 t0 = t[:, 0].min()
 print("CTAs", t.shape[0], "kernel span us", (t[:, 7].max() - t0).item() / 1e3)
 names = ["start->alloc", "pdl_wait", "->S issued(TMA)", "S mma done", "softmax", "PV done", "epilogue"]
-d = t[:, 1:] - t[:, :-1]
+if BWD:
+    names = ["start -> zero rows done (thread 0: barriers + TMA issue)", "pdl_wait + D / lse", "sync (waits for TMEM alloc)", "TMA wait + S,dP mma", "elementwise", "dV dK dQ mma", "remaining steps + stores"]
+if BWD:
+    heavy = t[t[:, 6] > 0]                      # windows with 2 x 2 tile pairs
+    light = t[t[:, 6] == 0]
+    names = ["prologue", "step 0", "step 1", "store dK dV (block 0)", "step 2", "step 3", "store dK dV (block 1) + dQ"]
+    d = heavy[:, 1:] - heavy[:, :-1]
+    print("heavy CTAs", heavy.shape[0], "light", light.shape[0], "light life mean", ((light[:, 7] - light[:, 0]).mean() / 1e3).item())
+else:
+    d = t[:, 1:] - t[:, :-1]
 for i, n in enumerate(names):
     print(f"{n:18s} mean {d[:, i].mean().item() / 1e3:6.2f} us  max {d[:, i].max().item() / 1e3:6.2f}")
-print("CTA life mean us", ((t[:, 7] - t[:, 0]).mean() / 1e3).item())
+life = (t[:, 7] - t[:, 0]) / 1e3
+print("CTA life mean us", life.mean().item(), "quantiles", [round(float(torch.quantile(life, q)), 2) for q in (0.1, 0.5, 0.75, 0.9, 1.0)])
 start = (t[:, 0] - t0) / 1e3
 print("CTA start offsets us: quantiles", [round(float(torch.quantile(start, q)), 2) for q in (0.1, 0.5, 0.62, 0.9, 1.0)])
