@@ -36,8 +36,10 @@ using namespace umma;
 #ifdef S2U_ATC_TIMING
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define ATC_STAMP(i) do { if (threadIdx.x == 0 && p.dws) reinterpret_cast<long long*>(p.dws)[8LL * (blockIdx.y * gridDim.x + blockIdx.x) + (i)] = gtime(); } while (0)
+#define ATC_STAMP_T(i, thr) do { if (threadIdx.x == (thr) && p.dws) reinterpret_cast<long long*>(p.dws)[8LL * (blockIdx.y * gridDim.x + blockIdx.x) + (i)] = gtime(); } while (0)
 #else
 #define ATC_STAMP(i) do {} while (0)
+#define ATC_STAMP_T(i, thr) do {} while (0)
 #endif
 
 constexpr int NTHR = 128;
@@ -1013,24 +1015,37 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_win_kernel(const __grid_consta
 
   pdl_launch_dependents();
   if (warp == 0) {
+    // the four tensor maps miss the descriptor cache on a cold SM (~1 us each when fetched one after the other by
+    // the issuing thread): four lanes prefetch them at once, and four lanes issue the loads (one barrier group each)
+    if (lane == 0) tma_prefetch_desc(&p.q0[c]);
+    if (lane == 1) tma_prefetch_desc(&p.q1[c]);
+    if (lane == 2) tma_prefetch_desc(&p.o0[c]);
+    if (lane == 3) tma_prefetch_desc(&p.o1[c]);
     if (lane == 0) {
       for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8u * i, 1);
       mbar_init(bar_s, 2);                                   // one commit per MMA-issuing thread, see below
       mbar_init(bar_d, 3);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane < 4) {
       pdl_wait();
-      for (int i = 0; i < n_qt; ++i) {                       // tile i of the queries == block i of the keys (same boxes)
+      const int i = lane >> 1;                               // tile i of the queries == block i of the keys (same boxes)
+      if (i < n_qt) {
         const int y = it.yk0 + i * cl.qbh;
-        mbar_expect_tx(bar_k[i], 2 * tile_bytes);
-        tma_load_5d(tile0(sm::K, i), &p.q0[c], bar_k[i], 0, p.nh + head, it.x0, y, it.b);
-        if (C1) tma_load_5d(tile1(sm::K, i), &p.q1[c], bar_k[i], 64, p.nh + head, it.x0, y, it.b);
-        tma_load_5d(tile0(sm::V, i), &p.q0[c], bar_k[i], 0, 2 * p.nh + head, it.x0, y, it.b);
-        if (C1) tma_load_5d(tile1(sm::V, i), &p.q1[c], bar_k[i], 64, 2 * p.nh + head, it.x0, y, it.b);
-        mbar_expect_tx(bar_q[i], 2 * tile_bytes);
-        tma_load_5d(tile0(sm::Q, i), &p.q0[c], bar_q[i], 0, head, it.x0, y, it.b);
-        if (C1) tma_load_5d(tile1(sm::Q, i), &p.q1[c], bar_q[i], 64, head, it.x0, y, it.b);
-        tma_load_5d(tile0(sm::DO, i), &p.o0[c], bar_q[i], 0, head, it.x0, y, it.b);
-        if (C1) tma_load_5d(tile1(sm::DO, i), &p.o1[c], bar_q[i], 64, head, it.x0, y, it.b);
+        if (lane & 1) {
+          mbar_expect_tx(bar_q[i], 2 * tile_bytes);
+          tma_load_5d(tile0(sm::Q, i), &p.q0[c], bar_q[i], 0, head, it.x0, y, it.b);
+          if (C1) tma_load_5d(tile1(sm::Q, i), &p.q1[c], bar_q[i], 64, head, it.x0, y, it.b);
+          tma_load_5d(tile0(sm::DO, i), &p.o0[c], bar_q[i], 0, head, it.x0, y, it.b);
+          if (C1) tma_load_5d(tile1(sm::DO, i), &p.o1[c], bar_q[i], 64, head, it.x0, y, it.b);
+        } else {
+          mbar_expect_tx(bar_k[i], 2 * tile_bytes);
+          tma_load_5d(tile0(sm::K, i), &p.q0[c], bar_k[i], 0, p.nh + head, it.x0, y, it.b);
+          if (C1) tma_load_5d(tile1(sm::K, i), &p.q1[c], bar_k[i], 64, p.nh + head, it.x0, y, it.b);
+          tma_load_5d(tile0(sm::V, i), &p.q0[c], bar_k[i], 0, 2 * p.nh + head, it.x0, y, it.b);
+          if (C1) tma_load_5d(tile1(sm::V, i), &p.q1[c], bar_k[i], 64, 2 * p.nh + head, it.x0, y, it.b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -1050,26 +1065,54 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_win_kernel(const __grid_consta
             make_uint4(0, 0, 0, 0));
     }
   }
+  tc_fence_before();
+  __syncthreads();                                           // barriers initialised, TMEM allocated
+  tc_fence_after();
   pdl_wait();
-  // lse and D = sum_d dO * O of the window's queries: thread t owns query (t / 128, t % 128)
+  // lse and D = sum_d dO * O of the window's queries: thread t owns query (t / 128, t % 128).  The O row comes from
+  // global memory (loads issued here, consumed below), the dO row from its TMA-loaded tile
   {
+    constexpr int NCH = (64 + C1) / 8;
     const int i = tid >> 7, r = tid & 127;
+    const bool liveq = i < n_qt && r < q_rows_of(i);
     float L = INFINITY, D = 0.f;
-    if (i < n_qt && r < q_rows_of(i)) {
+    uint4 uo[NCH];
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) uo[cc] = make_uint4(0, 0, 0, 0);
+    if (liveq) {
       const int ry = r / cl.rw, rx = r - ry * cl.rw;
       const long long tk = ((long long)it.b * p.H + it.yk0 + i * cl.qbh + ry) * p.W + it.x0 + rx;
       L = p.lse[tk * p.nh + head] * 1.4426950408889634f;
-      D = row_dot<C1>(p.dout + tk * C + head * p.hd, p.o_in + tk * C + head * p.hd, p.hd);
+      const uint4* src = reinterpret_cast<const uint4*>(p.o_in + tk * C + head * p.hd);
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc)
+        if (cc * 8 < p.hd) uo[cc] = __ldg(src + cc);
+    }
+    if (i < n_qt) {
+      mbar_wait(bar_q[i], 0);                                // dO_i has landed
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) {
+        uint4 ud;
+        const uint32_t ad = cc < 8 ? tile0_addr(tile0(sm::DO, i), r, cc) : tile1_addr<C1>(tile1(sm::DO, i), r, cc - 8);
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ud.x), "=r"(ud.y), "=r"(ud.z), "=r"(ud.w) : "r"(ad));
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ud);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&uo[cc]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+          d0 = fmaf(fa.x, fb.x, d0);
+          d1 = fmaf(fa.y, fb.y, d1);
+        }
+      }
+      D = liveq ? d0 + d1 : 0.f;                             // (rows beyond the window: uo = 0)
     }
     LDs[i * 256 + r] = L;
     LDs[i * 256 + 128 + r] = D;
   }
   fence_proxy_async();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
   const uint32_t tmem = tmem_holder;
-  ATC_STAMP(1);
   const uint32_t t_row = tmem + ((uint32_t)(quarter * 32) << 16);
   const uint32_t tK = tmem + 256, tV = tmem + 256 + 64 + C1, tQ = tmem + 256 + 2 * (64 + C1);
   const float sl2 = p.scale * 1.4426950408889634f;
@@ -1202,10 +1245,6 @@ __global__ void __launch_bounds__(NTHR_KV, 1) bwd_win_kernel(const __grid_consta
       tc_fence_before();
       __syncthreads();                                       // the next step overwrites S^T / dP^T, the dS^T tile and dQ part
       tc_fence_after();
-      if (step == 1) ATC_STAMP(2);
-      if (step == 2) ATC_STAMP(3);
-      if (step == 3) ATC_STAMP(5);
-      if (step == 4) ATC_STAMP(6);
     }
     // dK_j (column half 0) and dV_j (half 1) are complete: rows = keys.  Their tiles K_j / V_j are dead now and stage
     // the bf16 rows for a coalesced copy-out

@@ -41,6 +41,11 @@ print("CTAs", t.shape[0], "kernel span us", (t[:, 7].max() - t0).item() / 1e3)
 names = ["start->alloc", "pdl_wait", "->S issued(TMA)", "S mma done", "softmax", "PV done", "epilogue"]
 if BWD:
     names = ["start -> zero rows done (thread 0: barriers + TMA issue)", "pdl_wait + D / lse", "sync (waits for TMEM alloc)", "TMA wait + S,dP mma", "elementwise", "dV dK dQ mma", "remaining steps + stores"]
+if BWD and os.environ.get("PRO", "0") == "1":
+    rel = (t - t[:, :1]) / 1e3
+    for nm, col in (("zero rows done (thread 128)", 1), ("pdl_wait done", 2), ("D / lse done", 3), ("after sync", 4), ("TMA issued (thread 0)", 5), ("TMEM alloc done (thread 32)", 6), ("end", 7)):
+        print(f"{nm:30s} mean {rel[:, col].mean().item():6.2f} us after start, max {rel[:, col].max().item():6.2f}")
+    sys.exit(0)
 if BWD:
     heavy = t[t[:, 6] > 0]                      # windows with 2 x 2 tile pairs
     light = t[t[:, 6] == 0]
