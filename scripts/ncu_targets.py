@@ -1,0 +1,75 @@
+"""One launch of each non-GEMM kernel family at its dominant Hiera-L 352x352 batch-12 shape, for ncu captures:
+
+    python scripts/ncu_targets.py                      # plain run first (must exit 0)
+    ncu --set full --clock-control none --import-source on -k regex:"<names>" -o gpurun_out/r2_kernels python scripts/ncu_targets.py
+
+Kernels (in launch order after the warm-up pass): attention forward / fused backward (tcgen05, 16x16 windows of a 22x22
+map), global attention forward / dQ / dK-dV (streaming), LayerNorm forward / backward, BatchNorm statistics / apply /
+backward, structure_loss forward / backward."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from sam2_unet_b200 import _lib
+from sam2_unet_b200.engine import Ops
+
+dev = torch.device("cuda:0")
+ops = Ops(torch.bfloat16, dev, 0)
+bf, f32 = torch.bfloat16, torch.float32
+g = torch.Generator().manual_seed(0)
+
+
+def r(*s, dt=bf):
+    return torch.randn(*s, generator=g).to(dev).to(dt)
+
+
+B, H, nh, hd = 12, 22, 8, 72
+C = nh * hd
+qkv, dout, bias = r(B, H, H, 3 * C), r(B, H, H, C), r(3 * C, dt=f32)
+out, lse = torch.empty(B, H, H, C, device=dev, dtype=bf), torch.empty(B, H, H, nh, device=dev)
+dqkv = torch.empty_like(qkv)
+R, Cl = 5808, 576
+ln = dict(x=r(R, Cl, dt=f32), g=r(Cl, dt=f32), b=r(Cl, dt=f32), y=torch.empty(R, Cl, device=dev, dtype=bf),
+          mean=torch.empty(R, device=dev), rstd=torch.empty(R, device=dev), dy=r(R, Cl), dres=r(R, Cl),
+          dx=torch.empty(R, Cl, device=dev, dtype=bf))
+M, Cb = 92928, 64
+bn = dict(x=r(M, Cb), sums=torch.zeros(_lib.load().s2u_bn_ws_doubles(Cb), device=dev, dtype=torch.float64), gamma=r(Cb, dt=f32),
+          beta=r(Cb, dt=f32), rm=torch.zeros(Cb, device=dev), rv=torch.ones(Cb, device=dev), nb=torch.zeros(1, device=dev, dtype=torch.int64),
+          scale=torch.empty(Cb, device=dev), shift=torch.empty(Cb, device=dev), mean=torch.empty(Cb, device=dev),
+          rstd=torch.empty(Cb, device=dev), out=torch.empty(M, Cb, device=dev, dtype=bf), dy=r(M, Cb),
+          dgamma=torch.zeros(Cb, device=dev), dbeta=torch.zeros(Cb, device=dev), c1=torch.empty(Cb, device=dev),
+          c2=torch.empty(Cb, device=dev), dx=torch.empty(M, Cb, device=dev, dtype=bf))
+Bl, Sl = 12, 352
+ls = dict(p=[r(Bl, 1, Sl, Sl, dt=f32) for _ in range(3)], m=(torch.rand(Bl, 1, Sl, Sl, generator=g) > 0.7).float().to(dev),
+          w=torch.empty(Bl, Sl, Sl, device=dev), sums=torch.zeros(3 * Bl * 2 + 3, device=dev, dtype=torch.float64),
+          loss=torch.empty(3, device=dev), g=[torch.empty(Bl, 1, Sl, Sl, device=dev) for _ in range(3)])
+
+
+def once():
+    _lib.call("s2u_set_attn_backend", 2)
+    ops.attn_fwd(qkv, bias, out, lse, B, H, H, nh, hd, 16, False)
+    ops.attn_bwd(qkv, bias, out, lse, dout, dqkv, B, H, H, nh, hd, 16, False)
+    ops.attn_fwd(qkv, bias, out, lse, B, H, H, nh, hd, 0, False)
+    ops.attn_bwd(qkv, bias, out, lse, dout, dqkv, B, H, H, nh, hd, 0, False)
+    _lib.call("s2u_set_attn_backend", 0)
+    ops.ln_fwd(ln["x"], ln["g"], ln["b"], ln["y"], ln["mean"], ln["rstd"], R, Cl)
+    ops.ln_bwd(ln["dy"], ln["x"], ln["g"], ln["mean"], ln["rstd"], ln["dres"], ln["dx"], R, Cl)
+    ops.bn_stats_finalize(bn["x"], Cb, bn["sums"], bn["gamma"], bn["beta"], bn["rm"], bn["rv"], bn["nb"], bn["scale"],
+                          bn["shift"], bn["mean"], bn["rstd"], M, Cb)
+    ops.bn_apply(bn["x"], Cb, bn["scale"], bn["shift"], None, 0, bn["out"], Cb, M, Cb, True)
+    ops.bn_bwd(bn["dy"], Cb, bn["out"], Cb, bn["x"], Cb, bn["mean"], bn["rstd"], bn["gamma"], bn["sums"], bn["dgamma"],
+               bn["dbeta"], bn["c1"], bn["c2"], bn["dx"], Cb, M, Cb)
+    _lib.call("s2u_structure_loss_fwd", ls["p"][0].data_ptr(), ls["p"][1].data_ptr(), ls["p"][2].data_ptr(), ls["m"].data_ptr(),
+              ls["w"].data_ptr(), ls["sums"].data_ptr(), ls["loss"].data_ptr(), Bl, Sl, Sl, 3, ops.stream)
+    _lib.call("s2u_structure_loss_bwd", ls["p"][0].data_ptr(), ls["p"][1].data_ptr(), ls["p"][2].data_ptr(), ls["m"].data_ptr(),
+              ls["w"].data_ptr(), ls["sums"].data_ptr(), 0, ls["g"][0].data_ptr(), ls["g"][1].data_ptr(), ls["g"][2].data_ptr(),
+              Bl, Sl, Sl, 3, ops.stream)
+
+
+once()
+torch.cuda.synchronize()
+once()
+torch.cuda.synchronize()
+print("ncu targets done", float(out.float().abs().mean()), float(ls["loss"].sum()))
