@@ -126,13 +126,27 @@ __global__ void __launch_bounds__(256) loss_fwd_vec_kernel(LossPtrs p, const flo
     for (int h = 0; h < MAXH; ++h)
       pre[it][h] = (ok && h < nheads) ? __ldg(reinterpret_cast<const float4*>(p.pred[h] + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // halo tile: tile column c = image column x0 - 16 + c, in 4-pixel groups (16-byte aligned since x0 % 4 == 0)
-  for (int i = threadIdx.x; i < VHALO_H * (VPITCH / 4); i += 256) {
-    const int ty = i / (VPITCH / 4), g = i - ty * (VPITCH / 4);
-    const int y = y0 + ty - LR, x = x0 - 16 + 4 * g;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = __ldg(reinterpret_cast<const float4*>(mb + (long long)y * W + x));
-    *reinterpret_cast<float4*>(&tile[ty][4 * g]) = v;       // W % 4 == 0 and x % 4 == 0: a group is all in or all out
+  // halo tile: tile column c = image column x0 - 16 + c, in 4-pixel groups (16-byte aligned since x0 % 4 == 0).
+  // All of a thread's loads are issued before the first store: a load -> store loop pays the DRAM latency per trip
+  {
+    constexpr int NV = (VHALO_H * (VPITCH / 4) + 255) / 256;
+    float4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int ty = i / (VPITCH / 4), g = i - ty * (VPITCH / 4);
+      const int y = y0 + ty - LR, x = x0 - 16 + 4 * g;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // W % 4 == 0 and x % 4 == 0: a group is all in or all out
+      if (i < VHALO_H * (VPITCH / 4) && y >= 0 && y < H && x >= 0 && x + 3 < W)
+        v[k] = __ldg(reinterpret_cast<const float4*>(mb + (long long)y * W + x));
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int ty = i / (VPITCH / 4), g = i - ty * (VPITCH / 4);
+      if (i < VHALO_H * (VPITCH / 4)) *reinterpret_cast<float4*>(&tile[ty][4 * g]) = v[k];
+    }
   }
   __syncthreads();
   // vertical 31-tap sums of every halo column for the 16 output rows: (column, 8-row run), lanes = consecutive columns
