@@ -15,6 +15,7 @@ gradient buffer, so AdamW and the data-parallel all-reduce are single flat opera
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -99,6 +100,25 @@ class Ops:
         _lib.call("s2u_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
                   rstd.data_ptr(), _ptr(dres), dx.data_ptr(), _ptr(pre), _ptr(dx2), _ptr(colsum), _ptr(ws),
                   1 if pre_is_grad else 0, R, C, 1 if x.dtype == torch.float32 else 0, self.dt, self.stream)
+
+    def adapter_supported(self, C: int) -> bool:
+        return self.T == torch.bfloat16 and bool(_lib.load().s2u_adapter_supported(C))
+
+    def adapter_ln_fwd(self, xs, w1, b1, w2, b2, gamma, beta, xa, n1, mean, rstd, u, g1, g2, R, C):
+        _lib.call("s2u_adapter_ln_fwd", xs.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                  gamma.data_ptr(), beta.data_ptr(), 1e-6, xa.data_ptr(), n1.data_ptr(), mean.data_ptr(),
+                  rstd.data_ptr(), _ptr(u), _ptr(g1), _ptr(g2), R, C, self.stream)
+
+    def adapter_ln_bwd(self, dn1, xa, mean, rstd, gamma, dres, g2, g1, w2t, w1t, dh2, dh1, dx, db1, db2, R, C):
+        key = ("adp", C, self.stream)
+        ws = self._ln_ws.get(key)
+        if ws is None:
+            n = _lib.load().s2u_adapter_ws_floats(C)
+            ws = self._ln_ws[key] = torch.zeros(n, dtype=torch.float32, device=self.device)
+        _lib.call("s2u_adapter_ln_bwd", dn1.data_ptr(), xa.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                  gamma.data_ptr(), _ptr(dres), g2.data_ptr(), g1.data_ptr(), w2t.data_ptr(), w1t.data_ptr(),
+                  dh2.data_ptr(), dh1.data_ptr(), dx.data_ptr(), db1.data_ptr(), db2.data_ptr(), ws.data_ptr(), R, C,
+                  self.stream)
 
     def dgelu_mul(self, dy, pre, out):
         _lib.call("s2u_dgelu_mul", dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), self.dt, self.stream)
@@ -227,6 +247,7 @@ class Engine:
         self._shadow_version = -1
         self._refresh = None
         self._streams = None
+        self.fuse_adapter = os.environ.get("S2U_FUSE_ADAPTER", "1") != "0"   # adapter + norm1 as one kernel per direction
         self.overlap = self.device.type == "cuda"   # RFB forward/backward on side streams, overlapped with the trunk
 
     # ------------------------------------------------------------------------------------------ weights
@@ -408,15 +429,22 @@ class Engine:
         f32 = torch.float32
         # adapter (SAM2UNet.py:61-63): xa = x + gelu(gelu(x W1^T + b1) W2^T + b2)
         # h1 / hid hold gelu'(pre-activation), evaluated by the forward epilogue next to gelu itself (SAVE_DGELU)
-        h1, u = (ops.empty(R, 32) if tape is not None else None), ops.empty(R, 32)
-        ops.gemm(x, sh[a + "0.w"], u, bias=P[a + "0.bias"], pre_out=h1, flags=GELU | (SAVE_DGELU if tape is not None else 0))
-        h2, xa = (ops.empty(R, C) if tape is not None else None), ops.empty(R, C, dtype=f32)
-        ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=xs,
-                 flags=GELU | RESID | SF | (SAVE_DGELU if tape is not None else 0))
-        # norm1 (hieradet.py:134)
-        n1 = ops.empty(R, C)
+        xa, n1 = ops.empty(R, C, dtype=f32), ops.empty(R, C)
         mean1, rstd1 = ops.empty(R, dtype=f32), ops.empty(R, dtype=f32)
-        ops.ln_fwd(xa, fz[p + "norm1.g"], fz[p + "norm1.b"], n1, mean1, rstd1, R, C)
+        if self.fuse_adapter and ops.adapter_supported(C):
+            # adapter + norm1 (hieradet.py:134) in one launch, the 32-wide hidden activation never leaves the SM
+            h1, u, h2 = (ops.empty(R, 32), ops.empty(R, 32), ops.empty(R, C)) if tape is not None else (None,) * 3
+            ops.adapter_ln_fwd(xs, sh[a + "0.w"], P[a + "0.bias"], sh[a + "2.w"], P[a + "2.bias"], fz[p + "norm1.g"],
+                               fz[p + "norm1.b"], xa, n1, mean1, rstd1, u, h1, h2, R, C)
+        else:
+            h1, u = (ops.empty(R, 32) if tape is not None else None), ops.empty(R, 32)
+            ops.gemm(x, sh[a + "0.w"], u, bias=P[a + "0.bias"], pre_out=h1,
+                     flags=GELU | (SAVE_DGELU if tape is not None else 0))
+            h2 = ops.empty(R, C) if tape is not None else None
+            ops.gemm(u, sh[a + "2.w"], xa, bias=P[a + "2.bias"], pre_out=h2, resid=xs,
+                     flags=GELU | RESID | SF | (SAVE_DGELU if tape is not None else 0))
+            # norm1 (hieradet.py:134)
+            ops.ln_fwd(xa, fz[p + "norm1.g"], fz[p + "norm1.b"], n1, mean1, rstd1, R, C)
         pr = None
         Ho, Wo = H, W
         if C != C2:                                   # hieradet.py:137-138: shortcut = pool(proj(norm1(x)))
@@ -661,6 +689,12 @@ class Engine:
             dres = None
         # LN1 backward fused with the head of the adapter backward (xa = x + gelu(h2), h2 = u W2^T + b2,
         # u = gelu(h1), h1 = x W1^T + b1): dxa, dh2 = dxa * gelu'(h2) and db2 = colsum(dh2) in one pass
+        if self.fuse_adapter and ops.adapter_supported(C):
+            dh2, dh1, dx = ops.empty(R, C), ops.empty(R, 32), ops.empty(R, C)
+            ops.adapter_ln_bwd(dn1, tp["xa"], tp["mean1"], tp["rstd1"], fz[p + "norm1.g"], dres, tp["h2"], tp["h1"],
+                               sh[a + "2.wt"], sh[a + "0.wt"], dh2, dh1, dx, G[a + "0.bias"], G[a + "2.bias"], R, C)
+            ops.wgrad_pair(dh2, tp["u"], G[a + "2.weight"], 32, dh1, tp["x"], G[a + "0.weight"], C)
+            return dx
         dxa, dh2 = ops.empty(R, C), ops.empty(R, C)
         ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C, pre=tp["h2"], dx2=dh2,
                    colsum=G[a + "2.bias"], pre_is_grad=True)         # h2 holds gelu'(pre-activation)

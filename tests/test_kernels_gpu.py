@@ -622,3 +622,71 @@ def test_wgrad_pair(cuda, dtype, shape):
     tol = 1e-4 if dtype == "fp32" else 2e-3
     _close(G2, dh2.float().t() @ u.float(), tol, "pair: dW2")
     _close(G1, 1 + dh1.float().t() @ x.float(), tol, "pair: dW1")
+
+
+# ------------------------------------------------------------------------- fused adapter + LayerNorm (bf16 mode)
+
+def _dgelu(x):
+    return 0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327
+
+
+@pytest.mark.parametrize("shape", [(5808, 576), (1000, 144), (23232 + 5, 288), (1452, 1152), (333, 32), (100, 64),
+                                   (77, 128), (50, 256), (500, 96), (301, 448), (17, 768)])
+def test_adapter_ln_fused(cuda, shape):
+    """s2u_adapter_ln_fwd / _bwd (SAM2UNet.py:57-63 + hieradet.py:134) against the same math in fp32 torch."""
+    from sam2_unet_b200 import _lib
+    R, C = shape
+    ops = _ops("bf16", cuda)
+    assert ops.adapter_supported(C)
+    xs = _rand((R, C), "fp32", cuda, 1, 2.0) + 0.3
+    W1, W2 = _rand((32, C), "bf16", cuda, 2, C ** -0.5), _rand((C, 32), "bf16", cuda, 3, 32 ** -0.5)
+    b1, b2 = _rand((32,), "fp32", cuda, 4, 0.5), _rand((C,), "fp32", cuda, 5, 0.5)
+    gamma, beta = _rand((C,), "fp32", cuda, 6) + 1.0, _rand((C,), "fp32", cuda, 7)
+    f32 = torch.float32
+    xa, n1 = ops.empty(R, C, dtype=f32), ops.empty(R, C)
+    mean, rstd = ops.empty(R, dtype=f32), ops.empty(R, dtype=f32)
+    u, g1, g2 = ops.empty(R, 32), ops.empty(R, 32), ops.empty(R, C)
+    ops.adapter_ln_fwd(xs, W1, b1, W2, b2, gamma, beta, xa, n1, mean, rstd, u, g1, g2, R, C)
+    h = xs.bfloat16().float() @ W1.float().t() + b1
+    u_ref = F.gelu(h)
+    pre2 = u_ref.bfloat16().float() @ W2.float().t() + b2
+    xa_ref = xs + F.gelu(pre2)
+    _close(u, u_ref, 2e-2, "u")
+    _close(g1, _dgelu(h), 2e-2, "gelu'(h1)")
+    _close(g2, _dgelu(pre2), 2e-2, "gelu'(h2)")
+    _close(xa, xa_ref, 5e-3, "xa")
+    mu = xa_ref.mean(1)
+    var = xa_ref.var(1, unbiased=False)
+    _close(mean, mu, 5e-3, "mean")
+    _close(rstd, torch.rsqrt(var + 1e-6), 5e-3, "rstd")
+    _close(n1, F.layer_norm(xa_ref, (C,), gamma, beta, 1e-6), 2e-2, "n1")
+    # inference variant: nothing saved, same outputs
+    xa2, n2 = ops.empty(R, C, dtype=f32), ops.empty(R, C)
+    ops.adapter_ln_fwd(xs, W1, b1, W2, b2, gamma, beta, xa2, n2, mean, rstd, None, None, None, R, C)
+    assert torch.equal(xa2, xa) and torch.equal(n2, n1)
+
+    # backward, from the tensors the forward saved
+    dn1, dres = _rand((R, C), "bf16", cuda, 8), _rand((R, C), "bf16", cuda, 9)
+    W2t, W1t = W2.t().contiguous(), W1.t().contiguous()
+    for with_res in (True, False):
+        dh2, dh1, dx = ops.empty(R, C), ops.empty(R, 32), ops.empty(R, C)
+        db1 = torch.full((32,), 0.5, dtype=f32, device=cuda)
+        db2 = torch.full((C,), -0.25, dtype=f32, device=cuda)
+        ops.adapter_ln_bwd(dn1, xa, mean, rstd, gamma, dres if with_res else None, g2, g1, W2t, W1t, dh2, dh1, dx, db1,
+                           db2, R, C)
+        xh = (xa - mean[:, None]) * rstd[:, None]
+        gd = dn1.float() * gamma
+        dxa = rstd[:, None] * (gd - gd.mean(1, keepdim=True) - xh * (gd * xh).mean(1, keepdim=True))
+        if with_res:
+            dxa = dxa + dres.float()
+        dh2_ref = dxa * g2.float()
+        dh1_ref = (dh2_ref.bfloat16().float() @ W2.float()) * g1.float()
+        dx_ref = dxa + dh1_ref.bfloat16().float() @ W1.float()
+        _close(dh2, dh2_ref, 2e-2, "dh2")
+        _close(dh1, dh1_ref, 2e-2, "dh1")
+        _close(dx, dx_ref, 2e-2, "dx")
+        _close(db1 - 0.5, dh1_ref.sum(0), 2e-3, "db1")
+        _close(db2 + 0.25, dh2_ref.sum(0), 2e-3, "db2")
+    # the replicated accumulators are left zeroed
+    for key, ws in ops._ln_ws.items():
+        assert float(ws.abs().max()) == 0.0
