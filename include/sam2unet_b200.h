@@ -66,20 +66,18 @@ int s2u_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
  * Forward of SAM2UNet.py:57-63 followed by hieradet.py:134 in ONE launch:
  *   xa = x + gelu(gelu(x W1^T + b1) W2^T + b2)  (fp32),  n1 = LayerNorm(xa) (bf16), mean / rstd of the rows,
  *   and for the backward u = gelu(.) [R,32], g1 = gelu'(.) [R,32], g2 = gelu'(.) [R,C] (all three NULL at inference).
- * W1 [32,C], W2 [C,32] bf16.  Backward in ONE launch (+ a tiny fold): dxa = LN'(dn1) + dres (dres may be NULL),
+ * W1 [32,C], W2 [C,32] bf16.  Backward in ONE launch: dxa = LN'(dn1) + dres (dres may be NULL),
  *   dh2 = dxa * g2, dh1 = (dh2 W2) * g1, dx = dxa + dh1 W1, db1[32] += colsum(dh1), db2[C] += colsum(dh2);
  *   W2t [32,C], W1t [C,32] are the transposed weights; dh2 / dh1 are written for s2u_gemm_wgrad_pair.
- *   ws: s2u_adapter_ws_floats(C) floats, zero before the first use, left zeroed (one per concurrent stream).
  * s2u_adapter_supported(C) = 1 when C = 16 * {2,6,7,9} * {1,2,4,8} (every Hiera stage width), else the entry
  * points return -2 and the caller uses s2u_gemm + s2u_layernorm_*. */
 int s2u_adapter_supported(int C);
-int s2u_adapter_ws_floats(int C);
 int s2u_adapter_ln_fwd(const float* x, const void* W1, const float* b1, const void* W2, const float* b2,
                        const float* gamma, const float* beta, float eps, float* xa, void* n1, float* mean, float* rstd,
                        void* u, void* g1, void* g2, long long R, int C, void* stream);
 int s2u_adapter_ln_bwd(const void* dn1, const float* xa, const float* mean, const float* rstd, const float* gamma,
                        const void* dres, const void* g2, const void* g1, const void* W2t, const void* W1t, void* dh2,
-                       void* dh1, void* dx, float* db1, float* db2, float* ws, long long R, int C, void* stream);
+                       void* dh1, void* dx, float* db1, float* db2, long long R, int C, void* stream);
 
 /* ---- element-wise helpers --------------------------------------------------------------------------------- */
 int s2u_dgelu_mul(const void* dy, const void* pre, void* out, long long n, int dtype, void* stream);

@@ -24,9 +24,8 @@ SIGNATURES = {
     "s2u_layernorm_ws_floats": [I],
     "s2u_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P],
     "s2u_adapter_supported": [I],
-    "s2u_adapter_ws_floats": [I],
     "s2u_adapter_ln_fwd": [P, P, P, P, P, P, P, F, P, P, P, P, P, P, P, L, I, P],
-    "s2u_adapter_ln_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, L, I, P],
+    "s2u_adapter_ln_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, L, I, P],
     "s2u_dgelu_mul": [P, P, P, L, I, P],
     "s2u_add": [P, P, P, L, I, P],
     "s2u_maxpool2_fwd": [P, P, I, I, I, I, I, P],

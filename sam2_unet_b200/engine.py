@@ -110,15 +110,9 @@ class Ops:
                   rstd.data_ptr(), _ptr(u), _ptr(g1), _ptr(g2), R, C, self.stream)
 
     def adapter_ln_bwd(self, dn1, xa, mean, rstd, gamma, dres, g2, g1, w2t, w1t, dh2, dh1, dx, db1, db2, R, C):
-        key = ("adp", C, self.stream)
-        ws = self._ln_ws.get(key)
-        if ws is None:
-            n = _lib.load().s2u_adapter_ws_floats(C)
-            ws = self._ln_ws[key] = torch.zeros(n, dtype=torch.float32, device=self.device)
         _lib.call("s2u_adapter_ln_bwd", dn1.data_ptr(), xa.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                   gamma.data_ptr(), _ptr(dres), g2.data_ptr(), g1.data_ptr(), w2t.data_ptr(), w1t.data_ptr(),
-                  dh2.data_ptr(), dh1.data_ptr(), dx.data_ptr(), db1.data_ptr(), db2.data_ptr(), ws.data_ptr(), R, C,
-                  self.stream)
+                  dh2.data_ptr(), dh1.data_ptr(), dx.data_ptr(), db1.data_ptr(), db2.data_ptr(), R, C, self.stream)
 
     def dgelu_mul(self, dy, pre, out):
         _lib.call("s2u_dgelu_mul", dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), self.dt, self.stream)

@@ -47,7 +47,19 @@ ls = dict(p=[r(Bl, 1, Sl, Sl, dt=f32) for _ in range(3)], m=(torch.rand(Bl, 1, S
           loss=torch.empty(3, device=dev), g=[torch.empty(Bl, 1, Sl, Sl, device=dev) for _ in range(3)])
 
 
+ad = dict(xs=r(R, Cl, dt=f32), W1=r(32, Cl) * Cl ** -0.5, W2=r(Cl, 32) * 32 ** -0.5, b1=r(32, dt=f32), b2=r(Cl, dt=f32),
+          xa=torch.empty(R, Cl, device=dev), n1=torch.empty(R, Cl, device=dev, dtype=bf), u=torch.empty(R, 32, device=dev, dtype=bf),
+          g1=torch.empty(R, 32, device=dev, dtype=bf), g2=torch.empty(R, Cl, device=dev, dtype=bf),
+          dh2=torch.empty(R, Cl, device=dev, dtype=bf), dh1=torch.empty(R, 32, device=dev, dtype=bf),
+          dx=torch.empty(R, Cl, device=dev, dtype=bf), db1=torch.zeros(32, device=dev), db2=torch.zeros(Cl, device=dev))
+ad["W2t"], ad["W1t"] = ad["W2"].t().contiguous(), ad["W1"].t().contiguous()
+
+
 def once():
+    ops.adapter_ln_fwd(ad["xs"], ad["W1"], ad["b1"], ad["W2"], ad["b2"], ln["g"], ln["b"], ad["xa"], ad["n1"], ln["mean"],
+                       ln["rstd"], ad["u"], ad["g1"], ad["g2"], R, Cl)
+    ops.adapter_ln_bwd(ln["dy"], ad["xa"], ln["mean"], ln["rstd"], ln["g"], ln["dres"], ad["g2"], ad["g1"], ad["W2t"],
+                       ad["W1t"], ad["dh2"], ad["dh1"], ad["dx"], ad["db1"], ad["db2"], R, Cl)
     _lib.call("s2u_set_attn_backend", 2)
     ops.attn_fwd(qkv, bias, out, lse, B, H, H, nh, hd, 16, False)
     ops.attn_bwd(qkv, bias, out, lse, dout, dqkv, B, H, H, nh, hd, 16, False)

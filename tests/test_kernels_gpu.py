@@ -687,6 +687,3 @@ def test_adapter_ln_fused(cuda, shape):
         _close(dx, dx_ref, 2e-2, "dx")
         _close(db1 - 0.5, dh1_ref.sum(0), 2e-3, "db1")
         _close(db2 + 0.25, dh2_ref.sum(0), 2e-3, "db2")
-    # the replicated accumulators are left zeroed
-    for key, ws in ops._ln_ws.items():
-        assert float(ws.abs().max()) == 0.0
