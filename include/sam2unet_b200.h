@@ -119,6 +119,20 @@ int s2u_patch_im2col(const float* x, void* out, int B, int S, void* stream);
 /* taps of a stride-1 conv gathered to [B*H*W, KH*KW*Cin] (SAM2UNet.py:68-125,9-26). */
 int s2u_im2col(const void* x, int ldx, void* out, int B, int H, int W, int Cin, int KH, int KW, int dil_h, int dil_w,
                int pad_h, int pad_w, int dtype, void* stream);
+/* Implicit-GEMM convolution (bf16, tcgen05 + 4-D TMA boxes, no im2col matrix): forward of SAM2UNet.py:83-86 and its
+ * input gradient (x = d(raw), Wm = the flipped / transposed operand of s2u_conv_weight_pack).  Stride 1, "same" zero
+ * padding, dilation dil; Cin % 64 == 0, N in {64, 128, 256} (s2u_conv_igemm_supported), else -2.
+ * out = epi(conv): + bias[N] (NULL: none), + resid (NULL: none; resid == out accumulates), relu.  sums (N == 64, or
+ * NULL): the fp64 workspace of s2u_bn_ws_doubles(64), receives the BatchNorm batch statistics of the rounded output
+ * (finalise with s2u_bn_finalize) - no separate statistics pass. */
+int s2u_conv_igemm_supported(int Cin, int N, int ldx, int ld_out);
+int s2u_conv_igemm(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int N, int KH, int KW, int dil,
+                   void* out, int ld_out, const float* bias, const void* resid, int ld_res, int relu, double* sums,
+                   void* stream);
+/* G [Cout][Cin][KH][KW] (fp32, accumulated) += weight gradient of the convolution from the un-expanded activations:
+ * dy [B,H,W,Cout <= 64] pitch ld_dy, x [B,H,W,Cin % 64 == 0] pitch ldx (bf16). */
+int s2u_conv_wgrad(const void* dy, int ld_dy, const void* x, int ldx, float* G, int B, int H, int W, int Cin, int Cout,
+                   int KH, int KW, int dil, void* stream);
 int s2u_conv_weight_pack(const float* w, void* wf, void* wd, int Cout, int Cin, int KH, int KW, int dtype,
                          void* stream);
 

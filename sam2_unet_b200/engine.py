@@ -150,6 +150,23 @@ class Ops:
         _lib.call("s2u_im2col", x.data_ptr(), ldx, out.data_ptr(), B, H, W, Cin, KH, KW, dh, dw, ph, pw, self.dt,
                   self.stream)
 
+    def conv_igemm_ok(self, Cin, N, ldx, ld_out) -> bool:
+        return self.T == torch.bfloat16 and bool(_lib.load().s2u_conv_igemm_supported(Cin, N, ldx, ld_out))
+
+    def conv_igemm(self, x, ldx, B, H, W, Cin, wm, N, KH, KW, dil, out, ld_out, bias=None, resid=None, ld_res=0,
+                   relu=False, sums=None):
+        """out = epi(conv(x, wm)) without an im2col matrix; x / out / resid: tensors or raw device pointers."""
+        xp = x.data_ptr() if isinstance(x, torch.Tensor) else x
+        op = out.data_ptr() if isinstance(out, torch.Tensor) else out
+        rp = 0 if resid is None else (resid.data_ptr() if isinstance(resid, torch.Tensor) else resid)
+        _lib.call("s2u_conv_igemm", xp, ldx, B, H, W, Cin, wm.data_ptr(), N, KH, KW, dil, op, ld_out, _ptr(bias), rp,
+                  ld_res, 1 if relu else 0, _ptr(sums), self.stream)
+
+    def conv_wgrad(self, dy, ld_dy, x, ldx, G, B, H, W, Cin, Cout, KH, KW, dil):
+        xp = x.data_ptr() if isinstance(x, torch.Tensor) else x
+        _lib.call("s2u_conv_wgrad", dy.data_ptr(), ld_dy, xp, ldx, G.data_ptr(), B, H, W, Cin, Cout, KH, KW, dil,
+                  self.stream)
+
     def conv_weight_pack(self, w, wf, wd, Cout, Cin, KH, KW):
         _lib.call("s2u_conv_weight_pack", w.data_ptr(), _ptr(wf), _ptr(wd), Cout, Cin, KH, KW, self.dt, self.stream)
 
@@ -242,6 +259,7 @@ class Engine:
         self._refresh = None
         self._streams = None
         self.fuse_adapter = os.environ.get("S2U_FUSE_ADAPTER", "1") != "0"   # adapter + norm1 as one kernel per direction
+        self.igemm = os.environ.get("S2U_CONV_IGEMM", "1") != "0"            # implicit-GEMM convolutions (no im2col)
         self.overlap = self.device.type == "cuda"   # RFB forward/backward on side streams, overlapped with the trunk
 
     # ------------------------------------------------------------------------------------------ weights
@@ -499,42 +517,59 @@ class Engine:
         M = B * H * H
         taps = cs.kh * cs.kw
         esz = x.element_size()
+        xin = x.view(-1)[xoff:] if xoff else x
+        ig = self.igemm and taps > 1 and ops.conv_igemm_ok(cs.cin, 64, ldx, ld_out)
+        col, ldcol, col_ptr_off = None, 0, 0
         if taps == 1:
             col, ldcol = x, ldx
             col_ptr_off = xoff
-        else:
+        elif not ig:
             col = ops.empty(M, taps * cs.cin)
             ph, pw = cs.dil * (cs.kh - 1) // 2, cs.dil * (cs.kw - 1) // 2
-            xin = x.view(-1)[xoff:] if xoff else x
             ops.im2col(xin, ldx, col, B, H, H, cs.cin, cs.kh, cs.kw, cs.dil, cs.dil, ph, pw)
             ldcol, col_ptr_off = taps * cs.cin, 0
-        A = col.view(-1)[col_ptr_off:] if col_ptr_off else col
+        A = None if ig else (col.view(-1)[col_ptr_off:] if col_ptr_off else col)
         if not training and tape is None:
             # inference: BatchNorm (running statistics) folded into the weights and a bias, residual and ReLU in the
             # GEMM epilogue - one launch per conv instead of GEMM + finalize + apply
             wf, shift = self._bn_folded(cs)
             C = out.view(-1)[out_off:] if out_off else out
-            ops.gemm(A, wf, C, bias=shift, resid=resid, ld_res=ld_res, M=M, N=64, K=taps * cs.cin, lda=ldcol,
-                     ldw=taps * cs.cin, ldc=ld_out, flags=(RESID if resid is not None else 0) | (RELU if relu else 0))
+            if ig:
+                ops.conv_igemm(xin, ldx, B, H, H, cs.cin, wf, 64, cs.kh, cs.kw, cs.dil, C, ld_out, bias=shift,
+                               resid=resid, ld_res=ld_res, relu=relu)
+            else:
+                ops.gemm(A, wf, C, bias=shift, resid=resid, ld_res=ld_res, M=M, N=64, K=taps * cs.cin, lda=ldcol,
+                         ldw=taps * cs.cin, ldc=ld_out,
+                         flags=(RESID if resid is not None else 0) | (RELU if relu else 0))
             return
         raw = ops.empty(M, 64)
-        ops.gemm(A, sh[cs.name + ".wf"], raw, M=M, N=64, K=taps * cs.cin, lda=ldcol, ldw=taps * cs.cin, ldc=64)
         ws = self._bn_workspace(cs.bn, 64)
         mean = rstd = None
-        if training:
-            mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
-            ops.bn_stats_finalize(raw, 64, ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"],
-                                  Bf[cs.bn + ".running_mean"], Bf[cs.bn + ".running_var"],
-                                  Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"], mean, rstd, M, 64)
-        else:
+        if ig:
+            # conv + BatchNorm batch statistics in one launch (the epilogue sums the rounded output per channel)
+            ops.conv_igemm(xin, ldx, B, H, H, cs.cin, sh[cs.name + ".wf"], 64, cs.kh, cs.kw, cs.dil, raw, 64,
+                           sums=ws["sums"] if training else None)
+            if training:
+                mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
             ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
                             Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
-                            None, None, M, 64, False)
+                            mean, rstd, M, 64, training)
+        else:
+            ops.gemm(A, sh[cs.name + ".wf"], raw, M=M, N=64, K=taps * cs.cin, lda=ldcol, ldw=taps * cs.cin, ldc=64)
+            if training:
+                mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
+                ops.bn_stats_finalize(raw, 64, ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"],
+                                      Bf[cs.bn + ".running_mean"], Bf[cs.bn + ".running_var"],
+                                      Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"], mean, rstd, M, 64)
+            else:
+                ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
+                                Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
+                                None, None, M, 64, False)
         out_ptr = out.data_ptr() + out_off * esz
         ops.bn_apply(raw, 64, ws["scale"], ws["shift"], resid, ld_res, out_ptr, ld_out, M, 64, relu)
         if tape is not None:
             tape["convs"][cs.name] = dict(col=col, ldcol=ldcol, coff=col_ptr_off, raw=raw, mean=mean, rstd=rstd, B=B,
-                                          H=H)
+                                          H=H, ig=ig, xin=xin, ldx=ldx)
 
     def _rfb_fwd(self, k, f, H, B, training, tape):
         """RFB_modified k on the stage-k feature map f [B*H*H, Cin] (SAM2UNet.py:117-125); returns (dst, ld, H) where
@@ -718,14 +753,24 @@ class Engine:
             yv = y.view(-1)[y_off:] if y_off else y
         ops.bn_bwd(dyv, ld_dy, yv, ld_y, tp["raw"], 64, tp["mean"], tp["rstd"], P[cs.bn + ".weight"], ws["sums"],
                    G[cs.bn + ".weight"], G[cs.bn + ".bias"], ws["c1"], ws["c2"], draw, 64, M, 64)
-        col = tp["col"]
-        colv = col.view(-1)[tp["coff"]:] if tp["coff"] else col
-        ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin, lda=64, ldb=tp["ldcol"],
-                  ldg=taps * cs.cin, q_inner=cs.cin, q_taps=taps)
+        if tp["ig"]:
+            # weight gradient straight from the un-expanded input map (tap-shifted TMA boxes)
+            ops.conv_wgrad(draw, 64, tp["xin"], tp["ldx"], G[cs.name + ".weight"], B, H, H, cs.cin, 64, cs.kh, cs.kw,
+                           cs.dil)
+        else:
+            col = tp["col"]
+            colv = col.view(-1)[tp["coff"]:] if tp["coff"] else col
+            ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin, lda=64, ldb=tp["ldcol"],
+                      ldg=taps * cs.cin, q_inner=cs.cin, q_taps=taps)
         if dst is None:
             return
         dt, ld_d, d_off = dst
         dv = dt.view(-1)[d_off:] if d_off else dt
+        if taps > 1 and self.igemm and ops.conv_igemm_ok(64, cs.cin, 64, ld_d):
+            # input gradient = the same implicit convolution of d(raw) with the flipped / transposed weights
+            ops.conv_igemm(draw, 64, B, H, H, 64, sh[cs.name + ".wd"], cs.cin, cs.kh, cs.kw, cs.dil, dv, ld_d,
+                           resid=dv if accumulate else None, ld_res=ld_d)
+            return
         if taps == 1:
             A, lda = draw, 64
         else:

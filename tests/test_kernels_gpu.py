@@ -687,3 +687,60 @@ def test_adapter_ln_fused(cuda, shape):
         _close(dx, dx_ref, 2e-2, "dx")
         _close(db1 - 0.5, dh1_ref.sum(0), 2e-3, "db1")
         _close(db2 + 0.25, dh2_ref.sum(0), 2e-3, "db2")
+
+
+# ---------------------------------------------------------------------- implicit-GEMM convolution (bf16, no im2col)
+
+@pytest.mark.parametrize("geom", [(2, 11), (3, 22), (1, 44), (2, 88), (1, 19)])
+@pytest.mark.parametrize("conv", CONVS + [(64, 1, 5, 1), (64, 5, 1, 1), (64, 3, 3, 5)])
+def test_conv_igemm(cuda, conv, geom):
+    """s2u_conv_igemm (forward with bias / residual / ReLU and the BatchNorm statistics epilogue, input gradient with
+    accumulation, strided input / output maps) and s2u_conv_wgrad vs F.conv2d autograd (SAM2UNet.py:83-86)."""
+    cin, kh, kw, dil = conv
+    B, H = geom
+    ops = _ops("bf16", cuda)
+    M, taps = B * H * H, kh * kw
+    ldx = cin + 64                                                   # the input is a channel slice of a wider map
+    xbuf = _rand((M, ldx), "bf16", cuda, 1)
+    x = xbuf[:, 64:]
+    w = _rand((64, cin, kh, kw), "fp32", cuda, 2, (cin * taps) ** -0.5)
+    wf, wd = ops.empty(64, taps * cin), ops.empty(cin, taps * 64)
+    ops.conv_weight_pack(w, wf, wd, 64, cin, kh, kw)
+    ph, pw = dil * (kh - 1) // 2, dil * (kw - 1) // 2
+    xr = x.float().reshape(B, H, H, cin).permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.bfloat16().float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, padding=(ph, pw), dilation=dil)
+    refr = ref.permute(0, 2, 3, 1).reshape(M, 64)
+    assert ops.conv_igemm_ok(cin, 64, ldx, 64)
+    # forward + statistics
+    from sam2_unet_b200 import _lib
+    sums = torch.zeros(_lib.load().s2u_bn_ws_doubles(64), dtype=torch.float64, device=cuda)
+    y = ops.empty(M, 64)
+    ops.conv_igemm(xbuf.view(-1)[64:], ldx, B, H, H, cin, wf, 64, kh, kw, dil, y, 64, sums=sums)
+    _close(y, refr, 2e-2, "conv fwd")
+    rep = sums[:16 * 128].view(16, 128).sum(0)
+    yf = y.double()
+    assert torch.allclose(rep[:64], yf.sum(0), rtol=1e-5, atol=1e-3), "BatchNorm sums"
+    assert torch.allclose(rep[64:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3), "BatchNorm sums of squares"
+    # bias + residual + ReLU into a strided output
+    bias, res = _rand((64,), "fp32", cuda, 5), _rand((M, 64), "bf16", cuda, 6)
+    obuf = torch.zeros(M, 256, dtype=torch.bfloat16, device=cuda)
+    ops.conv_igemm(xbuf.view(-1)[64:], ldx, B, H, H, cin, wf, 64, kh, kw, dil, obuf.view(-1)[128:], 256, bias=bias,
+                   resid=res, ld_res=64, relu=True)
+    _close(obuf[:, 128:192], torch.relu(refr + bias + res.float()), 2e-2, "conv fwd epilogue")
+    assert float(obuf[:, :128].abs().max()) == 0.0 and float(obuf[:, 192:].abs().max()) == 0.0
+    # input gradient (accumulating) and weight gradient
+    dy = _rand((M, 64), "bf16", cuda, 3)
+    gx, gw = torch.autograd.grad(ref, (xr, wr), dy.float().view(B, H, H, 64).permute(0, 3, 1, 2))
+    gxr = gx.permute(0, 2, 3, 1).reshape(M, cin)
+    assert ops.conv_igemm_ok(64, cin, 64, cin)
+    dx = ops.empty(M, cin)
+    ops.conv_igemm(dy, 64, B, H, H, 64, wd, cin, kh, kw, dil, dx, cin)
+    _close(dx, gxr, 2e-2, "conv dgrad")
+    base = _rand((M, cin), "bf16", cuda, 7)
+    dx2 = base.clone()
+    ops.conv_igemm(dy, 64, B, H, H, 64, wd, cin, kh, kw, dil, dx2, cin, resid=dx2, ld_res=cin)
+    _close(dx2, gxr + base.float(), 2e-2, "conv dgrad accumulate")
+    G = torch.full((64, cin, kh, kw), 0.25, device=cuda)
+    ops.conv_wgrad(dy, 64, xbuf.view(-1)[64:], ldx, G, B, H, H, cin, 64, kh, kw, dil)
+    _close(G - 0.25, gw, 1e-2, "conv wgrad")
