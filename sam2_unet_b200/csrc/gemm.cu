@@ -343,12 +343,26 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const __grid_constant__ 
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 // ------------------------------------------------------------------------------------------------------------
 
-constexpr int WS_EPI_WARPS = 8;
+#ifndef S2U_EPI_WARPS
+#define S2U_EPI_WARPS 8
+#endif
+constexpr int WS_EPI_WARPS = S2U_EPI_WARPS;            // 8 or 16: 2 or 4 warps per TMEM lane quarter
+constexpr int EPI_PARTS = WS_EPI_WARPS / 4;            // warps sharing a lane quarter take every EPI_PARTS-th 32-column chunk
+constexpr bool EPI_DB = EPI_PARTS == 2;                // side inputs prefetched one chunk ahead (two slots); with four warps
+                                                       // per scheduler the other warps hide that latency and one slot suffices
 constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
 constexpr int EPI_BUF_BYTES = 32 * 64;                 // one staging tile: 32 rows x 64 bytes, 16-byte chunks XOR-swizzled
-// per epilogue warp: side-input slots [chunk parity] (one tile, or two for the fp32 halves of the stream epilogue)
-// + one output tile
-constexpr int epi_warp_bytes(bool f32s) { return (f32s ? 5 : 3) * EPI_BUF_BYTES; }
+// per epilogue warp: side-input slots (one tile, or two for the fp32 halves of the stream epilogue; x2 when
+// double-buffered) + one output tile
+constexpr int epi_warp_bytes(bool f32s) { return ((EPI_DB ? 2 : 1) * (f32s ? 2 : 1) + 1) * EPI_BUF_BYTES; }
+
+constexpr int SMEM_BUDGET = 227 * 1024 - 512;
+constexpr int epi_bytes(bool f32s) { return (WS_EPI_WARPS * epi_warp_bytes(f32s) + 1023) & ~1023; }
+// deepest operand ring (<= 8 stages) that fits next to the epilogue staging
+constexpr int fit_stages(int stage_bytes, bool f32s) {
+  const int n = (SMEM_BUDGET - 1024 - epi_bytes(f32s)) / stage_bytes;
+  return n > 8 ? 8 : n;
+}
 
 template <int BN, int STAGES, bool F32S>
 struct CfgWS {
@@ -443,7 +457,7 @@ struct EpiTiles {
 };
 
 template <int BN, bool F32S>
-__device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, int q, int half, int lane,
+__device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, int q, int part, int lane,
                                               bf16* __restrict__ C, int ldc, int M, int N,
                                               const EpiView<bf16>& epi) {
   const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
@@ -454,15 +468,16 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   const long long ld16 = (dgelu || mulaux) ? epi.ld_aux : epi.ld_res;
   const float* side32 = resid_f32 ? reinterpret_cast<const float*>(epi.resid) : nullptr;
   const bool has_side = side16 != nullptr || side32 != nullptr;
-  const int nch = (BN - half * 32 + 63) / 64;                               // this warp's chunks per tile (0 when BN == 32)
+  constexpr int CSTRIDE = 32 * EPI_PARTS;                                   // column distance between this warp's chunks
+  const int nch = (BN - part * 32 + CSTRIDE - 1) / CSTRIDE;                 // this warp's chunks per tile (may be 0)
   constexpr uint32_t SLOT = (F32S ? 2 : 1) * EPI_BUF_BYTES;                 // one chunk's side input
-  const uint32_t so = stg + 2 * SLOT;                                       // output staging tile
+  const uint32_t so = stg + (EPI_DB ? 2 : 1) * SLOT;                        // output staging tile
 
   auto prefetch = [&](int tile, int ci, int par) {
     const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
-    const int col0 = (tile / t.m_tiles) * BN + half * 32 + ci * 64;
+    const int col0 = (tile / t.m_tiles) * BN + part * 32 + ci * CSTRIDE;
     const int rows_ok = (int)min((long long)32, (long long)M - row0);
-    const int cols_ok = min(min(32, BN - half * 32 - ci * 64), N - col0);
+    const int cols_ok = min(min(32, BN - part * 32 - ci * CSTRIDE), N - col0);
     if (rows_ok <= 0 || cols_ok <= 0) return;
     const uint32_t b = stg + (uint32_t)par * SLOT;
     if (side16) {
@@ -482,7 +497,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   };
 
   uint32_t lt = 0, cc = 0;
-  if (has_side && nch > 0 && t.first < t.num_tiles) prefetch(t.first, 0, 0);
+  if (EPI_DB && has_side && nch > 0 && t.first < t.num_tiles) prefetch(t.first, 0, 0);
   cp_async_commit();
   for (int tile = t.first; tile < t.num_tiles; tile += t.stride, ++lt) {
     const int acc = lt & 1;
@@ -493,12 +508,13 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
     const int rows_ok = (int)min((long long)32, (long long)M - row0);       // may be <= 0
 #pragma unroll 1
     for (int ci = 0; ci < nch; ++ci, ++cc) {
-      const int par = cc & 1;
-      const int c0 = half * 32 + ci * 64, col0 = n0 + c0;
+      const int par = EPI_DB ? (cc & 1) : 0;
+      const int c0 = part * 32 + ci * CSTRIDE, col0 = n0 + c0;
       const int cols_ok = min(min(32, BN - c0), N - col0);                  // tile edge (BN = 144) / matrix edge; may be <= 0
       const bool live = rows_ok > 0 && cols_ok > 0;                         // warp-uniform
-      if (has_side) {                                                       // next chunk's side input
-        if (ci + 1 < nch) prefetch(tile, ci + 1, par ^ 1);
+      if (has_side) {
+        if (!EPI_DB) prefetch(tile, ci, 0);                                 // this chunk's side input (single slot)
+        else if (ci + 1 < nch) prefetch(tile, ci + 1, par ^ 1);             // next chunk's
         else if (tile + t.stride < t.num_tiles) prefetch(tile + t.stride, 0, par ^ 1);
       }
       cp_async_commit();
@@ -510,7 +526,8 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       }
-      cp_async_wait<1>();                                                   // this chunk's side input has landed
+      if (EPI_DB) cp_async_wait<1>();                                       // this chunk's side input has landed
+      else cp_async_wait<0>();
       __syncwarp();
       if (!live) continue;
       const uint32_t h0 = stg + (uint32_t)par * SLOT, h1 = h0 + EPI_BUF_BYTES;   // h1: F32S only
@@ -1060,9 +1077,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN>
 static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
                      const GemmEpi& e, cudaStream_t st) {
+  constexpr int STAGES = fit_stages((BM + BN) * BK * 2, true) > 6 ? 6 : fit_stages((BM + BN) * BK * 2, true);
+  static_assert(STAGES >= 2, "operand ring");
   using cfg = CfgWS<BN, STAGES, true>;            // the larger of the two footprints
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, BM);
@@ -1095,9 +1114,11 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
 
 // CTA-pair kernel: clusters of 2, one pair per TPC
 // STP / STS: operand stages of the compute-dtype and of the stream (fp32 side input: larger staging) instantiation
-template <int BN, int STP, int STS>
+template <int BN>
 static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
                        const GemmEpi& e, cudaStream_t st) {
+  constexpr int STP = fit_stages((BM + BN / 2) * BK * 2, false), STS = fit_stages((BM + BN / 2) * BK * 2, true);
+  static_assert(STP >= 3 && STS >= 3, "operand ring");
   using cfgp = Cfg2<BN, STP, false>;
   using cfgs = Cfg2<BN, STS, true>;
   static_assert(cfgp::SMEM_BYTES <= 227 * 1024 - 512 && cfgs::SMEM_BYTES <= 227 * 1024 - 512, "shared memory budget");
@@ -1281,20 +1302,20 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     }
     if (pair) {
       switch (bn) {
-        case 32: return umma::launch_pair<32, 8, 8>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 64: return umma::launch_pair<64, 8, 7>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 128: return umma::launch_pair<128, 7, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 144: return umma::launch_pair<144, 7, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 192: return umma::launch_pair<192, 6, 5>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-        case 256: return umma::launch_pair<256, 5, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 32: return umma::launch_pair<32>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 64: return umma::launch_pair<64>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 128: return umma::launch_pair<128>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 144: return umma::launch_pair<144>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 192: return umma::launch_pair<192>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+        case 256: return umma::launch_pair<256>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
         default: return S2U_EINVAL;
       }
     }
     switch (bn) {
-      case 32: return umma::launch_ws<32, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 64: return umma::launch_ws<64, 6>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 128: return umma::launch_ws<128, 4>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
-      case 256: return umma::launch_ws<256, 3>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 32: return umma::launch_ws<32>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 64: return umma::launch_ws<64>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 128: return umma::launch_ws<128>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
+      case 256: return umma::launch_ws<256>(a, lda, w, ldw, c, ldc, M, N, K, e, st);
       default: return S2U_EINVAL;
     }
   }

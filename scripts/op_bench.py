@@ -76,5 +76,5 @@ for t, calls, us, key in res:
 for k, v in sorted(by.items(), key=lambda kv: -kv[1]):
     print(f"  {k:28s} {v / 1e3:7.3f} ms {100 * v / tot:5.1f}%")
 print()
-for t, calls, us, key in sorted(res, key=lambda r: -r[0])[:60]:
+for t, calls, us, key in sorted(res, key=lambda r: -r[0])[:400]:
     print(f"{t / 1e3:7.3f} ms  {calls:4d} x {us:7.1f} us  {key[0]:24s} {key[1:]}")
