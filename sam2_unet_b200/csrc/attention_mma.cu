@@ -692,6 +692,339 @@ __global__ void __launch_bounds__(NT, 3) bwd_dkv_kernel(const bf16* __restrict__
 
 
 // ------------------------------------------------------------------------------------------------------------
+// Whole-window variant for windows of <= 64 tokens (Hiera stage 1: 8x8 windows, and the pooled transition into
+// stage 2): the window is ONE 64-row tile, so one CTA = (window, head) does the entire forward or the entire
+// backward with every operand loaded once by cp.async:
+//   * q max-pool: the window's raw q rows are staged in shared memory and pooled there (the pooled loader of the
+//     general kernel issues four dependent global loads per 16 bytes); the backward routes dq to the arg-max from the
+//     same staged rows instead of re-reading global memory;
+//   * backward: dQ part (warp = 16 queries: S, P, dP, D = rowsum(P o dP), dS, dQ = dS K) and dK/dV part (warp = 16
+//     keys: S^T = K Q^T needs no transpose) share the tiles; log-sum-exp and D cross between them through shared
+//     memory instead of the lse / D workspaces, and dK / dV / dQ leave through the dead K / V tiles and a dQ tile with
+//     16-byte row stores.
+// Traffic per call: qkv read once + dqkv written once (the two-kernel path reads qkv twice and O once).
+// ------------------------------------------------------------------------------------------------------------
+
+// raw q rows of the window's real tokens (row-major in the real extent) -> Qraw by cp.async; rows beyond: zero
+template <int HDP>
+__device__ __forceinline__ void load_qraw(bf16* dst, const bf16* qkv, const Geom& g, const Win& w, int head) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  bf16* d = dst + r * LD;
+  if (r < w.n_real) {
+    const int ty = r / w.rw, tx = r - ty * w.rw;
+    const bf16* src = qkv + (((long long)w.b * g.H + (w.wy * g.wh + ty)) * g.W + (w.wx * g.ww + tx)) *
+                                (3LL * g.nh * g.hd) + head * g.hd;
+#pragma unroll
+    for (int c = par; c < CH; c += 2) {
+      if (c * 8 < g.hd) cp_async16(d + c * 8, src + c * 8);
+      else *reinterpret_cast<uint4*>(d + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int c = par; c < CH; c += 2) *reinterpret_cast<uint4*>(d + c * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+// Qs[pooled query] = max over its 2x2 raw rows (real extents are even when pooling); rows beyond nq: zero
+template <int HDP>
+__device__ __forceinline__ void pool_q_smem(bf16* Qs, const bf16* Qraw, const Win& w) {
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  if (r < w.nq) {
+    const int py = r / w.qrw, px = r - py * w.qrw;
+    const bf16* s0 = Qraw + ((2 * py) * w.rw + 2 * px) * LD;
+    const bf16* s1 = s0 + w.rw * LD;
+#pragma unroll
+    for (int c = par; c < CH; c += 2)
+      *reinterpret_cast<uint4*>(Qs + r * LD + c * 8) =
+          max8(max8(*reinterpret_cast<const uint4*>(s0 + c * 8), *reinterpret_cast<const uint4*>(s0 + LD + c * 8)),
+               max8(*reinterpret_cast<const uint4*>(s1 + c * 8), *reinterpret_cast<const uint4*>(s1 + LD + c * 8)));
+  } else {
+#pragma unroll
+    for (int c = par; c < CH; c += 2) *reinterpret_cast<uint4*>(Qs + r * LD + c * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(NT, 3) fwd_w64_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                       bf16* __restrict__ out, float* __restrict__ lse, Geom g) {
+  pdl_sync();
+  constexpr int LD = HDP + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + BM * LD;
+  bf16* Vs = Ks + BN * LD;
+  bf16* Qraw = Vs + BN * LD;                                    // pooling only
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.z;
+  const Win w = make_win(g, blockIdx.y);
+  const int nk = w.nk;
+  const float sl2 = g.scale * 1.4426950408889634f;
+  if (g.pool) load_qraw<HDP>(Qraw, qkv, g, w, head);
+  else load_q<HDP>(Qs, qkv, bias, g, w, head, 0);
+  load_kv<HDP>(Ks, Vs, qkv, bias, g, w, head, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (g.pool) {
+    pool_q_smem<HDP>(Qs, Qraw, w);
+    __syncthreads();
+  }
+  if (warp * 16 >= w.nq) return;                                // no barrier below
+  float s[8][4];
+  mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
+  float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = j * 8 + 2 * (lane & 3);
+    if (c == w.n_real) { s[j][0] += w.bonus; s[j][2] += w.bonus; }
+    if (c + 1 == w.n_real) { s[j][1] += w.bonus; s[j][3] += w.bonus; }
+    if (c >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+    if (c + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+    t0 = fmaxf(t0, fmaxf(s[j][0], s[j][1]));
+    t1 = fmaxf(t1, fmaxf(s[j][2], s[j][3]));
+  }
+  t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+  t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+  t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+  t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+  float p0 = 0.f, p1 = 0.f;
+  const float b0 = -t0 * sl2, b1 = -t1 * sl2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j][0] = ex2(fmaf(s[j][0], sl2, b0));
+    s[j][1] = ex2(fmaf(s[j][1], sl2, b0));
+    s[j][2] = ex2(fmaf(s[j][2], sl2, b1));
+    s[j][3] = ex2(fmaf(s[j][3], sl2, b1));
+    p0 += s[j][0] + s[j][1];
+    p1 += s[j][2] + s[j][3];
+  }
+  p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+  p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+  p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+  p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int j = 0; j < HDP / 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[j][t] = 0.f;
+  mm_p_b<HDP>(o, s, Vs, lane);
+  const int C = g.nh * g.hd;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int row = warp * 16 + (lane >> 2) + half * 8;
+    const long long tok = out_token(g, w, row);
+    if (tok < 0) continue;
+    const float inv = 1.f / (half ? p1 : p0);
+    bf16* orow = out + tok * C + head * g.hd;
+#pragma unroll
+    for (int j = 0; j < HDP / 8; ++j) {
+      const int d = j * 8 + 2 * (lane & 3);
+      if (d < g.hd)
+        *reinterpret_cast<__nv_bfloat162*>(orow + d) = __floats2bfloat162_rn(o[j][half * 2] * inv, o[j][half * 2 + 1] * inv);
+    }
+    if ((lane & 3) == 0) lse[tok * g.nh + head] = (half ? t1 : t0) * g.scale + __logf(half ? p1 : p0);
+  }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(NT, 3) bwd_w64_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                       const bf16* __restrict__ dout, bf16* __restrict__ dqkv, Geom g) {
+  pdl_sync();
+  constexpr int LD = HDP + 8, CH = HDP / 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Ks = Qs + BM * LD;
+  bf16* Vs = Ks + BN * LD;
+  bf16* dOs = Vs + BN * LD;
+  bf16* Ts = dOs + BM * LD;                                     // dQ tile
+  bf16* Qraw = Ts + BM * LD;                                    // pooling only
+  __shared__ float Lsm[BM], Dsm[BM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.z;
+  const Win w = make_win(g, blockIdx.y);
+  const int nk = w.nk;
+  const float sl2 = g.scale * 1.4426950408889634f;
+  if (g.pool) load_qraw<HDP>(Qraw, qkv, g, w, head);
+  else load_q<HDP>(Qs, qkv, bias, g, w, head, 0);
+  load_kv<HDP>(Ks, Vs, qkv, bias, g, w, head, 0);
+  load_o<HDP>(dOs, dout, g, w, head, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (g.pool) {
+    pool_q_smem<HDP>(Qs, Qraw, w);
+    __syncthreads();
+  }
+  const int r0 = warp * 16 + (lane >> 2);
+  // ---- part 1: this warp's 16 queries
+  {
+    float s[8][4], dp[8][4];
+    mm_ab_t<HDP>(s, Qs, Ks, warp, lane);
+    mm_ab_t<HDP>(dp, dOs, Vs, warp, lane);
+    float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = j * 8 + 2 * (lane & 3);
+      if (c == w.n_real) { s[j][0] += w.bonus; s[j][2] += w.bonus; }
+      if (c + 1 == w.n_real) { s[j][1] += w.bonus; s[j][3] += w.bonus; }
+      if (c >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (c + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      t0 = fmaxf(t0, fmaxf(s[j][0], s[j][1]));
+      t1 = fmaxf(t1, fmaxf(s[j][2], s[j][3]));
+    }
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+    float p0 = 0.f, p1 = 0.f;
+    const float b0 = -t0 * sl2, b1 = -t1 * sl2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = ex2(fmaf(s[j][0], sl2, b0));
+      s[j][1] = ex2(fmaf(s[j][1], sl2, b0));
+      s[j][2] = ex2(fmaf(s[j][2], sl2, b1));
+      s[j][3] = ex2(fmaf(s[j][3], sl2, b1));
+      p0 += s[j][0] + s[j][1];
+      p1 += s[j][2] + s[j][3];
+    }
+    p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+    p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+    const float i0 = 1.f / p0, i1 = 1.f / p1;
+    float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] *= i0; s[j][1] *= i0; s[j][2] *= i1; s[j][3] *= i1;
+      D0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
+      D1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
+    }
+    D0 += __shfl_xor_sync(0xffffffffu, D0, 1);
+    D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+    D1 += __shfl_xor_sync(0xffffffffu, D1, 1);
+    D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+    if ((lane & 3) == 0) {
+      // log2-domain log-sum-exp of the row (infinite for rows beyond nq: their P^T column is zero in part 2)
+      Lsm[r0] = r0 < w.nq ? t0 * sl2 + __log2f(p0) : INFINITY;
+      Lsm[r0 + 8] = r0 + 8 < w.nq ? t1 * sl2 + __log2f(p1) : INFINITY;
+      Dsm[r0] = D0;
+      Dsm[r0 + 8] = D1;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] *= (dp[j][0] - D0) * g.scale;
+      s[j][1] *= (dp[j][1] - D0) * g.scale;
+      s[j][2] *= (dp[j][2] - D1) * g.scale;
+      s[j][3] *= (dp[j][3] - D1) * g.scale;
+    }
+    float dq[CH][4];
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dq[j][t] = 0.f;
+    mm_p_b<HDP>(dq, s, Ks, lane);
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        *reinterpret_cast<__nv_bfloat162*>(Ts + (r0 + half * 8) * LD + j * 8 + 2 * (lane & 3)) =
+            __floats2bfloat162_rn(dq[j][half * 2], dq[j][half * 2 + 1]);
+  }
+  __syncthreads();
+  // ---- part 2: this warp's 16 keys
+  {
+    float st[8][4], dpt[8][4];
+    mm_ab_t<HDP>(st, Ks, Qs, warp, lane);
+    mm_ab_t<HDP>(dpt, Vs, dOs, warp, lane);
+    float dk[CH][4], dv[CH][4];
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { dk[j][t] = 0.f; dv[j][t] = 0.f; }
+    const bool ka = r0 < w.n_real, kb = r0 + 8 < w.n_real;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = j * 8 + 2 * (lane & 3);
+      const float La = Lsm[c], Lb = Lsm[c + 1];
+      st[j][0] = ka ? ex2(st[j][0] * sl2 - La) : 0.f;
+      st[j][1] = ka ? ex2(st[j][1] * sl2 - Lb) : 0.f;
+      st[j][2] = kb ? ex2(st[j][2] * sl2 - La) : 0.f;
+      st[j][3] = kb ? ex2(st[j][3] * sl2 - Lb) : 0.f;
+    }
+    mm_p_b<HDP>(dv, st, dOs, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = j * 8 + 2 * (lane & 3);
+      const float Da = Dsm[c], Db = Dsm[c + 1];
+      st[j][0] *= (dpt[j][0] - Da) * g.scale;
+      st[j][1] *= (dpt[j][1] - Db) * g.scale;
+      st[j][2] *= (dpt[j][2] - Da) * g.scale;
+      st[j][3] *= (dpt[j][3] - Db) * g.scale;
+    }
+    mm_p_b<HDP>(dk, st, Qs, lane);
+    // this warp's rows of the K / V tiles are read by this warp only: they become the dK / dV staging rows
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int o = (r0 + half * 8) * LD + j * 8 + 2 * (lane & 3);
+        *reinterpret_cast<__nv_bfloat162*>(Ks + o) = __floats2bfloat162_rn(dk[j][half * 2], dk[j][half * 2 + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(Vs + o) = __floats2bfloat162_rn(dv[j][half * 2], dv[j][half * 2 + 1]);
+      }
+  }
+  __syncthreads();
+  // ---- rows out: two threads per row, 16-byte stores
+  const int C = g.nh * g.hd;
+  const long long row3 = 3LL * C;
+  const int r = threadIdx.x >> 1, par = threadIdx.x & 1;
+  if (r < w.n_real) {                                           // (the virtual pad key is the frozen bias: no gradient)
+    const int ty = r / w.rw, tx = r - ty * w.rw;
+    bf16* dst = dqkv + (((long long)w.b * g.H + (w.wy * g.wh + ty)) * g.W + (w.wx * g.ww + tx)) * row3 + head * g.hd;
+#pragma unroll
+    for (int c = par; c < CH; c += 2) {
+      if (c * 8 >= g.hd) continue;
+      *reinterpret_cast<uint4*>(dst + C + c * 8) = *reinterpret_cast<const uint4*>(Ks + r * LD + c * 8);
+      *reinterpret_cast<uint4*>(dst + 2 * C + c * 8) = *reinterpret_cast<const uint4*>(Vs + r * LD + c * 8);
+    }
+    if (!g.pool) {
+#pragma unroll
+      for (int c = par; c < CH; c += 2)
+        if (c * 8 < g.hd) *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(Ts + r * LD + c * 8);
+    } else {
+      // dq of raw token r: the pooled query's gradient where this token is the arg-max of its 2x2 group (first
+      // maximum in scan order, like ATen's max_pool2d backward), zero elsewhere
+      const int py = ty >> 1, px = tx >> 1, me = (ty & 1) * 2 + (tx & 1);
+      const bf16* g0 = Qraw + ((2 * py) * w.rw + 2 * px) * LD;
+      const bf16* src[4] = {g0, g0 + LD, g0 + w.rw * LD, g0 + w.rw * LD + LD};
+      const bf16* dqr = Ts + (py * w.qrw + px) * LD;
+#pragma unroll
+      for (int c = par; c < CH; c += 2) {
+        if (c * 8 >= g.hd) continue;
+        uint4 v[4], o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const uint4*>(src[k] + c * 8);
+        const uint4 dv4 = *reinterpret_cast<const uint4*>(dqr + c * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int best = 0;
+          float vb = __bfloat162float(reinterpret_cast<const bf16*>(&v[0])[e]);
+#pragma unroll
+          for (int k = 1; k < 4; ++k) {
+            const float vk = __bfloat162float(reinterpret_cast<const bf16*>(&v[k])[e]);
+            if (vk > vb) { vb = vk; best = k; }
+          }
+          reinterpret_cast<bf16*>(&o)[e] = best == me ? reinterpret_cast<const bf16*>(&dv4)[e] : __float2bfloat16(0.f);
+        }
+        *reinterpret_cast<uint4*>(dst + c * 8) = o;
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
 // Packed variant for tiny windows (window area <= 16 tokens: Hiera stage 2 and its transition block): one CTA serves
 // FOUR windows of one head, warp w <-> window w (a warp's 16 MMA rows are exactly one window's query slot), so the
 // score tile of a window is a single 16x16 MMA block and nothing is wasted on cross-window pairs.  The backward is ONE
@@ -977,6 +1310,14 @@ static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse,
     S2U_LAUNCH_CHECK();
     return 0;
   }
+  if (g.wh * g.ww <= BN && g.pool) {                           // one tile per window: raw q staged and pooled in smem
+    dim3 wgrid(1, g.B * g.nwy * g.nwx, g.nh);
+    const size_t wsmem = (size_t)(BM + 3 * BN) * (HDP + 8) * sizeof(bf16);
+    S2U_ALLOW_SMEM(fwd_w64_kernel<HDP>);
+    S2U_LAUNCH((fwd_w64_kernel<HDP>), wgrid, NT, wsmem, st, qkv, bias, out, lse, g);
+    S2U_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(ceil_div(g.qh * g.qw, BM), g.B * g.nwy * g.nwx, g.nh);
   const size_t smem = (size_t)(BM + 4 * BN) * (HDP + 8) * sizeof(bf16);
   S2U_ALLOW_SMEM(fwd_kernel<HDP>);
@@ -993,6 +1334,14 @@ static int launch_bwd(const bf16* qkv, const float* bias, const bf16* out, const
     const size_t psmem = (size_t)(4 * BM * (HDP + 8) + 4 * 2 * 16 * 24) * sizeof(bf16);
     S2U_ALLOW_SMEM(bwd_packed_kernel<HDP>);
     S2U_LAUNCH((bwd_packed_kernel<HDP>), pgrid, NT, psmem, st, qkv, bias, dout, dqkv, g);
+    S2U_LAUNCH_CHECK();
+    return 0;
+  }
+  if (g.wh * g.ww <= BN) {                                     // whole window in one tile: fused single kernel
+    dim3 wgrid(1, g.B * g.nwy * g.nwx, g.nh);
+    const size_t wsmem = (size_t)((g.pool ? 3 : 2) * BM + 3 * BN) * (HDP + 8) * sizeof(bf16);
+    S2U_ALLOW_SMEM(bwd_w64_kernel<HDP>);
+    S2U_LAUNCH((bwd_w64_kernel<HDP>), wgrid, NT, wsmem, st, qkv, bias, dout, dqkv, g);
     S2U_LAUNCH_CHECK();
     return 0;
   }

@@ -272,6 +272,9 @@ ATTN_CASES = [  # B, H, W, nh, hd, window, pool
     (1, 12, 12, 2, 32, 4, True), (2, 10, 10, 1, 32, 6, True), (1, 5, 5, 2, 56, 3, False), (1, 22, 22, 2, 96, 14, False),
     # tiny windows (packed 4-per-CTA kernels): Hiera-L stage 2, its q-pool transition, ragged window counts
     (2, 44, 44, 4, 72, 4, False), (1, 44, 44, 8, 72, 4, True), (3, 12, 12, 2, 96, 4, False), (1, 6, 10, 1, 32, 4, False),
+    # whole-window kernels (17..64 tokens per window): ragged maps, pooled ragged, odd window, other head dims
+    (1, 20, 12, 4, 72, 8, True), (1, 12, 20, 2, 72, 8, False), (1, 24, 24, 1, 80, 8, False), (1, 14, 14, 2, 64, 7, False),
+    (1, 88, 88, 2, 72, 8, False), (1, 88, 88, 4, 72, 8, True),
 ]
 
 
