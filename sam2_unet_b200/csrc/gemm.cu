@@ -354,7 +354,9 @@ constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
 constexpr int EPI_BUF_BYTES = 32 * 64;                 // one staging tile: 32 rows x 64 bytes, 16-byte chunks XOR-swizzled
 // per epilogue warp: side-input slots (one tile, or two for the fp32 halves of the stream epilogue; x2 when
 // double-buffered) + one output tile
-constexpr int epi_warp_bytes(bool f32s) { return ((EPI_DB ? 2 : 1) * (f32s ? 2 : 1) + 1) * EPI_BUF_BYTES; }
+// + two 128-byte bias segments (the chunk's 32 bias values, prefetched with the side input)
+constexpr int EPI_BIAS_BYTES = 256;
+constexpr int epi_warp_bytes(bool f32s) { return ((EPI_DB ? 2 : 1) * (f32s ? 2 : 1) + 1) * EPI_BUF_BYTES + EPI_BIAS_BYTES; }
 
 constexpr int SMEM_BUDGET = 227 * 1024 - 512;
 constexpr int epi_bytes(bool f32s) { return (WS_EPI_WARPS * epi_warp_bytes(f32s) + 1023) & ~1023; }
@@ -468,10 +470,12 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   const long long ld16 = (dgelu || mulaux) ? epi.ld_aux : epi.ld_res;
   const float* side32 = resid_f32 ? reinterpret_cast<const float*>(epi.resid) : nullptr;
   const bool has_side = side16 != nullptr || side32 != nullptr;
+  const bool has_pf = has_side || epi.bias != nullptr;                      // anything to prefetch per chunk
   constexpr int CSTRIDE = 32 * EPI_PARTS;                                   // column distance between this warp's chunks
   const int nch = (BN - part * 32 + CSTRIDE - 1) / CSTRIDE;                 // this warp's chunks per tile (may be 0)
   constexpr uint32_t SLOT = (F32S ? 2 : 1) * EPI_BUF_BYTES;                 // one chunk's side input
   const uint32_t so = stg + (EPI_DB ? 2 : 1) * SLOT;                        // output staging tile
+  const uint32_t sbias = so + EPI_BUF_BYTES;                                // [parity][32] bias values of a chunk
 
   auto prefetch = [&](int tile, int ci, int par) {
     const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
@@ -480,6 +484,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
     const int cols_ok = min(min(32, BN - part * 32 - ci * CSTRIDE), N - col0);
     if (rows_ok <= 0 || cols_ok <= 0) return;
     const uint32_t b = stg + (uint32_t)par * SLOT;
+    // the chunk's bias segment: a __ldg right before the add cost ~9 % of the kernel in L2 round trips (ncu, long
+    // scoreboard on the first FADD of every chunk)
+    if (epi.bias && lane * 4 < cols_ok) cp_async16(sbias + (uint32_t)(par * 128 + lane * 16), epi.bias + col0 + lane * 4);
+    if (!has_side) return;
     if (side16) {
       g2s_async(b, reinterpret_cast<const char*>(side16 + row0 * ld16 + col0), ld16 * 2, rows_ok, cols_ok * 2, lane);
     } else {
@@ -497,7 +505,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   };
 
   uint32_t lt = 0, cc = 0;
-  if (EPI_DB && has_side && nch > 0 && t.first < t.num_tiles) prefetch(t.first, 0, 0);
+  if (EPI_DB && has_pf && nch > 0 && t.first < t.num_tiles) prefetch(t.first, 0, 0);
   cp_async_commit();
   for (int tile = t.first; tile < t.num_tiles; tile += t.stride, ++lt) {
     const int acc = lt & 1;
@@ -512,7 +520,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
       const int c0 = part * 32 + ci * CSTRIDE, col0 = n0 + c0;
       const int cols_ok = min(min(32, BN - c0), N - col0);                  // tile edge (BN = 144) / matrix edge; may be <= 0
       const bool live = rows_ok > 0 && cols_ok > 0;                         // warp-uniform
-      if (has_side) {
+      if (has_pf) {
         if (!EPI_DB) prefetch(tile, ci, 0);                                 // this chunk's side input (single slot)
         else if (ci + 1 < nch) prefetch(tile, ci + 1, par ^ 1);             // next chunk's
         else if (tile + t.stride < t.num_tiles) prefetch(tile + t.stride, 0, par ^ 1);
@@ -531,17 +539,12 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
       __syncwarp();
       if (!live) continue;
       const uint32_t h0 = stg + (uint32_t)par * SLOT, h1 = h0 + EPI_BUF_BYTES;   // h1: F32S only
-      if (epi.bias) {
-        if (cols_ok == 32) {
+      if (epi.bias) {                                                       // (columns >= cols_ok: never stored)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
-            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
+        for (int j = 0; j < 8; ++j) {
+          const uint4 b4 = lds16(sbias + (uint32_t)(par * 128 + j * 16));
+          v[4 * j] += __uint_as_float(b4.x); v[4 * j + 1] += __uint_as_float(b4.y);
+          v[4 * j + 2] += __uint_as_float(b4.z); v[4 * j + 3] += __uint_as_float(b4.w);
         }
       }
       if ((epi.flags & GEMM_GELU) && epi.pre_out && !pre_final && (epi.flags & GEMM_SAVE_DGELU)) {
