@@ -280,11 +280,156 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, int ld_dy, const T
   }
 }
 
+// BatchNorm backward in ONE pass over the inputs (C = 64, bf16): a persistent grid of at most one CTA per SM keeps
+// its rows' g = dy * (y > 0) and x in shared memory between the reduction and the apply phase, which are separated
+// by a grid-wide barrier (every CTA is resident: the grid never exceeds the SM count and a CTA needs one SM's worth of
+// nothing but shared memory; dependents of a programmatic launch cannot start before every CTA of this grid has).
+// Traffic: dy, y, x read once + dx written (the two-kernel path reads them twice).
+// `sums` layout as above; the two words after the accumulators are the barrier counter and the exit ticket.
+constexpr int BNF_THREADS = 512;
+__global__ void __launch_bounds__(BNF_THREADS, 1)
+bn_bwd_fused_kernel(const bf16* __restrict__ dy, int ld_dy, const bf16* __restrict__ y, int ld_y,
+                    const bf16* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, double* __restrict__ sums, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, bf16* __restrict__ dx, int ld_dx, long long M, int rows_per_cta) {
+  constexpr int C = 64, CG = 8, NSUB = BNF_THREADS / CG;
+  pdl_sync();
+  extern __shared__ __align__(16) uint8_t bnf_smem[];
+  uint4* gs = reinterpret_cast<uint4*>(bnf_smem);                      // [rows][8] masked gradient (8 bf16 each)
+  uint4* xs = gs + (size_t)rows_per_cta * CG;                           // [rows][8] conv output
+  float* red = reinterpret_cast<float*>(xs + (size_t)rows_per_cta * CG);   // [NSUB][2C], later coef[2C]
+  const int g = threadIdx.x % CG, sub = threadIdx.x / CG;
+  const long long r_beg = (long long)blockIdx.x * rows_per_cta;
+  const long long r_end = min(M, r_beg + rows_per_cta);
+  const F8 mu = ld8(mean + g * 8), rs = ld8(rstd + g * 8);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  for (long long r0 = r_beg + sub; r0 < r_end; r0 += 4 * NSUB) {
+    uint4 d[4], v[4], yy[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * NSUB;
+      if (r < r_end) {
+        d[u] = *reinterpret_cast<const uint4*>(dy + r * ld_dy + g * 8);
+        v[u] = *reinterpret_cast<const uint4*>(x + r * ldx + g * 8);
+        if (y) yy[u] = *reinterpret_cast<const uint4*>(y + r * ld_y + g * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * NSUB;
+      if (r >= r_end) continue;
+      __nv_bfloat162* dh = reinterpret_cast<__nv_bfloat162*>(&d[u]);
+      const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+      const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yy[u]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 df = __bfloat1622float2(dh[e]);
+        const float2 vf = __bfloat1622float2(vh[e]);
+        if (y) {
+          const float2 yf = __bfloat1622float2(yh[e]);
+          if (!(yf.x > 0.f)) df.x = 0.f;
+          if (!(yf.y > 0.f)) df.y = 0.f;
+          dh[e] = __floats2bfloat162_rn(df.x, df.y);
+        }
+        s[2 * e] += df.x;
+        s[2 * e + 1] += df.y;
+        q[2 * e] = fmaf(df.x, (vf.x - mu.v[2 * e]) * rs.v[2 * e], q[2 * e]);
+        q[2 * e + 1] = fmaf(df.y, (vf.y - mu.v[2 * e + 1]) * rs.v[2 * e + 1], q[2 * e + 1]);
+      }
+      gs[(r - r_beg) * CG + g] = d[u];
+      xs[(r - r_beg) * CG + g] = v[u];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[sub * 2 * C + g * 8 + j] = s[j];
+    red[sub * 2 * C + C + g * 8 + j] = q[j];
+  }
+  __syncthreads();
+  double* rep = sums + (size_t)(blockIdx.x % BN_NREP) * 2 * C;
+  if (threadIdx.x < 2 * C) {
+    float t = 0.f;
+    for (int k = 0; k < NSUB; ++k) t += red[k * 2 * C + threadIdx.x];
+    atomicAdd(rep + threadIdx.x, (double)t);
+  }
+  // ---- grid barrier
+  unsigned int* bar = reinterpret_cast<unsigned int*>(sums + BN_NREP * 2 * C);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(bar) < gridDim.x) {
+      if (clock64() - t0 > 4000000000LL) __trap();            // a missing CTA must fail loudly, not hang
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- totals -> per-channel coefficients (every CTA), parameter gradients (the last CTA to get here)
+  float* coef = red;                                           // [0,C): sum g / M, [C,2C): sum g xhat / M
+  if (threadIdx.x < 2 * C) {
+    double t = 0.0;
+    const volatile double* vs = sums;
+#pragma unroll
+    for (int r = 0; r < BN_NREP; ++r) t += vs[r * 2 * C + threadIdx.x];
+    coef[threadIdx.x] = (float)(t / (double)M);
+    red[2 * C + threadIdx.x] = (float)t;
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(bar + 1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {                                                  // everyone has read the totals: clear for the next use
+    if (threadIdx.x < C) {
+      dbeta[threadIdx.x] += red[2 * C + threadIdx.x];
+      dgamma[threadIdx.x] += red[2 * C + C + threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < BN_NREP * 2 * C; i += BNF_THREADS) sums[i] = 0.0;
+    if (threadIdx.x == 0) { bar[0] = 0u; bar[1] = 0u; }
+  }
+  const F8 ga = ld8(gamma + g * 8);
+  float k0[8], k1[8], k2[8];                                   // dx = k0 * g - k1 - k2 * (x - mean)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float gr = ga.v[j] * rs.v[j];
+    k0[j] = gr;
+    k1[j] = gr * coef[g * 8 + j];
+    k2[j] = gr * coef[C + g * 8 + j] * rs.v[j];
+  }
+  for (long long r = r_beg + sub; r < r_end; r += NSUB) {
+    const uint4 d = gs[(r - r_beg) * CG + g], v = xs[(r - r_beg) * CG + g];
+    const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+    const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 df = __bfloat1622float2(dh[e]), vf = __bfloat1622float2(vh[e]);
+      oh[e] = __floats2bfloat162_rn(fmaf(k0[2 * e], df.x, -fmaf(k2[2 * e], vf.x - mu.v[2 * e], k1[2 * e])),
+                                    fmaf(k0[2 * e + 1], df.y, -fmaf(k2[2 * e + 1], vf.y - mu.v[2 * e + 1], k1[2 * e + 1])));
+    }
+    *reinterpret_cast<uint4*>(dx + r * ld_dx + g * 8) = o;
+  }
+}
+
 static inline int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   if (g > 148LL * 16) g = 148LL * 16;
   if (g < 1) g = 1;
   return (int)g;
+}
+static inline bool bn_fused_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("S2U_BN_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 static inline bool bn_c_ok(int C) { return C >= 8 && (C & 7) == 0 && (C >> 3) <= 256; }
 // reduction grid: every block gets at least BN_UNROLL rows per row lane, at most 4 blocks per SM
@@ -299,7 +444,7 @@ static inline int bn_reduce_grid(long long M, int C) {
 extern "C" {
 
 // size of the fp64 workspace `sums` of the functions below (replicated accumulators + ticket)
-int s2u_bn_ws_doubles(int C) { return BN_NREP * 2 * C + 1; }
+int s2u_bn_ws_doubles(int C) { return BN_NREP * 2 * C + 2; }
 
 // statistics only (the caller finalises with s2u_bn_finalize)
 int s2u_bn_stats(const void* x, int ldx, double* sums, long long M, int C, int dtype, void* stream) {
@@ -372,6 +517,26 @@ int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x
                void* dx, int ld_dx, long long M, int C, int dtype, void* stream) {
   if (M <= 0 || !bn_c_ok(C) || (ldx & 7) || (ld_dy & 7) || (ld_dx & 7) || (y && (ld_y & 7))) return S2U_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == S2U_BF16 && C == 64 && bn_fused_enabled()) {
+    // one pass: the rows stay in shared memory across a grid barrier (fits when M / #SMs rows x 256 B <= ~190 KB)
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int rows = (int)((M + sms - 1) / sms);
+    if (rows < 64) rows = 64;
+    const int grid = (int)((M + rows - 1) / rows);
+    const size_t fsmem = (size_t)rows * 256 + (size_t)(BNF_THREADS / 8) * 2 * 64 * sizeof(float) + 3 * 64 * sizeof(float);
+    if (fsmem <= 200 * 1024) {
+      S2U_ALLOW_SMEM(bn_bwd_fused_kernel);
+      S2U_LAUNCH((bn_bwd_fused_kernel), grid, BNF_THREADS, fsmem, st, (const bf16*)dy, ld_dy, (const bf16*)y, ld_y,
+                 (const bf16*)x, ldx, mean, rstd, gamma, sums, dgamma, dbeta, (bf16*)dx, ld_dx, M, rows);
+      S2U_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const int nsub = 256 / (C >> 3);
   const size_t smem = (size_t)nsub * 2 * C * sizeof(float);
   S2U_DISPATCH_T(dtype, {

@@ -385,7 +385,7 @@ def test_conv_im2col_gemm(cuda, dtype, conv):
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("relu", [False, True])
-@pytest.mark.parametrize("M", [2 * 11 * 11, 12 * 44 * 44 + 3])
+@pytest.mark.parametrize("M", [2 * 11 * 11, 12 * 44 * 44 + 3, 12 * 88 * 88])
 def test_batchnorm(cuda, dtype, relu, M):
     from sam2_unet_b200 import _lib
     ops = _ops(dtype, cuda)
@@ -425,6 +425,7 @@ def test_batchnorm(cuda, dtype, relu, M):
     _close(dx, gx, _tol(dtype, 2e-4, 3e-2), "bn dx")
     _close(dg, gg, _tol(dtype, 2e-4, 2e-2), "bn dgamma")
     _close(db, gb, _tol(dtype, 2e-4, 2e-2), "bn dbeta")
+    assert float(sums.abs().max()) == 0.0, "workspace (accumulators, barrier words) must be left zeroed"
     # eval mode uses the running statistics
     ops.bn_finalize(sums, g, b, rm, rv, nbt, scale, shift, None, None, M, C, False)
     ops.bn_apply(x, C, scale, shift, None, 0, y, C, M, C, False)
