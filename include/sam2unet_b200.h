@@ -38,6 +38,10 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
              int ld_res, int flags, int dtype, int backend, void* stream);
 /* G[P,Q] += A[M,P]^T . B[M,Q] (fp32 G): weight gradients of the adapters (SAM2UNet.py:57-59) and convs
  * (SAM2UNet.py:72-80); q_inner/q_taps map q = tap*Cin+ci to the [Cout,Cin,kh,kw] parameter layout (0,0: plain). */
+/* Number of bf16 GEMM / weight-gradient calls so far that backend 0 routed to the fp32-FMA kernels because the
+ * TMA / tcgen05 path cannot describe them (pointer or pitch alignment); reset != 0 clears the counter.  0 on every
+ * shape of the Hiera trunks. */
+int s2u_gemm_simt_fallbacks(int reset);
 int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int ldg, long long M, int P, int Q,
                    int q_inner, int q_taps, int dtype, void* stream);
 /* Two weight gradients sharing the row count M in one launch (an adapter's dW2 and dW1, SAM2UNet.py:57-59): G0 +=

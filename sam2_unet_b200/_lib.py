@@ -17,6 +17,7 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 # name -> argument ctypes, mirrors include/sam2unet_b200.h (tests check both against the .so)
 SIGNATURES = {
     "s2u_gemm": [P, I, P, I, P, I, I, I, I, P, P, I, P, I, P, I, I, I, I, P],
+    "s2u_gemm_simt_fallbacks": [I],
     "s2u_gemm_wgrad": [P, I, P, I, P, I, L, I, I, I, I, I, P],
     "s2u_gemm_wgrad_pair": [P, I, P, I, P, I, I, I, P, I, P, I, P, I, I, I, L, I, P],
     "s2u_colsum": [P, I, P, L, I, I, P],

@@ -12,6 +12,7 @@
 //                         1e-3 parity bar, SURVEY.md section 7 hard part 6) and for operand shapes the TMA
 //                         path cannot describe (row pitch not a multiple of 16 bytes).
 #include <cuda.h>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -1251,7 +1252,16 @@ static int launch_wgrad(const WgProblem* probs, int nprob, long long M, cudaStre
 
 // ------------------------------------------------------------------------------------------- C ABI
 
+// bf16 problems that backend 0 had to route to the fp32-FMA kernels because the TMA / tcgen05 path cannot describe
+// them (alignment, pitch): ~50x slower, so it is counted and reported instead of happening silently
+static std::atomic<long long> g_simt_fallbacks{0};
+
 extern "C" {
+
+int s2u_gemm_simt_fallbacks(int reset) {
+  const long long n = reset ? g_simt_fallbacks.exchange(0) : g_simt_fallbacks.load();
+  return n > 0x7fffffffLL ? 0x7fffffff : (int)n;
+}
 
 // backend: 0 = auto (tcgen05 for bf16 when describable, else SIMT), 1 = force SIMT, 2 = force tcgen05,
 //          16+bn = force tcgen05 with tile width bn (32/64/128/256; tuning and tests),
@@ -1323,6 +1333,7 @@ int s2u_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, i
     }
   }
   if (backend >= 2) return S2U_EUNSUPPORTED;
+  if (want_umma) g_simt_fallbacks.fetch_add(1);
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
   S2U_DISPATCH_T(dtype, {
     S2U_LAUNCH((gemm_simt_kernel<T>), grid, 256, 0, st, (const T*)A, lda, (const T*)W, ldw, (T*)C, ldc, M, N, K, EpiView<T>(e));
@@ -1341,6 +1352,7 @@ int s2u_gemm_wgrad(const void* A, int lda, const void* B, int ldb, float* G, int
     const int rc = umma::launch_wgrad(&pr, 1, M, (cudaStream_t)stream);
     if (rc != S2U_EUNSUPPORTED) return rc;
   }
+  if (dtype == S2U_BF16) g_simt_fallbacks.fetch_add(1);
   const int tiles = ceil_div(P, 64) * ceil_div(Q, 64);
   int splits = (int)((M + 255) / 256);
   const int want = (4 * 148 + tiles - 1) / tiles;

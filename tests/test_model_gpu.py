@@ -261,13 +261,16 @@ def test_hiera_l_bf16_train_step_vs_oracle(cuda):
     masks"): scripts/debug_bf16_grads.py shows the trunk's forward error staying at 0.3-0.7 % per block while the
     gradient distance of e.g. rfb4 moves between 0.12 and 0.43 when nothing but the attention kernel family changes."""
     from oracle import port
-    from sam2_unet_b200 import structure_loss
+    from sam2_unet_b200 import _lib, structure_loss
     m, sd = _build("sam2_hiera_l.yaml", "bf16", cuda)
     m.train()
     x, mask = port.synthetic_batch(12, 352, seed=3)
+    simt0 = _lib.load().s2u_gemm_simt_fallbacks(0)
     outs = m(x.to(cuda))
     loss = sum(structure_loss(o, mask.to(cuda)) for o in outs)
     loss.backward()
+    # every GEMM / weight gradient of the benchmarked configuration runs on the tcgen05 kernels
+    assert _lib.load().s2u_gemm_simt_fallbacks(0) == simt0, "a bf16 GEMM fell back to the fp32-FMA kernel"
     torch.set_num_threads(os.cpu_count() or 1)
     loss_ref, _, grads_ref = port.loss_and_grads(sd, port.TRUNKS["l"], x, mask, True, port.BNState())
     assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
