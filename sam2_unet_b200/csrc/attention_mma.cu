@@ -1310,9 +1310,9 @@ static int launch_fwd(const bf16* qkv, const float* bias, bf16* out, float* lse,
     S2U_LAUNCH_CHECK();
     return 0;
   }
-  if (g.wh * g.ww <= BN && g.pool) {                           // one tile per window: raw q staged and pooled in smem
+  if (g.wh * g.ww <= BN) {                                     // one tile per window (pooling: raw q staged and pooled in smem)
     dim3 wgrid(1, g.B * g.nwy * g.nwx, g.nh);
-    const size_t wsmem = (size_t)(BM + 3 * BN) * (HDP + 8) * sizeof(bf16);
+    const size_t wsmem = (size_t)(BM + (g.pool ? 3 : 2) * BN) * (HDP + 8) * sizeof(bf16);
     S2U_ALLOW_SMEM(fwd_w64_kernel<HDP>);
     S2U_LAUNCH((fwd_w64_kernel<HDP>), wgrid, NT, wsmem, st, qkv, bias, out, lse, g);
     S2U_LAUNCH_CHECK();

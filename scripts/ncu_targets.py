@@ -55,7 +55,30 @@ ad = dict(xs=r(R, Cl, dt=f32), W1=r(32, Cl) * Cl ** -0.5, W2=r(Cl, 32) * 32 ** -
 ad["W2t"], ad["W1t"] = ad["W2"].t().contiguous(), ad["W1"].t().contiguous()
 
 
+# implicit-GEMM convolution (3x3, 64 -> 64, dilation 3, 12 x 88 x 88) + its weight gradient, one-pass BatchNorm backward
+Bc, Hc = 12, 88
+cv = dict(x=r(Bc * Hc * Hc, 64), w=r(64, 64, 3, 3, dt=f32) * 0.04, wf=torch.empty(64, 576, device=dev, dtype=bf),
+          wd=torch.empty(64, 576, device=dev, dtype=bf), y=torch.empty(Bc * Hc * Hc, 64, device=dev, dtype=bf),
+          dy=r(Bc * Hc * Hc, 64), dx=torch.empty(Bc * Hc * Hc, 64, device=dev, dtype=bf), G=torch.zeros(64, 64, 3, 3, device=dev))
+ops.conv_weight_pack(cv["w"], cv["wf"], cv["wd"], 64, 64, 3, 3)
+# stage-1 windows (8 x 8 tokens, 2 heads) and the pooled transition block (4 heads): whole-window kernels
+q1, q2 = r(12, 88, 88, 3 * 144), r(12, 88, 88, 3 * 288)
+o1, o2 = torch.empty(12, 88, 88, 144, device=dev, dtype=bf), torch.empty(12, 44, 44, 288, device=dev, dtype=bf)
+l1, l2 = torch.empty(12, 88, 88, 2, device=dev), torch.empty(12, 44, 44, 4, device=dev)
+do1, do2 = r(12, 88, 88, 144), r(12, 44, 44, 288)
+dq1, dq2 = torch.empty_like(q1), torch.empty_like(q2)
+b1a, b2a = r(3 * 144, dt=f32), r(3 * 288, dt=f32)
+
+
 def once():
+    ops.conv_igemm(cv["x"], 64, Bc, Hc, Hc, 64, cv["wf"], 64, 3, 3, 3, cv["y"], 64, sums=bn["sums"])
+    bn["sums"].zero_()
+    ops.conv_igemm(cv["dy"], 64, Bc, Hc, Hc, 64, cv["wd"], 64, 3, 3, 3, cv["dx"], 64)
+    ops.conv_wgrad(cv["dy"], 64, cv["x"], 64, cv["G"], Bc, Hc, Hc, 64, 64, 3, 3, 3)
+    ops.attn_fwd(q1, b1a, o1, l1, 12, 88, 88, 2, 72, 8, False)
+    ops.attn_bwd(q1, b1a, o1, l1, do1, dq1, 12, 88, 88, 2, 72, 8, False)
+    ops.attn_fwd(q2, b2a, o2, l2, 12, 88, 88, 4, 72, 8, True)
+    ops.attn_bwd(q2, b2a, o2, l2, do2, dq2, 12, 88, 88, 4, 72, 8, True)
     ops.adapter_ln_fwd(ad["xs"], ad["W1"], ad["b1"], ad["W2"], ad["b2"], ln["g"], ln["b"], ad["xa"], ad["n1"], ln["mean"],
                        ln["rstd"], ad["u"], ad["g1"], ad["g2"], R, Cl)
     ops.adapter_ln_bwd(ln["dy"], ad["xa"], ln["mean"], ln["rstd"], ln["g"], ln["dres"], ad["g2"], ad["g1"], ad["W2t"],

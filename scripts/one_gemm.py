@@ -9,8 +9,8 @@ from sam2_unet_b200.engine import Ops  # noqa: E402
 
 dev = torch.device("cuda:0")
 ops = Ops(torch.bfloat16, dev)
-M, N, K = 5808, 2304, 576
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 129
+M, N, K = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (5808, 2304, 576)
 A = torch.randn(M, K, device=dev).bfloat16()
 W = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
 bias = torch.randn(N, device=dev)
