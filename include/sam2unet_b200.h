@@ -133,6 +133,12 @@ int s2u_conv_igemm_supported(int Cin, int N, int ldx, int ld_out);
 int s2u_conv_igemm(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int N, int KH, int KW, int dil,
                    void* out, int ld_out, const float* bias, const void* resid, int ld_res, int relu, double* sums,
                    void* stream);
+/* Training forward of conv + BatchNorm batch statistics in ONE launch (N = 64): the CTA that finishes last finalises
+ * scale / shift (for s2u_bn_apply), the saved mean / rstd and the running statistics, like s2u_bn_stats_finalize. */
+int s2u_conv_igemm_bn(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int KH, int KW, int dil,
+                      void* out, int ld_out, double* sums, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long long* num_batches, float* scale, float* shift, float* save_mean,
+                      float* save_rstd, float eps, float momentum, void* stream);
 /* G [Cout][Cin][KH][KW] (fp32, accumulated) += weight gradient of the convolution from the un-expanded activations:
  * dy [B,H,W,Cout <= 64] pitch ld_dy, x [B,H,W,Cin % 64 == 0] pitch ldx (bf16). */
 int s2u_conv_wgrad(const void* dy, int ld_dy, const void* x, int ldx, float* G, int B, int H, int W, int Cin, int Cout,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "s2u_im2col": [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "s2u_conv_igemm_supported": [I, I, I, I],
     "s2u_conv_igemm": [P, I, I, I, I, I, P, I, I, I, I, P, I, P, P, I, I, P, P],
+    "s2u_conv_igemm_bn": [P, I, I, I, I, I, P, I, I, I, P, I, P, P, P, P, P, P, P, P, P, P, F, F, P],
     "s2u_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, P],
     "s2u_conv_weight_pack": [P, P, P, I, I, I, I, I, P],
     "s2u_bn_ws_doubles": [I],

@@ -20,6 +20,7 @@
 // written and read by the im2col formulation it replaces.
 #include <cuda.h>
 
+#include "bn_common.cuh"
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -30,7 +31,6 @@ constexpr int TW = 16, TH = 8;                 // pixel rectangle of one 128-row
 constexpr int BM = 128, BK = 64;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int BN_NREP = 16;                    // replicated fp64 accumulators of bn.cu's workspace
 
 struct Geo {
   int B, H, W, tiles_x, tiles_y;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
                                                                bf16* __restrict__ C, int ldc, Geo g,
                                                                const float* __restrict__ bias,
                                                                const bf16* __restrict__ resid, int ld_res, int relu,
-                                                               double* __restrict__ sums) {
+                                                               double* __restrict__ sums, BnFin fin) {
   using cfg = Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS)
                  : "memory");
   }
+  // BatchNorm finalisation (scale / shift, saved mean / rstd, running statistics) by whichever CTA finishes last
+  if (sums && fin.gamma && last_block(reinterpret_cast<unsigned int*>(sums + BN_NREP * 2 * BN)))
+    bn_finalize_block(sums, fin, (long long)g.B * g.H * g.W, BN, 1);
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradient
@@ -421,7 +424,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <int BN, int STAGES>
 static int launch_igemm(const CUtensorMap& mx, const CUtensorMap& mw, bf16* C, int ldc, const Geo& g, const float* bias,
-                        const bf16* resid, int ld_res, int relu, double* sums, cudaStream_t st) {
+                        const bf16* resid, int ld_res, int relu, double* sums, const BnFin& fin, cudaStream_t st) {
   using cfg = Cfg<BN, STAGES>;
   static_assert(cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
@@ -434,7 +437,7 @@ static int launch_igemm(const CUtensorMap& mx, const CUtensorMap& mw, bf16* C, i
   const int tiles = g.B * g.tiles_x * g.tiles_y;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   S2U_LAUNCH((conv_igemm_kernel<BN, STAGES>), grid, THREADS, cfg::SMEM_BYTES, st, mx, mw, C, ldc, g, bias, resid, ld_res,
-             relu, sums);
+             relu, sums, fin);
   S2U_LAUNCH_CHECK();
   return 0;
 }
@@ -452,9 +455,9 @@ int s2u_conv_igemm_supported(int Cin, int N, int ldx, int ld_out) {
 // dilation; bf16.  epi: + bias[N] (NULL to skip), + resid [.., N] pitch ld_res (NULL to skip; resid == out accumulates),
 // relu.  sums (N == 64 only, may be NULL): bn.cu's fp64 statistics workspace, receives the per-channel sum and sum of
 // squares of the rounded output (finalise with s2u_bn_finalize).
-int s2u_conv_igemm(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int N, int KH, int KW, int dil,
-                   void* out, int ld_out, const float* bias, const void* resid, int ld_res, int relu, double* sums,
-                   void* stream) {
+static int conv_igemm_impl(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int N, int KH, int KW,
+                           int dil, void* out, int ld_out, const float* bias, const void* resid, int ld_res, int relu,
+                           double* sums, const BnFin& fin, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0 || KH <= 0 || KW <= 0 || dil <= 0) return S2U_EINVAL;
   if (!s2u_conv_igemm_supported(Cin, N, ldx, ld_out) || !cig::aligned16(x) || !cig::aligned16(Wm) || !cig::aligned16(out))
     return S2U_EUNSUPPORTED;
@@ -472,11 +475,31 @@ int s2u_conv_igemm(const void* x, int ldx, int B, int H, int W, int Cin, const v
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (N) {
-    case 64: return cig::launch_igemm<64, 8>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, st);
-    case 128: return cig::launch_igemm<128, 6>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, st);
-    case 256: return cig::launch_igemm<256, 4>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, st);
+    case 64: return cig::launch_igemm<64, 8>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
+    case 128: return cig::launch_igemm<128, 6>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
+    case 256: return cig::launch_igemm<256, 4>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
   }
   return S2U_EUNSUPPORTED;
+}
+
+int s2u_conv_igemm(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int N, int KH, int KW, int dil,
+                   void* out, int ld_out, const float* bias, const void* resid, int ld_res, int relu, double* sums,
+                   void* stream) {
+  return conv_igemm_impl(x, ldx, B, H, W, Cin, Wm, N, KH, KW, dil, out, ld_out, bias, resid, ld_res, relu, sums, BnFin{},
+                         stream);
+}
+
+// Training forward of conv + BatchNorm statistics in ONE launch (N = 64): out = conv(x, Wm) (bf16, pitch ld_out), and
+// the CTA that finishes last turns the batch statistics of the rounded output into scale / shift for s2u_bn_apply,
+// the saved mean / rstd for the backward and the running-statistics update (SAM2UNet.py:80-86).  sums: the fp64
+// workspace of s2u_bn_ws_doubles(64), zero on entry and on exit.
+int s2u_conv_igemm_bn(const void* x, int ldx, int B, int H, int W, int Cin, const void* Wm, int KH, int KW, int dil,
+                      void* out, int ld_out, double* sums, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long long* num_batches, float* scale, float* shift, float* save_mean,
+                      float* save_rstd, float eps, float momentum, void* stream) {
+  if (!sums || !gamma || !beta || !running_mean || !running_var || !scale || !shift) return S2U_EINVAL;
+  const BnFin fin{gamma, beta, running_mean, running_var, num_batches, scale, shift, save_mean, save_rstd, eps, momentum};
+  return conv_igemm_impl(x, ldx, B, H, W, Cin, Wm, 64, KH, KW, dil, out, ld_out, nullptr, nullptr, 0, 0, sums, fin, stream);
 }
 
 // G [Cout][Cin][KH][KW] (fp32, the state-dict layout) += d(raw)^T (*) x: the convolution's weight gradient from the

@@ -121,7 +121,8 @@ struct S2uRefreshEntry {
   unsigned long long src, dst0, dst1;   // fp32 master; compute-dtype outputs (0 = skip)
   int kind;                             // 0: [d0, d1] matrix -> dst0 (same layout) and dst1 (transposed)
   int d0, d1, d2, d3;                   // 1: conv weight [Cout=d0][Cin=d1][KH=d2][KW=d3] -> dst0 [Cout][tap][Cin],
-  int pad;                              //    dst1 [Cin][flipped tap][Cout]
+  int pad;                              //    dst1 [Cin][flipped tap][Cout]; pad != 0: row pitch of dst1 (the five 1x1
+                                        //    convs of an RFB write column slices of one [Cin][320] operand)
 };
 
 template <typename T>
@@ -152,7 +153,10 @@ __global__ void __launch_bounds__(256) refresh_kernel(const S2uRefreshEntry* __r
       const int ci = (int)((i / taps) % e.d1);
       const int co = (int)(i / ((long long)taps * e.d1));
       if (dst0) stf(dst0 + ((long long)co * taps + tap) * e.d1 + ci, v);
-      if (dst1) stf(dst1 + ((long long)ci * taps + (taps - 1 - tap)) * e.d0 + co, v);
+      if (dst1) {
+        if (e.pad) stf(dst1 + (long long)ci * e.pad + (taps - 1 - tap) * e.d0 + co, v);
+        else stf(dst1 + ((long long)ci * taps + (taps - 1 - tap)) * e.d0 + co, v);
+      }
     }
   }
 }

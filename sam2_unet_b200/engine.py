@@ -162,6 +162,14 @@ class Ops:
         _lib.call("s2u_conv_igemm", xp, ldx, B, H, W, Cin, wm.data_ptr(), N, KH, KW, dil, op, ld_out, _ptr(bias), rp,
                   ld_res, 1 if relu else 0, _ptr(sums), self.stream)
 
+    def conv_igemm_bn(self, x, ldx, B, H, W, Cin, wm, KH, KW, dil, out, ld_out, sums, gamma, beta, rm, rv, nbt, scale,
+                      shift, mean, rstd):
+        """training forward: conv + BatchNorm batch statistics + finalisation in one launch"""
+        xp = x.data_ptr() if isinstance(x, torch.Tensor) else x
+        _lib.call("s2u_conv_igemm_bn", xp, ldx, B, H, W, Cin, wm.data_ptr(), KH, KW, dil, out.data_ptr(), ld_out,
+                  sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), _ptr(nbt),
+                  scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), 1e-5, 0.1, self.stream)
+
     def conv_wgrad(self, dy, ld_dy, x, ldx, G, B, H, W, Cin, Cout, KH, KW, dil):
         xp = x.data_ptr() if isinstance(x, torch.Tensor) else x
         _lib.call("s2u_conv_wgrad", dy.data_ptr(), ld_dy, xp, ldx, G.data_ptr(), B, H, W, Cin, Cout, KH, KW, dil,
@@ -259,6 +267,7 @@ class Engine:
         self._refresh = None
         self._streams = None
         self.fuse_adapter = os.environ.get("S2U_FUSE_ADAPTER", "1") != "0"   # adapter + norm1 as one kernel per direction
+        self.merge_1x1 = os.environ.get("S2U_MERGE_1X1", "1") != "0"         # an RFB's five 1x1 convs as one GEMM per direction
         self.igemm = os.environ.get("S2U_CONV_IGEMM", "1") != "0"            # implicit-GEMM convolutions (no im2col)
         self.overlap = self.device.type == "cuda"   # RFB forward/backward on side streams, overlapped with the trunk
 
@@ -331,12 +340,24 @@ class Engine:
                 sh[key + ".wf"], sh[key + ".wd"] = ops.empty(64, taps * cs.cin), ops.empty(cs.cin, taps * 64)
                 ent.append((P[key + ".weight"].data_ptr(), sh[key + ".wf"].data_ptr(), sh[key + ".wd"].data_ptr(), 1, 64,
                             cs.cin, cs.kh, cs.kw, 64 * cs.cin * taps))
+            # the five 1x1 convs that read an RFB's input (branch0-3 entry convs, conv_res): ONE [320, Cin] forward
+            # operand and ONE [Cin, 320] input-gradient operand, so each direction is a single GEMM
+            esz = torch.empty(0, dtype=self.T).element_size()
+            for k in range(4):
+                names = [f"rfb{k + 1}.branch{b}.0.conv" for b in range(4)] + [f"rfb{k + 1}.conv_res.conv"]
+                cin = self._units[names[0]].cin
+                wf5, wd5 = ops.empty(320, cin), ops.empty(cin, 320)
+                sh[f"rfb{k + 1}.in5.wf"], sh[f"rfb{k + 1}.in5.wd"] = wf5, wd5
+                for j, nm in enumerate(names):
+                    ent.append((P[nm + ".weight"].data_ptr(), wf5.data_ptr() + 64 * j * cin * esz,
+                                wd5.data_ptr() + 64 * j * esz, 1, 64, cin, 1, 1, 64 * cin, 320))
             rec = np.zeros(len(ent), dtype=np.dtype([("src", "<u8"), ("d0p", "<u8"), ("d1p", "<u8"), ("kind", "<i4"),
                                                      ("d0", "<i4"), ("d1", "<i4"), ("d2", "<i4"), ("d3", "<i4"),
                                                      ("pad", "<i4")]))
             blocks = []
-            for j, (src, d0p, d1p, kind, d0, d1, d2, d3, n) in enumerate(ent):
-                rec[j] = (src, d0p, d1p, kind, d0, d1, d2, d3, 0)
+            for j, e in enumerate(ent):
+                src, d0p, d1p, kind, d0, d1, d2, d3, n = e[:9]
+                rec[j] = (src, d0p, d1p, kind, d0, d1, d2, d3, e[9] if len(e) > 9 else 0)
                 blocks += [(j, ch) for ch in range((n + 1023) // 1024)]
             entries = torch.from_numpy(rec.view(np.uint8).copy()).to(self.device)
             blk = torch.tensor(blocks, dtype=torch.int32).to(self.device)
@@ -510,7 +531,9 @@ class Engine:
         return wf, shift
 
     # conv (+ BN (+ residual) (+ ReLU)) on NHWC rows.  `src`: (tensor, ld, channel offset) of the input map.
-    def _conv_bn(self, cs: _ConvSpec, src, B, H, out, ld_out, out_off, relu, training, tape, resid=None, ld_res=0):
+    def _conv_bn(self, cs: _ConvSpec, src, B, H, out, ld_out, out_off, relu, training, tape, resid=None, ld_res=0,
+                 raw_in=None):
+        """raw_in = (tensor, pitch): the conv output already computed (column slice of a merged GEMM)."""
         ops, sh = self.ops, self._shadow
         P, Bf = self.model.flat.views, self.model.flat.buffers
         x, ldx, xoff = src
@@ -542,18 +565,32 @@ class Engine:
                          ldw=taps * cs.cin, ldc=ld_out,
                          flags=(RESID if resid is not None else 0) | (RELU if relu else 0))
             return
-        raw = ops.empty(M, 64)
+        raw, ldraw = (ops.empty(M, 64), 64) if raw_in is None else raw_in
         ws = self._bn_workspace(cs.bn, 64)
         mean = rstd = None
-        if ig:
-            # conv + BatchNorm batch statistics in one launch (the epilogue sums the rounded output per channel)
-            ops.conv_igemm(xin, ldx, B, H, H, cs.cin, sh[cs.name + ".wf"], 64, cs.kh, cs.kw, cs.dil, raw, 64,
-                           sums=ws["sums"] if training else None)
+        if raw_in is not None:
             if training:
                 mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
-            ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
-                            Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
-                            mean, rstd, M, 64, training)
+                ops.bn_stats_finalize(raw, ldraw, ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"],
+                                      Bf[cs.bn + ".running_mean"], Bf[cs.bn + ".running_var"],
+                                      Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"], mean, rstd, M, 64)
+            else:
+                ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
+                                Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
+                                None, None, M, 64, False)
+        elif ig:
+            # conv + BatchNorm batch statistics (+ their finalisation by the last CTA) in one launch
+            if training:
+                mean, rstd = ops.empty(64, dtype=torch.float32), ops.empty(64, dtype=torch.float32)
+                ops.conv_igemm_bn(xin, ldx, B, H, H, cs.cin, sh[cs.name + ".wf"], cs.kh, cs.kw, cs.dil, raw, 64,
+                                  ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
+                                  Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"],
+                                  ws["shift"], mean, rstd)
+            else:
+                ops.conv_igemm(xin, ldx, B, H, H, cs.cin, sh[cs.name + ".wf"], 64, cs.kh, cs.kw, cs.dil, raw, 64)
+                ops.bn_finalize(ws["sums"], P[cs.bn + ".weight"], P[cs.bn + ".bias"], Bf[cs.bn + ".running_mean"],
+                                Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
+                                None, None, M, 64, False)
         else:
             ops.gemm(A, sh[cs.name + ".wf"], raw, M=M, N=64, K=taps * cs.cin, lda=ldcol, ldw=taps * cs.cin, ldc=64)
             if training:
@@ -566,10 +603,10 @@ class Engine:
                                 Bf[cs.bn + ".running_var"], Bf[cs.bn + ".num_batches_tracked"], ws["scale"], ws["shift"],
                                 None, None, M, 64, False)
         out_ptr = out.data_ptr() + out_off * esz
-        ops.bn_apply(raw, 64, ws["scale"], ws["shift"], resid, ld_res, out_ptr, ld_out, M, 64, relu)
+        ops.bn_apply(raw, ldraw, ws["scale"], ws["shift"], resid, ld_res, out_ptr, ld_out, M, 64, relu)
         if tape is not None:
-            tape["convs"][cs.name] = dict(col=col, ldcol=ldcol, coff=col_ptr_off, raw=raw, mean=mean, rstd=rstd, B=B,
-                                          H=H, ig=ig, xin=xin, ldx=ldx)
+            tape["convs"][cs.name] = dict(col=col, ldcol=ldcol, coff=col_ptr_off, raw=raw, ldraw=ldraw, mean=mean,
+                                          rstd=rstd, B=B, H=H, ig=ig, xin=xin, ldx=ldx)
 
     def _rfb_fwd(self, k, f, H, B, training, tape):
         """RFB_modified k on the stage-k feature map f [B*H*H, Cin] (SAM2UNet.py:117-125); returns (dst, ld, H) where
@@ -585,19 +622,26 @@ class Engine:
             dst, ld_dst = ops.empty(M, 64), 64
         cat = ops.empty(M, 256)
         src = (f, Cin, 0)
-        self._conv_bn(units[r + "branch0.0.conv"], src, B, H, cat, 256, 0, False, training, tape)
+        # the five 1x1 convs on f (branch0-3 entry convs, conv_res) as ONE GEMM with N = 320: f is read once
+        merged = (training or tape is not None) and self.merge_1x1
+        raw5 = None
+        if merged:
+            raw5 = ops.empty(M, 320)
+            ops.gemm(f, self._shadow[r + "in5.wf"], raw5, M=M, N=320, K=Cin, lda=Cin, ldw=Cin, ldc=320)
+        rin = (lambda j: (raw5.view(-1)[64 * j:], 320)) if merged else (lambda j: None)
+        self._conv_bn(units[r + "branch0.0.conv"], src, B, H, cat, 256, 0, False, training, tape, raw_in=rin(0))
         for bi in (1, 2, 3):
             t0, t1, t2 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
-            self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape)
+            self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape, raw_in=rin(bi))
             self._conv_bn(units[r + f"branch{bi}.1.conv"], (t0, 64, 0), B, H, t1, 64, 0, False, training, tape)
             self._conv_bn(units[r + f"branch{bi}.2.conv"], (t1, 64, 0), B, H, t2, 64, 0, False, training, tape)
             self._conv_bn(units[r + f"branch{bi}.3.conv"], (t2, 64, 0), B, H, cat, 256, 64 * bi, False, training, tape)
         res = ops.empty(M, 64)
-        self._conv_bn(units[r + "conv_res.conv"], src, B, H, res, 64, 0, False, training, tape)
+        self._conv_bn(units[r + "conv_res.conv"], src, B, H, res, 64, 0, False, training, tape, raw_in=rin(4))
         self._conv_bn(units[r + "conv_cat.conv"], (cat, 256, 0), B, H, dst, ld_dst, 0, True, training, tape,
                       resid=res, ld_res=64)
         if tape is not None:
-            tape["dec"][r] = dict(f=f, cat=cat, dst=dst, ld_dst=ld_dst, H=H, Cin=Cin)
+            tape["dec"][r] = dict(f=f, cat=cat, dst=dst, ld_dst=ld_dst, H=H, Cin=Cin, merged=merged)
         return dst, ld_dst, H
 
     def _up_fwd(self, rfb_out, B, S, training, tape):
@@ -736,7 +780,7 @@ class Engine:
         ops.gemm(dh1, sh[a + "0.wt"], dx, resid=dxa, flags=RESID)
         return dx
 
-    def _conv_bn_bwd(self, cs: _ConvSpec, tape, dy, ld_dy, dy_off, y, ld_y, y_off, dst, accumulate):
+    def _conv_bn_bwd(self, cs: _ConvSpec, tape, dy, ld_dy, dy_off, y, ld_y, y_off, dst, accumulate, draw_out=None):
         """Backward of one conv+BN unit.  dy / y: (tensor, pitch, channel offset) of the output gradient and, when
         the unit ends in a ReLU, of its saved output.  dst = (tensor, ld, offset) receiving d(input)."""
         ops, sh = self.ops, self._shadow
@@ -746,13 +790,14 @@ class Engine:
         M = B * H * H
         taps = cs.kh * cs.kw
         ws = self._bn_workspace(cs.bn, 64)
-        draw = ops.empty(M, 64)
+        # d(raw): its own [M,64] tensor, or a column slice (pitch 320) of the merged input-gradient GEMM's operand
+        draw, ld_draw = (ops.empty(M, 64), 64) if draw_out is None else draw_out
         dyv = dy.view(-1)[dy_off:] if dy_off else dy
         yv = None
         if y is not None:
             yv = y.view(-1)[y_off:] if y_off else y
-        ops.bn_bwd(dyv, ld_dy, yv, ld_y, tp["raw"], 64, tp["mean"], tp["rstd"], P[cs.bn + ".weight"], ws["sums"],
-                   G[cs.bn + ".weight"], G[cs.bn + ".bias"], ws["c1"], ws["c2"], draw, 64, M, 64)
+        ops.bn_bwd(dyv, ld_dy, yv, ld_y, tp["raw"], tp["ldraw"], tp["mean"], tp["rstd"], P[cs.bn + ".weight"], ws["sums"],
+                   G[cs.bn + ".weight"], G[cs.bn + ".bias"], ws["c1"], ws["c2"], draw, ld_draw, M, 64)
         if tp["ig"]:
             # weight gradient straight from the un-expanded input map (tap-shifted TMA boxes)
             ops.conv_wgrad(draw, 64, tp["xin"], tp["ldx"], G[cs.name + ".weight"], B, H, H, cs.cin, 64, cs.kh, cs.kw,
@@ -760,7 +805,7 @@ class Engine:
         else:
             col = tp["col"]
             colv = col.view(-1)[tp["coff"]:] if tp["coff"] else col
-            ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin, lda=64, ldb=tp["ldcol"],
+            ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin, lda=ld_draw, ldb=tp["ldcol"],
                       ldg=taps * cs.cin, q_inner=cs.cin, q_taps=taps)
         if dst is None:
             return
@@ -830,14 +875,21 @@ class Engine:
         ops.relu_bwd(dy, ld_dy, tp["dst"], tp["ld_dst"], g, 64, M, 64)
         df = ops.empty(M, Cin)
         dcatb = ops.empty(M, 256)
+        merged = tp["merged"]
+        draw5 = ops.empty(M, 320) if merged else None
+        dsl = (lambda j: (draw5.view(-1)[64 * j:], 320)) if merged else (lambda j: None)
+        dfd = (lambda acc: None) if merged else (lambda acc: (df, Cin, 0))
         self._conv_bn_bwd(units[r + "conv_cat.conv"], tape, g, 64, 0, None, 0, 0, (dcatb, 256, 0), False)
-        self._conv_bn_bwd(units[r + "conv_res.conv"], tape, g, 64, 0, None, 0, 0, (df, Cin, 0), False)
-        self._conv_bn_bwd(units[r + "branch0.0.conv"], tape, dcatb, 256, 0, None, 0, 0, (df, Cin, 0), True)
+        self._conv_bn_bwd(units[r + "conv_res.conv"], tape, g, 64, 0, None, 0, 0, dfd(False), False, draw_out=dsl(4))
+        self._conv_bn_bwd(units[r + "branch0.0.conv"], tape, dcatb, 256, 0, None, 0, 0, dfd(True), True, draw_out=dsl(0))
         for bi in (1, 2, 3):
             d2, d1, d0 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
             self._conv_bn_bwd(units[r + f"branch{bi}.3.conv"], tape, dcatb, 256, 64 * bi, None, 0, 0, (d2, 64, 0), False)
             self._conv_bn_bwd(units[r + f"branch{bi}.2.conv"], tape, d2, 64, 0, None, 0, 0, (d1, 64, 0), False)
             self._conv_bn_bwd(units[r + f"branch{bi}.1.conv"], tape, d1, 64, 0, None, 0, 0, (d0, 64, 0), False)
-            self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, (df, Cin, 0), True)
-        tape["dec"][r]["keep"] = (g, dcatb, dy)         # alive until the streams are joined
+            self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, dfd(True), True,
+                              draw_out=dsl(bi))
+        if merged:                                      # df = [d(raw) of the five 1x1 convs] . [Cin, 320]^T in one GEMM
+            ops.gemm(draw5, self._shadow[r + "in5.wd"], df, M=M, N=Cin, K=320, lda=320, ldw=320, ldc=Cin)
+        tape["dec"][r]["keep"] = (g, dcatb, dy, draw5)  # alive until the streams are joined
         return df

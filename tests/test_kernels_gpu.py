@@ -726,6 +726,26 @@ def test_conv_igemm(cuda, conv, geom):
     yf = y.double()
     assert torch.allclose(rep[:64], yf.sum(0), rtol=1e-5, atol=1e-3), "BatchNorm sums"
     assert torch.allclose(rep[64:], (yf * yf).sum(0), rtol=1e-5, atol=1e-3), "BatchNorm sums of squares"
+    # the same with the finalisation fused (last CTA): scale / shift / saved statistics / running statistics must equal
+    # the standalone statistics pass over the same output
+    gmm, bta = _rand((64,), "fp32", cuda, 11) * 0.1 + 1, _rand((64,), "fp32", cuda, 12) * 0.1
+    outs = {}
+    for fused in (True, False):
+        rm, rv = torch.zeros(64, device=cuda), torch.ones(64, device=cuda)
+        nbt = torch.zeros((), dtype=torch.long, device=cuda)
+        sc, sh_, mu, rs = (torch.empty(64, device=cuda) for _ in range(4))
+        sums.zero_()
+        if fused:
+            y2 = ops.empty(M, 64)
+            ops.conv_igemm_bn(xbuf.view(-1)[64:], ldx, B, H, H, cin, wf, kh, kw, dil, y2, 64, sums, gmm, bta, rm, rv, nbt,
+                              sc, sh_, mu, rs)
+            assert torch.equal(y2, y)
+        else:
+            ops.bn_stats_finalize(y, 64, sums, gmm, bta, rm, rv, nbt, sc, sh_, mu, rs, M, 64)
+        assert float(sums.abs().max()) == 0.0 and int(nbt) == 1
+        outs[fused] = (sc, sh_, mu, rs, rm, rv)
+    for a, b_, nm in zip(outs[True], outs[False], ("scale", "shift", "mean", "rstd", "running_mean", "running_var")):
+        assert torch.allclose(a, b_, rtol=1e-4, atol=1e-5), nm
     # bias + residual + ReLU into a strided output
     bias, res = _rand((64,), "fp32", cuda, 5), _rand((M, 64), "bf16", cuda, 6)
     obuf = torch.zeros(M, 256, dtype=torch.bfloat16, device=cuda)
