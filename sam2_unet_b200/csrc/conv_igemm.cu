@@ -45,32 +45,39 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-template <int BN, int STAGES>
+constexpr int WRES_MAX_KB = 9;                 // resident-weight variant: up to 9 k-blocks of [64 x 64] (3x3 taps, Cin = 64)
+// WRES: the whole weight operand (<= WRES_MAX_KB k-blocks, N = 64) is loaded ONCE per CTA and stays in shared memory,
+// so the ring carries only the activation boxes: a third less L2 -> SM traffic for the 64 -> 64 convolutions, which are
+// bound by exactly that (every tap re-reads its shifted box from L2)
+template <int BN, int STAGES, bool WRES>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int W_BYTES = WRES ? WRES_MAX_KB * B_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(BM >> 4) << 24);
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool WRES>
 __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_x,
                                                                const __grid_constant__ CUtensorMap tma_w,
                                                                bf16* __restrict__ C, int ldc, Geo g,
                                                                const float* __restrict__ bias,
                                                                const bf16* __restrict__ resid, int ld_res, int relu,
                                                                double* __restrict__ sums, BnFin fin) {
-  using cfg = Cfg<BN, STAGES>;
+  using cfg = Cfg<BN, STAGES, WRES>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 5];
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // resident weights (WRES), then the ring
+  const uint32_t stage_base = w_base + (uint32_t)cfg::W_BYTES;
   const uint32_t bar0 = smem_u32(bars);
+  const uint32_t w_bar = bar0 + 8u * (2 * STAGES + 4);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
@@ -92,6 +99,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EPI_WARPS);
     }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -108,6 +116,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
+      if (WRES) {                                            // the whole weight operand, once
+        mbar_expect_tx(w_bar, (uint32_t)(num_kb * cfg::B_BYTES));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(w_base + (uint32_t)(kb * cfg::B_BYTES), &tma_w, w_bar, kb * BK, 0);
+      }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, rem = tile - b * tiles_img;
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
             mbar_expect_tx(full_bar(s), (uint32_t)cfg::STAGE_BYTES);
             const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
             tma_load_4d(sa, &tma_x, full_bar(s), kc * BK, x0 + ox, y0 + oy, b);
-            tma_load_2d(sa + cfg::A_BYTES, &tma_w, full_bar(s), (tap * g.kchunks + kc) * BK, 0);
+            if (!WRES) tma_load_2d(sa + cfg::A_BYTES, &tma_w, full_bar(s), (tap * g.kchunks + kc) * BK, 0);
           }
         }
       }
@@ -129,6 +141,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
+      if (WRES) mbar_wait(w_bar, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int acc = lt & 1;
         mbar_wait(tempty_bar(acc), ((lt >> 1) & 1u) ^ 1u);
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
           tc_fence_after();
           const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
           const uint64_t adesc = smem_desc_sw128(sa);
-          const uint64_t bdesc = smem_desc_sw128(sa + cfg::A_BYTES);
+          const uint64_t bdesc = smem_desc_sw128(WRES ? w_base + (uint32_t)(kb * cfg::B_BYTES) : sa + cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             tc_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), cfg::IDESC, (kb > 0 || k > 0) ? 1u : 0u);
@@ -422,21 +435,21 @@ static int num_sms() {
 }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool WRES>
 static int launch_igemm(const CUtensorMap& mx, const CUtensorMap& mw, bf16* C, int ldc, const Geo& g, const float* bias,
                         const bf16* resid, int ld_res, int relu, double* sums, const BnFin& fin, cudaStream_t st) {
-  using cfg = Cfg<BN, STAGES>;
+  using cfg = Cfg<BN, STAGES, WRES>;
   static_assert(cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t ce = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           cfg::SMEM_BYTES);
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
   const int tiles = g.B * g.tiles_x * g.tiles_y;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  S2U_LAUNCH((conv_igemm_kernel<BN, STAGES>), grid, THREADS, cfg::SMEM_BYTES, st, mx, mw, C, ldc, g, bias, resid, ld_res,
+  S2U_LAUNCH((conv_igemm_kernel<BN, STAGES, WRES>), grid, THREADS, cfg::SMEM_BYTES, st, mx, mw, C, ldc, g, bias, resid, ld_res,
              relu, sums, fin);
   S2U_LAUNCH_CHECK();
   return 0;
@@ -475,9 +488,12 @@ static int conv_igemm_impl(const void* x, int ldx, int B, int H, int W, int Cin,
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (N) {
-    case 64: return cig::launch_igemm<64, 8>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
-    case 128: return cig::launch_igemm<128, 6>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
-    case 256: return cig::launch_igemm<256, 4>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
+    case 64:
+      if (g.taps * g.kchunks <= cig::WRES_MAX_KB)
+        return cig::launch_igemm<64, 8, true>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
+      return cig::launch_igemm<64, 8, false>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
+    case 128: return cig::launch_igemm<128, 6, false>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
+    case 256: return cig::launch_igemm<256, 4, false>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
   }
   return S2U_EUNSUPPORTED;
 }
@@ -529,7 +545,13 @@ int s2u_conv_wgrad(const void* dy, int ld_dy, const void* x, int ldx, float* G, 
   }
   const int xt = ceil_div(g.taps * g.kchunks, 2);
   const int total = B * g.tiles_x * g.tiles_y;
-  int splits = (2 * cig::num_sms() + xt - 1) / xt;
+  static int mult = 0;                                      // CTAs per SM (S2U_WG_CTAS_PER_SM): more splits = more
+  if (mult == 0) {                                          // parallelism but one fp32 atomic per weight per split
+    const char* e = getenv("S2U_WG_CTAS_PER_SM");
+    mult = e ? atoi(e) : 1;                                 // measured (scripts/wg_bench.py): 1 <= 2 < 3 < 4
+    if (mult < 1) mult = 1;
+  }
+  int splits = (mult * cig::num_sms() + xt - 1) / xt;
   if (splits > total / 4) splits = total / 4;               // at least 4 pixel tiles per CTA
   if (splits < 1) splits = 1;
   const int per = (total + splits - 1) / splits;

@@ -1237,7 +1237,13 @@ static int launch_wgrad(const WgProblem* probs, int nprob, long long M, cudaStre
   int x_tiles = ceil_div(jobs[0].X, 128);
   if (nprob == 2 && ceil_div(jobs[1].X, 128) > x_tiles) x_tiles = ceil_div(jobs[1].X, 128);
   const int total_kb = (int)((M + 63) / 64);
-  int splits = (2 * num_sms() + x_tiles * nprob - 1) / (x_tiles * nprob);
+  static int mult = 0;                                     // CTAs per SM (S2U_WG_CTAS_PER_SM)
+  if (mult == 0) {
+    const char* e = getenv("S2U_WG_CTAS_PER_SM");
+    mult = e ? atoi(e) : 2;
+    if (mult < 1) mult = 1;
+  }
+  int splits = (mult * num_sms() + x_tiles * nprob - 1) / (x_tiles * nprob);
   if (splits > total_kb / 4) splits = total_kb / 4;        // at least 4 k-blocks per CTA
   if (splits < 1) splits = 1;
   const int kb_per = (total_kb + splits - 1) / splits;
