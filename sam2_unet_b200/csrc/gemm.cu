@@ -471,7 +471,11 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
   const long long ld16 = (dgelu || mulaux) ? epi.ld_aux : epi.ld_res;
   const float* side32 = resid_f32 ? reinterpret_cast<const float*>(epi.resid) : nullptr;
   const bool has_side = side16 != nullptr || side32 != nullptr;
-  const bool has_pf = has_side || epi.bias != nullptr;                      // anything to prefetch per chunk
+  // the chunk's bias values travel with the cp.async prefetch in the compute-dtype epilogues (a __ldg right before the
+  // add cost ~9 % of the GELU kernel in L2 round trips: ncu, long scoreboard on the first FADD of every chunk); the
+  // stream epilogue is busier in shared memory and measured 3-5 % SLOWER with it, so it keeps the __ldg
+  constexpr bool BIAS_PF = !F32S;
+  const bool has_pf = has_side || (BIAS_PF && epi.bias != nullptr);         // anything to prefetch per chunk
   constexpr int CSTRIDE = 32 * EPI_PARTS;                                   // column distance between this warp's chunks
   const int nch = (BN - part * 32 + CSTRIDE - 1) / CSTRIDE;                 // this warp's chunks per tile (may be 0)
   constexpr uint32_t SLOT = (F32S ? 2 : 1) * EPI_BUF_BYTES;                 // one chunk's side input
@@ -485,9 +489,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
     const int cols_ok = min(min(32, BN - part * 32 - ci * CSTRIDE), N - col0);
     if (rows_ok <= 0 || cols_ok <= 0) return;
     const uint32_t b = stg + (uint32_t)par * SLOT;
-    // the chunk's bias segment: a __ldg right before the add cost ~9 % of the kernel in L2 round trips (ncu, long
-    // scoreboard on the first FADD of every chunk)
-    if (epi.bias && lane * 4 < cols_ok) cp_async16(sbias + (uint32_t)(par * 128 + lane * 16), epi.bias + col0 + lane * 4);
+    if (BIAS_PF && epi.bias && lane * 4 < cols_ok) cp_async16(sbias + (uint32_t)(par * 128 + lane * 16), epi.bias + col0 + lane * 4);
     if (!has_side) return;
     if (side16) {
       g2s_async(b, reinterpret_cast<const char*>(side16 + row0 * ld16 + col0), ld16 * 2, rows_ok, cols_ok * 2, lane);
@@ -540,12 +542,26 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
       __syncwarp();
       if (!live) continue;
       const uint32_t h0 = stg + (uint32_t)par * SLOT, h1 = h0 + EPI_BUF_BYTES;   // h1: F32S only
-      if (epi.bias) {                                                       // (columns >= cols_ok: never stored)
+      // fc1 forward (GELU + saved GELU', nothing else after it): the side-input slot is free to stage the second output
+      const bool dg_stage = !F32S && !has_side && !(epi.flags & (GEMM_RESID | GEMM_RELU));
+      if (epi.bias && BIAS_PF) {                                            // (columns >= cols_ok: never stored)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 b4 = lds16(sbias + (uint32_t)(par * 128 + j * 16));
           v[4 * j] += __uint_as_float(b4.x); v[4 * j + 1] += __uint_as_float(b4.y);
           v[4 * j + 2] += __uint_as_float(b4.z); v[4 * j + 3] += __uint_as_float(b4.w);
+        }
+      } else if (epi.bias) {
+        if (cols_ok == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cols_ok) v[j] += __ldg(epi.bias + col0 + j);
         }
       }
       if ((epi.flags & GEMM_GELU) && epi.pre_out && !pre_final && (epi.flags & GEMM_SAVE_DGELU)) {
@@ -560,7 +576,18 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, i
             v[8 * j + e] = gg.x; v[8 * j + e + 1] = gg.y;
             d[e] = dd.x; d[e + 1] = dd.y;
           }
-          sts16(stg_addr(so, lane, j), pack8(d));
+          sts16(stg_addr(dg_stage ? h0 : so, lane, j), pack8(d));
+        }
+        if (dg_stage) {
+          // gelu' waits in the (unused) side-input slot, gelu goes to the output tile: ONE round trip through shared
+          // memory for both outputs instead of two serialised ones
+          regs_to_stage(so, lane, v);
+          __syncwarp();
+          s2g_rows(h0, reinterpret_cast<char*>(epi.pre_out + row0 * epi.ld_pre + col0), (long long)epi.ld_pre * 2, rows_ok,
+                   cols_ok * 2, lane);
+          s2g_rows(so, reinterpret_cast<char*>(C + row0 * ldc + col0), (long long)ldc * 2, rows_ok, cols_ok * 2, lane);
+          __syncwarp();
+          continue;
         }
         __syncwarp();
         s2g_rows(so, reinterpret_cast<char*>(epi.pre_out + row0 * epi.ld_pre + col0), (long long)epi.ld_pre * 2, rows_ok,
