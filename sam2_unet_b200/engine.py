@@ -268,6 +268,15 @@ class Engine:
         self._streams = None
         self.fuse_adapter = os.environ.get("S2U_FUSE_ADAPTER", "1") != "0"   # adapter + norm1 as one kernel per direction
         self.merge_1x1 = os.environ.get("S2U_MERGE_1X1", "1") != "0"         # an RFB's five 1x1 convs as one GEMM per direction
+        # weight gradients feed nothing but the optimizer: they run on their own stream, off the dependency chain of the
+        # backward pass (the decoder's and RFB4's backward are chains of tiny kernels the trunk backward waits for)
+        self.async_wgrad = os.environ.get("S2U_ASYNC_WGRAD", "1") != "0"
+        # RFB branches 1-3 on their own streams: measured no gain (17.95 vs 17.97 ms: the GPU time-slices whole kernels,
+        # the step is the sum of their durations either way), so it stays an opt-in switch
+        self.branch_streams = os.environ.get("S2U_BRANCH_STREAMS", "0") != "0"
+        self._bstreams = None
+        self._wg_stream = None
+        self._wg_keep = []
         self.igemm = os.environ.get("S2U_CONV_IGEMM", "1") != "0"            # implicit-GEMM convolutions (no im2col)
         self.overlap = self.device.type == "cuda"   # RFB forward/backward on side streams, overlapped with the trunk
 
@@ -442,6 +451,54 @@ class Engine:
         if training:
             self.model.flat.bump()       # our kernels updated the BatchNorm running statistics through raw pointers
         return outs
+
+    def _branches(self, k, enabled, bodies):
+        """Run the three independent branch chains of RFB k (callables `bodies`): the first on the current stream, the
+        other two on the RFB's branch streams, forked after everything enqueued so far and joined before returning.
+        On the small maps (11x11, 22x22) every conv is a latency-bound launch chain that leaves the GPU idle."""
+        if not (enabled and self.overlap and self.branch_streams):
+            for body in bodies:
+                body()
+            return
+        if self._bstreams is None:
+            self._bstreams = [[torch.cuda.Stream(device=self.device) for _ in range(2)] for _ in range(4)]
+        cur = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        joins = []
+        for st, body in zip(self._bstreams[k], bodies[1:]):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                body()
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        bodies[0]()
+        for ev in joins:
+            cur.wait_event(ev)
+
+    def _wgrad_async(self, fn, keep):
+        """Run the weight-gradient launch `fn` on the weight-gradient stream, after everything enqueued so far on the
+        current stream; `keep` holds its operands alive until _wgrad_join()."""
+        if not (self.overlap and self.async_wgrad):
+            fn()
+            return
+        if self._wg_stream is None:
+            self._wg_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._wg_stream.wait_event(ev)
+        with torch.cuda.stream(self._wg_stream):
+            fn()
+        self._wg_keep.append(keep)
+
+    def _wgrad_join(self):
+        """The current stream waits for every weight gradient launched so far."""
+        if self._wg_stream is not None and self._wg_keep:
+            ev = torch.cuda.Event()
+            ev.record(self._wg_stream)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._wg_keep = []
 
     def _side_streams(self):
         if self._streams is None:
@@ -630,12 +687,19 @@ class Engine:
             ops.gemm(f, self._shadow[r + "in5.wf"], raw5, M=M, N=320, K=Cin, lda=Cin, ldw=Cin, ldc=320)
         rin = (lambda j: (raw5.view(-1)[64 * j:], 320)) if merged else (lambda j: None)
         self._conv_bn(units[r + "branch0.0.conv"], src, B, H, cat, 256, 0, False, training, tape, raw_in=rin(0))
-        for bi in (1, 2, 3):
-            t0, t1, t2 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
-            self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape, raw_in=rin(bi))
-            self._conv_bn(units[r + f"branch{bi}.1.conv"], (t0, 64, 0), B, H, t1, 64, 0, False, training, tape)
-            self._conv_bn(units[r + f"branch{bi}.2.conv"], (t1, 64, 0), B, H, t2, 64, 0, False, training, tape)
-            self._conv_bn(units[r + f"branch{bi}.3.conv"], (t2, 64, 0), B, H, cat, 256, 64 * bi, False, training, tape)
+        keep = []
+
+        def branch_fwd(bi):
+            def body():
+                t0, t1, t2 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
+                keep.append((t0, t1, t2))
+                self._conv_bn(units[r + f"branch{bi}.0.conv"], src, B, H, t0, 64, 0, False, training, tape, raw_in=rin(bi))
+                self._conv_bn(units[r + f"branch{bi}.1.conv"], (t0, 64, 0), B, H, t1, 64, 0, False, training, tape)
+                self._conv_bn(units[r + f"branch{bi}.2.conv"], (t1, 64, 0), B, H, t2, 64, 0, False, training, tape)
+                self._conv_bn(units[r + f"branch{bi}.3.conv"], (t2, 64, 0), B, H, cat, 256, 64 * bi, False, training, tape)
+            return body
+
+        self._branches(k, True, [branch_fwd(bi) for bi in (1, 2, 3)])
         res = ops.empty(M, 64)
         self._conv_bn(units[r + "conv_res.conv"], src, B, H, res, 64, 0, False, training, tape, raw_in=rin(4))
         self._conv_bn(units[r + "conv_cat.conv"], (cat, 256, 0), B, H, dst, ld_dst, 0, True, training, tape,
@@ -716,6 +780,7 @@ class Engine:
                 if stage == 0:                           # every RFB / decoder gradient is final now
                     for lo, hi, ready in buckets:
                         if ready == nblocks:
+                            self._wgrad_join()
                             on_bucket(lo, hi)
                 stage -= 1
                 if dz is None:
@@ -726,7 +791,9 @@ class Engine:
             tape["blocks"][i] = None
             for lo, hi, ready in buckets:
                 if ready == i:
+                    self._wgrad_join()
                     on_bucket(lo, hi)
+        self._wgrad_join()
 
     def _block_bwd(self, i, spec, tp, dz, B):
         ops, fz, sh = self.ops, self._frozen, self._shadow
@@ -766,7 +833,9 @@ class Engine:
             dh2, dh1, dx = ops.empty(R, C), ops.empty(R, 32), ops.empty(R, C)
             ops.adapter_ln_bwd(dn1, tp["xa"], tp["mean1"], tp["rstd1"], fz[p + "norm1.g"], dres, tp["h2"], tp["h1"],
                                sh[a + "2.wt"], sh[a + "0.wt"], dh2, dh1, dx, G[a + "0.bias"], G[a + "2.bias"], R, C)
-            ops.wgrad_pair(dh2, tp["u"], G[a + "2.weight"], 32, dh1, tp["x"], G[a + "0.weight"], C)
+            u_, x_ = tp["u"], tp["x"]
+            self._wgrad_async(lambda: ops.wgrad_pair(dh2, u_, G[a + "2.weight"], 32, dh1, x_, G[a + "0.weight"], C),
+                              (dh2, dh1, u_, x_))
             return dx
         dxa, dh2 = ops.empty(R, C), ops.empty(R, C)
         ops.ln_bwd(dn1, tp["xa"], fz[p + "norm1.g"], tp["mean1"], tp["rstd1"], dres, dxa, R, C, pre=tp["h2"], dx2=dh2,
@@ -800,13 +869,16 @@ class Engine:
                    G[cs.bn + ".weight"], G[cs.bn + ".bias"], ws["c1"], ws["c2"], draw, ld_draw, M, 64)
         if tp["ig"]:
             # weight gradient straight from the un-expanded input map (tap-shifted TMA boxes)
-            ops.conv_wgrad(draw, 64, tp["xin"], tp["ldx"], G[cs.name + ".weight"], B, H, H, cs.cin, 64, cs.kh, cs.kw,
-                           cs.dil)
+            xin_, ldx_ = tp["xin"], tp["ldx"]
+            self._wgrad_async(lambda: ops.conv_wgrad(draw, 64, xin_, ldx_, G[cs.name + ".weight"], B, H, H, cs.cin, 64,
+                                                     cs.kh, cs.kw, cs.dil), (draw, xin_))
         else:
             col = tp["col"]
             colv = col.view(-1)[tp["coff"]:] if tp["coff"] else col
-            ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin, lda=ld_draw, ldb=tp["ldcol"],
-                      ldg=taps * cs.cin, q_inner=cs.cin, q_taps=taps)
+            ldcol_ = tp["ldcol"]
+            self._wgrad_async(lambda: ops.wgrad(draw, colv, G[cs.name + ".weight"], M=M, P=64, Q=taps * cs.cin,
+                                                lda=ld_draw, ldb=ldcol_, ldg=taps * cs.cin, q_inner=cs.cin,
+                                                q_taps=taps), (draw, colv, col))
         if dst is None:
             return
         dt, ld_d, d_off = dst
@@ -882,14 +954,22 @@ class Engine:
         self._conv_bn_bwd(units[r + "conv_cat.conv"], tape, g, 64, 0, None, 0, 0, (dcatb, 256, 0), False)
         self._conv_bn_bwd(units[r + "conv_res.conv"], tape, g, 64, 0, None, 0, 0, dfd(False), False, draw_out=dsl(4))
         self._conv_bn_bwd(units[r + "branch0.0.conv"], tape, dcatb, 256, 0, None, 0, 0, dfd(True), True, draw_out=dsl(0))
-        for bi in (1, 2, 3):
-            d2, d1, d0 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
-            self._conv_bn_bwd(units[r + f"branch{bi}.3.conv"], tape, dcatb, 256, 64 * bi, None, 0, 0, (d2, 64, 0), False)
-            self._conv_bn_bwd(units[r + f"branch{bi}.2.conv"], tape, d2, 64, 0, None, 0, 0, (d1, 64, 0), False)
-            self._conv_bn_bwd(units[r + f"branch{bi}.1.conv"], tape, d1, 64, 0, None, 0, 0, (d0, 64, 0), False)
-            self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, dfd(True), True,
-                              draw_out=dsl(bi))
+        keep = []
+
+        def branch_bwd(bi):
+            def body():
+                d2, d1, d0 = ops.empty(M, 64), ops.empty(M, 64), ops.empty(M, 64)
+                keep.append((d2, d1, d0))
+                self._conv_bn_bwd(units[r + f"branch{bi}.3.conv"], tape, dcatb, 256, 64 * bi, None, 0, 0, (d2, 64, 0), False)
+                self._conv_bn_bwd(units[r + f"branch{bi}.2.conv"], tape, d2, 64, 0, None, 0, 0, (d1, 64, 0), False)
+                self._conv_bn_bwd(units[r + f"branch{bi}.1.conv"], tape, d1, 64, 0, None, 0, 0, (d0, 64, 0), False)
+                self._conv_bn_bwd(units[r + f"branch{bi}.0.conv"], tape, d0, 64, 0, None, 0, 0, dfd(True), True,
+                                  draw_out=dsl(bi))
+            return body
+
+        # (without the merged input-gradient GEMM the three chains accumulate into df one after the other)
+        self._branches(k, merged, [branch_bwd(bi) for bi in (1, 2, 3)])
         if merged:                                      # df = [d(raw) of the five 1x1 convs] . [Cin, 320]^T in one GEMM
             ops.gemm(draw5, self._shadow[r + "in5.wd"], df, M=M, N=Cin, K=320, lda=320, ldw=320, ldc=Cin)
-        tape["dec"][r]["keep"] = (g, dcatb, dy, draw5)  # alive until the streams are joined
+        tape["dec"][r]["keep"] = (g, dcatb, dy, draw5, keep)  # alive until the streams are joined
         return df
