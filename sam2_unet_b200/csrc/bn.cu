@@ -221,8 +221,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, int ld_dy, const T
 
 // BatchNorm backward in ONE pass over the inputs (C = 64, bf16): a persistent grid of at most one CTA per SM keeps
 // its rows' g = dy * (y > 0) and x in shared memory between the reduction and the apply phase, which are separated
-// by a grid-wide barrier (every CTA is resident: the grid never exceeds the SM count and a CTA needs one SM's worth of
-// nothing but shared memory; dependents of a programmatic launch cannot start before every CTA of this grid has).
+// by a grid-wide barrier (cooperative launch: the grid - never more than one CTA per SM - starts only when all of it
+// is resident, also when several of these kernels are in flight on different streams).
 // Traffic: dy, y, x read once + dx written (the two-kernel path reads them twice).
 // `sums` layout as above; the two words after the accumulators are the barrier counter and the exit ticket.
 constexpr int BNF_THREADS = 512;
@@ -470,8 +470,24 @@ int s2u_bn_bwd(const void* dy, int ld_dy, const void* y, int ld_y, const void* x
     const size_t fsmem = (size_t)rows * 256 + (size_t)(BNF_THREADS / 8) * 2 * 64 * sizeof(float) + 3 * 64 * sizeof(float);
     if (fsmem <= 200 * 1024) {
       S2U_ALLOW_SMEM(bn_bwd_fused_kernel);
-      S2U_LAUNCH((bn_bwd_fused_kernel), grid, BNF_THREADS, fsmem, st, (const bf16*)dy, ld_dy, (const bf16*)y, ld_y,
-                 (const bf16*)x, ldx, mean, rstd, gamma, sums, dgamma, dbeta, (bf16*)dx, ld_dx, M, rows);
+      // COOPERATIVE launch: the grid barrier needs every CTA resident at once.  Several of these kernels can be in
+      // flight on different streams (the four RFB backwards); with plain launches two of them could each hold part
+      // of the SMs and spin on CTAs that cannot be scheduled.  The cooperative attribute makes the hardware start
+      // the grid only when all of it fits.  (No programmatic-dependent-launch attribute on this one.)
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(grid);
+      lc.blockDim = dim3(BNF_THREADS);
+      lc.dynamicSmemBytes = fsmem;
+      lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      cudaError_t ce = cudaLaunchKernelEx(&lc, bn_bwd_fused_kernel, (const bf16*)dy, ld_dy, (const bf16*)y, ld_y,
+                                          (const bf16*)x, ldx, mean, rstd, gamma, sums, dgamma, dbeta, (bf16*)dx, ld_dx,
+                                          M, rows);
+      if (ce != cudaSuccess) return (int)ce;
       S2U_LAUNCH_CHECK();
       return 0;
     }
