@@ -35,6 +35,12 @@ constexpr int THREADS = 64 + 32 * EPI_WARPS;
 struct Geo {
   int B, H, W, tiles_x, tiles_y;
   int taps, KW, dil, ph, pw, kchunks;          // kchunks = Cin / 64
+  // "tall" mode (KH > 1, N = 64): ONE activation box per (kx, channel chunk) covers the rows of all KH taps of that
+  // column - TH + (KH-1)*dil image rows of TW pixels - and tap ky reads it at row offset ky*dil (whole image rows =
+  // multiples of the 1024-byte swizzle atom, so the operand descriptor just moves its start address): KH x fewer
+  // activation bytes through the TMA / L2 -> SM path, which is what bounds these kernels (ncu: 4.8 TB/s of TMA
+  // traffic, tensor pipe 17 %)
+  int tall, KH, a_bytes, stage_bytes, nstages;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -85,7 +91,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
 
   const int tiles_img = g.tiles_x * g.tiles_y;
   const int num_tiles = g.B * tiles_img;
-  const int num_kb = g.taps * g.kchunks;
+  const int num_kb = g.taps * g.kchunks;                    // weight k-blocks
+  const int units = g.tall ? g.KW * g.kchunks : num_kb;     // load units (ring slots) per tile
+  const int nst = g.nstages;
+  const int ntap = g.tall ? g.KH : 1;                       // taps served by one load unit
+  const int n_outer = g.tall ? g.KW : g.taps;               // load units per tile = n_outer x kchunks
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -124,17 +134,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, rem = tile - b * tiles_img;
         const int y0 = (rem / g.tiles_x) * TH, x0 = (rem % g.tiles_x) * TW;
-        for (int tap = 0; tap < g.taps; ++tap) {
-          const int oy = (tap / g.KW) * g.dil - g.ph, ox = (tap % g.KW) * g.dil - g.pw;
-          for (int kc = 0; kc < g.kchunks; ++kc, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_expect_tx(full_bar(s), (uint32_t)cfg::STAGE_BYTES);
-            const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
-            tma_load_4d(sa, &tma_x, full_bar(s), kc * BK, x0 + ox, y0 + oy, b);
-            if (!WRES) tma_load_2d(sa + cfg::A_BYTES, &tma_w, full_bar(s), (tap * g.kchunks + kc) * BK, 0);
+        // (no integer divisions in these loops: one elected thread issues every load of the CTA)
+        int s = (int)(it % (uint32_t)nst);
+        uint32_t ph = (it / (uint32_t)nst) & 1u;
+        for (int t0 = 0, ty = 0, tx = 0; t0 < n_outer; ++t0) {        // t0: tap (plain: ty, tx = its row, column) or kx (tall)
+         const int oy = g.tall ? -g.ph : ty * g.dil - g.ph;
+         const int ox = (g.tall ? t0 : tx) * g.dil - g.pw;
+         if (++tx == g.KW) { tx = 0; ++ty; }
+         for (int kc = 0; kc < g.kchunks; ++kc, ++it) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), (uint32_t)g.stage_bytes);
+          const uint32_t sa = stage_base + (uint32_t)(s * g.stage_bytes);
+          tma_load_4d(sa, &tma_x, full_bar(s), kc * BK, x0 + ox, y0 + oy, b);
+          if (!WRES) {
+            for (int t = 0; t < ntap; ++t) {
+              const int tap = g.tall ? t * g.KW + t0 : t0;
+              tma_load_2d(sa + (uint32_t)(g.a_bytes + t * cfg::B_BYTES), &tma_w, full_bar(s), (tap * g.kchunks + kc) * BK, 0);
+            }
           }
+          if (++s == nst) { s = 0; ph ^= 1u; }
+         }
         }
       }
     }
@@ -147,18 +166,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
         mbar_wait(tempty_bar(acc), ((lt >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
+        int s = (int)(it % (uint32_t)nst);
+        uint32_t ph = (it / (uint32_t)nst) & 1u;
+        for (int t0 = 0, u = 0; t0 < n_outer; ++t0) {
+         for (int kc = 0; kc < g.kchunks; ++kc, ++u, ++it) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = stage_base + (uint32_t)s * cfg::STAGE_BYTES;
-          const uint64_t adesc = smem_desc_sw128(sa);
-          const uint64_t bdesc = smem_desc_sw128(WRES ? w_base + (uint32_t)(kb * cfg::B_BYTES) : sa + cfg::A_BYTES);
+          const uint32_t sa = stage_base + (uint32_t)(s * g.stage_bytes);
+          for (int t = 0; t < ntap; ++t) {
+            const int kb = g.tall ? ((t * g.KW + t0) * g.kchunks + kc) : u;          // weight k-block of this tap
+            // tall: tap ky = t starts t*dil image rows (of TW pixels x 128 B) into the box
+            const uint64_t adesc = smem_desc_sw128(sa + (uint32_t)(g.tall ? t * g.dil * (TW * 128) : 0));
+            const uint64_t bdesc = smem_desc_sw128(WRES ? w_base + (uint32_t)(kb * cfg::B_BYTES)
+                                                        : sa + (uint32_t)(g.a_bytes + t * cfg::B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), cfg::IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), cfg::IDESC,
+                          (u > 0 || t > 0 || k > 0) ? 1u : 0u);
+          }
           tc_commit(empty_bar(s));
+          if (++s == nst) { s = 0; ph ^= 1u; }
+         }
         }
         tc_commit(tfull_bar(acc));
       }
@@ -443,13 +471,14 @@ static int launch_igemm(const CUtensorMap& mx, const CUtensorMap& mw, bf16* C, i
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          cfg::SMEM_BYTES);
+                                          226 * 1024);          // + < 1 KB of static shared memory
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
   const int tiles = g.B * g.tiles_x * g.tiles_y;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  S2U_LAUNCH((conv_igemm_kernel<BN, STAGES, WRES>), grid, THREADS, cfg::SMEM_BYTES, st, mx, mw, C, ldc, g, bias, resid, ld_res,
+  const size_t smem = (size_t)g.nstages * g.stage_bytes + cfg::W_BYTES + 1024;
+  S2U_LAUNCH((conv_igemm_kernel<BN, STAGES, WRES>), grid, THREADS, smem, st, mx, mw, C, ldc, g, bias, resid, ld_res,
              relu, sums, fin);
   S2U_LAUNCH_CHECK();
   return 0;
@@ -481,15 +510,38 @@ static int conv_igemm_impl(const void* x, int ldx, int B, int H, int W, int Cin,
   g.taps = KH * KW; g.KW = KW; g.dil = dil;
   g.ph = dil * (KH - 1) / 2; g.pw = dil * (KW - 1) / 2;
   g.kchunks = Cin / 64;
+  // ring geometry: plain = one [128 px x 64 ch] box (+ one weight k-block) per (tap, chunk); tall (KH > 1, N = 64) = one
+  // box of TH + (KH-1)*dil image rows (+ KH weight k-blocks) per (kx, chunk)
+  const bool wres = N == 64 && g.taps * g.kchunks <= cig::WRES_MAX_KB;
+  const int b_bytes = N * cig::BK * 2, budget = 226 * 1024 - 1024 - (wres ? cig::WRES_MAX_KB * b_bytes : 0);
+  static int tall_on = -1;
+  if (tall_on < 0) { const char* e = getenv("S2U_CONV_TALL"); tall_on = (e && e[0] == '0') ? 0 : 1; }
+  g.KH = KH;
+  g.tall = 0;
+  g.a_bytes = cig::BM * cig::BK * 2;
+  g.stage_bytes = g.a_bytes + (wres ? 0 : b_bytes);
+  int box_rows = cig::TH;
+  if (tall_on && N == 64 && KH > 1) {
+    const int rows = cig::TH + (KH - 1) * dil;
+    const int stage = rows * cig::TW * 128 + (wres ? 0 : KH * b_bytes);
+    if (rows <= 256 && budget / stage >= 2) {
+      g.tall = 1;
+      g.a_bytes = rows * cig::TW * 128;
+      g.stage_bytes = stage;
+      box_rows = rows;
+    }
+  }
+  const int max_st = N == 64 ? 8 : (N == 128 ? 6 : 4);
+  g.nstages = budget / g.stage_bytes < max_st ? budget / g.stage_bytes : max_st;
   CUtensorMap mx, mw;
-  int rc = cig::make_map_nhwc(&mx, x, B, H, W, Cin, ldx, cig::TW, cig::TH);
+  int rc = cig::make_map_nhwc(&mx, x, B, H, W, Cin, ldx, cig::TW, box_rows);
   if (rc) return rc;
   rc = cig::make_map_w(&mw, Wm, N, (long long)g.taps * Cin, N);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (N) {
     case 64:
-      if (g.taps * g.kchunks <= cig::WRES_MAX_KB)
+      if (wres)
         return cig::launch_igemm<64, 8, true>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
       return cig::launch_igemm<64, 8, false>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
     case 128: return cig::launch_igemm<128, 6, false>(mx, mw, (bf16*)out, ld_out, g, bias, (const bf16*)resid, ld_res, relu, sums, fin, st);
