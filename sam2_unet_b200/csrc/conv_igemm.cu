@@ -306,15 +306,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const __grid_con
 
 // ---------------------------------------------------------------------------------------------- weight gradient
 constexpr int WG_STAGES = 4;
-constexpr int WG_X_BYTES = 2 * 64 * 128;      // two [64 px x 64 ch] boxes = the 128 rows of D
-constexpr int WG_Y_BYTES = 64 * 128;
+constexpr int WG_TPH = 16;                    // pixel tile: 8 px wide x 16 rows = two 64-pixel K groups per TMA box (the
+                                              // kernels are bound by the number of boxes in flight, not by their bytes)
+constexpr int WG_PX = 8 * WG_TPH;
+constexpr int WG_X_BYTES = 2 * WG_PX * 128;   // two [128 px x 64 ch] boxes = the 128 rows of D
+constexpr int WG_Y_BYTES = WG_PX * 128;
 constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_Y_BYTES;
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024;
 constexpr uint32_t WG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                               ((uint32_t)(128 >> 4) << 24);
 
 struct WGeo {
-  int B, H, W, tiles_x, tiles_y;               // 8 x 8 pixel tiles
+  int B, H, W, tiles_x, tiles_y;               // 8 x WG_TPH pixel tiles
   int taps, KW, dil, ph, pw, kchunks, Cin, Cout;
 };
 
@@ -374,12 +377,12 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const __grid_constant__
       const uint32_t ph = (uint32_t)(i / WG_STAGES) & 1u;
       const int tile = t_beg + i;
       const int b = tile / tiles_img, rem = tile - b * tiles_img;
-      const int y0 = (rem / g.tiles_x) * 8, x0 = (rem % g.tiles_x) * 8;
+      const int y0 = (rem / g.tiles_x) * WG_TPH, x0 = (rem % g.tiles_x) * 8;
       mbar_wait(empty_bar(s), ph ^ 1u);
       mbar_expect_tx(full_bar(s), (uint32_t)WG_STAGE_BYTES);
       const uint32_t sa = smem_base + (uint32_t)s * WG_STAGE_BYTES;
       tma_load_4d(sa, &tma_x, full_bar(s), c0[0], x0 + ox[0], y0 + oy[0], b + bsel[0]);
-      tma_load_4d(sa + 8192, &tma_x, full_bar(s), c0[1], x0 + ox[1], y0 + oy[1], b + bsel[1]);
+      tma_load_4d(sa + WG_PX * 128, &tma_x, full_bar(s), c0[1], x0 + ox[1], y0 + oy[1], b + bsel[1]);
       tma_load_4d(sa + WG_X_BYTES, &tma_dy, full_bar(s), 0, x0, y0, b);
     }
   } else if (warp == 1 && lane == 0) {
@@ -390,9 +393,9 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t sa = smem_base + (uint32_t)s * WG_STAGE_BYTES;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {                        // 16 pixels (two 8-row groups = 2048 B) per instruction
-        const uint64_t adesc = smem_desc_mn_sw128(sa + (uint32_t)k * 2048u, 8192u);
-        const uint64_t bdesc = smem_desc_mn_sw128(sa + WG_X_BYTES + (uint32_t)k * 2048u, 8192u);
+      for (int k = 0; k < WG_PX / 16; ++k) {               // 16 pixels (two 8-row groups = 2048 B) per instruction
+        const uint64_t adesc = smem_desc_mn_sw128(sa + (uint32_t)k * 2048u, (uint32_t)(WG_PX * 128));
+        const uint64_t bdesc = smem_desc_mn_sw128(sa + WG_X_BYTES + (uint32_t)k * 2048u, (uint32_t)(WG_PX * 128));
         tc_mma_bf16(tmem_base, adesc, bdesc, WG_IDESC, (i > 0 || k > 0) ? 1u : 0u);
       }
       tc_commit(empty_bar(s));
@@ -579,14 +582,14 @@ int s2u_conv_wgrad(const void* dy, int ld_dy, const void* x, int ldx, float* G, 
     return S2U_EUNSUPPORTED;
   cig::WGeo g;
   g.B = B; g.H = H; g.W = W;
-  g.tiles_x = ceil_div(W, 8); g.tiles_y = ceil_div(H, 8);
+  g.tiles_x = ceil_div(W, 8); g.tiles_y = ceil_div(H, cig::WG_TPH);
   g.taps = KH * KW; g.KW = KW; g.dil = dil;
   g.ph = dil * (KH - 1) / 2; g.pw = dil * (KW - 1) / 2;
   g.kchunks = Cin / 64; g.Cin = Cin; g.Cout = Cout;
   CUtensorMap mx, my;
-  int rc = cig::make_map_nhwc(&mx, x, B, H, W, Cin, ldx, 8, 8);
+  int rc = cig::make_map_nhwc(&mx, x, B, H, W, Cin, ldx, 8, cig::WG_TPH);
   if (rc) return rc;
-  rc = cig::make_map_nhwc(&my, dy, B, H, W, Cout, ld_dy, 8, 8);
+  rc = cig::make_map_nhwc(&my, dy, B, H, W, Cout, ld_dy, 8, cig::WG_TPH);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -604,7 +607,7 @@ int s2u_conv_wgrad(const void* dy, int ld_dy, const void* x, int ldx, float* G, 
     if (mult < 1) mult = 1;
   }
   int splits = (mult * cig::num_sms() + xt - 1) / xt;
-  if (splits > total / 4) splits = total / 4;               // at least 4 pixel tiles per CTA
+  if (splits > total / 2) splits = total / 2;               // at least 2 pixel tiles per CTA
   if (splits < 1) splits = 1;
   const int per = (total + splits - 1) / splits;
   splits = (total + per - 1) / per;
