@@ -227,6 +227,24 @@ int s2u_cc_stats(const int* plabels, const int* glabels, long long n, int* parea
 int s2u_preprocess(const unsigned char* img, int H, int W, int S, int new_h, int new_w, int pad_left, int pad_top,
                    const float* mean3_host, const float* std3_host, float* tmp, float* out, void* stream);
 
+/* ---- training-time input pipeline on the device (dataset.py:34-333, FullDataset's train transform) -----------
+ * The random decisions stay on the host (sam2_unet_b200/augment.py draws them in the reference's order); one launch per
+ * transform on a [3,S,S] fp32 image / [1,S,S] fp32 label.
+ * s2u_aug_resize_pad: ResizeLongestSideAndPad from the uint8 sources (mode 0: pad to [ph,pw] at (off_y, off_x) with white
+ *   fill / label 0; mode 1: crop [ph,pw] at (off_y, off_x)), antialiased bilinear (image) / nearest (label) resize to
+ *   [new_h,new_w], centred in S x S with zeros; tmp = 3*ph*new_w floats.
+ * s2u_aug_rot90: RandomRotate (k x 90 degrees counter-clockwise, k = 1..3).
+ * s2u_aug_color: op 0 grayscale, 1 brightness, 2 contrast (ws = one double of scratch), 3 saturation, 4 hue, 5 gamma,
+ *   6 normalise (host mean / std); factor_c = (float)(1.0 - factor) for the blends.
+ * s2u_aug_blur: GaussianBlur k = 3 | 5 with the k normalised 1-D weights (host), reflect padding. */
+int s2u_aug_resize_pad(const unsigned char* img, const unsigned char* lab, int H, int W, int mode, int off_y, int off_x,
+                       int ph, int pw, int S, int new_h, int new_w, int pad_left, int pad_top, float* tmp, float* out_img,
+                       float* out_lab, void* stream);
+int s2u_aug_rot90(const float* in, float* out, int C, int S, int k, void* stream);
+int s2u_aug_color(float* img, int S, int op, float factor, float factor_c, double* ws, const float* m3_host,
+                  const float* s3_host, void* stream);
+int s2u_aug_blur(const float* in, float* out, int S, int k, const float* w1_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ from .model import SAM2UNet  # noqa: F401
 from .optim import FusedAdamW, Predictor, TrainStep, cosine_lr  # noqa: F401
 from .evalmetrics import evaluate_dataset, evaluate_segmentation_performance  # noqa: F401
 from .postprocess import infer_tail, preprocess_image  # noqa: F401
+from .augment import TrainAugment, draw_train_params  # noqa: F401
 
 __all__ = ["SAM2UNet", "structure_loss", "structure_loss3", "FusedAdamW", "TrainStep", "Predictor", "cosine_lr",
-           "infer_tail", "preprocess_image", "evaluate_segmentation_performance", "evaluate_dataset", "trunk_config"]
+           "infer_tail", "preprocess_image", "TrainAugment", "draw_train_params", "evaluate_segmentation_performance", "evaluate_dataset", "trunk_config"]

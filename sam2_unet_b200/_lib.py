@@ -65,6 +65,10 @@ SIGNATURES = {
     "s2u_cc_label": [P, F, I, I, P, P, P, I, P],
     "s2u_cc_stats": [P, P, L, P, P, P, P, I, P, P],
     "s2u_preprocess": [P, I, I, I, I, I, I, I, P, P, P, P, P],
+    "s2u_aug_resize_pad": [P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P],
+    "s2u_aug_rot90": [P, P, I, I, I, P],
+    "s2u_aug_color": [P, I, I, F, F, P, P, P, P],
+    "s2u_aug_blur": [P, P, I, I, P, P],
     "s2u_adamw": [P, P, P, P, L, P, F, F, F, F, P],
 }
 

@@ -15,7 +15,7 @@ def stage() -> bool:
     if not os.path.isfile(os.path.join(SRC, "SAM2UNet.py")):
         return False
     os.makedirs(DST, exist_ok=True)
-    for name in ("SAM2UNet.py", "train.py", "LICENSE"):
+    for name in ("SAM2UNet.py", "train.py", "dataset.py", "eval.py", "LICENSE"):
         shutil.copy2(os.path.join(SRC, name), os.path.join(DST, name))
     for sub in ("sam2", "sam2_configs"):
         dst = os.path.join(DST, sub)

@@ -386,3 +386,69 @@ def test_load_hiera_checkpoint_against_live_reference(tmp_path):
         n += 1
     assert n == sum(1 for nme, _ in m.encoder.named_parameters() if ".prompt_learn." not in nme)
     del ref_model
+
+
+# ------------------------------------------------------------------------------------------ training-time input pipeline
+
+def _augment_inputs(seed):
+    from oracle.make_golden_augment import inputs
+    return inputs(seed)
+
+
+def test_augment_oracle_against_reference_vectors():
+    """oracle/augment_port.py (the CPU restatement of dataset.py:288-313) reproduces tests/golden/augment_train.npz, which
+    the unmodified reference transform wrote (oracle/make_golden_augment.py): same `random.seed`, same uint8 inputs."""
+    import random
+    from oracle import augment_port as ap
+    g = np.load(os.path.join(GOLD, "augment_train.npz"))
+    S = int(g["size"])
+    assert len(g["seeds"]) >= 6
+    for seed in g["seeds"].tolist():
+        img, lab = _augment_inputs(seed)
+        random.seed(seed)
+        out = ap.apply(ap.draw(S, *lab.shape), torch.from_numpy(img), torch.from_numpy(lab), S)
+        assert torch.equal(out["label"], torch.from_numpy(g[f"label_{seed}"])), seed
+        err = (out["image"] - torch.from_numpy(g[f"image_{seed}"])).abs().max().item()
+        assert err <= 1e-5, (seed, err)
+
+
+def test_augment_draw_matches_the_oracle_draw():
+    """The product's host-side decision draw consumes `random` exactly like the oracle's (and so like the reference)."""
+    import random
+    from oracle import augment_port as ap
+    from sam2_unet_b200.augment import draw_train_params
+    for seed in range(200):
+        random.seed(seed)
+        a = ap.draw(352, 300 + seed, 517 - seed)
+        sa = random.random()
+        random.seed(seed)
+        b = draw_train_params(352, 300 + seed, 517 - seed)
+        sb = random.random()
+        assert sa == sb
+        assert a["geom"][1:] == b["geom"][1:] and (a["geom"][0] == "crop") == (b["geom"][0] == 1)
+        assert (a["rot"], a["gray"], a["color"], a["blur"]) == (b["rot"], b["gray"], b["color"], b["blur"])
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/dataset.py"), reason="reference not present")
+def test_augment_oracle_against_live_reference():
+    """60 more seeds straight through the reference's transform classes (needs torchvision, cv2 and PIL here)."""
+    import importlib.util
+    import random
+    pytest.importorskip("cv2")
+    from PIL import Image
+    from torchvision import transforms
+    from oracle import augment_port as ap
+    spec = importlib.util.spec_from_file_location("ref_dataset", "/root/reference/dataset.py")
+    rd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rd)
+    S = 64
+    tf = transforms.Compose([rd.ToTensor(), rd.ResizeLongestSideAndPad(S), rd.RandomRotate(), rd.ToGray(),
+                             rd.ColorAugmentations(), rd.GaussianBlur(), rd.Normalize()])
+    for seed in range(500, 560):
+        img, lab = _augment_inputs(seed)
+        random.seed(seed)
+        ref = tf({"image": Image.fromarray(img), "label": Image.fromarray(lab)})
+        random.seed(seed)
+        out = ap.apply(ap.draw(S, *lab.shape), torch.from_numpy(img), torch.from_numpy(lab), S)
+        assert torch.equal(out["label"], ref["label"]), seed
+        assert (out["image"] - ref["image"]).abs().max().item() <= 1e-5, seed

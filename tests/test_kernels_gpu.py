@@ -613,6 +613,65 @@ def test_preprocess_image(cuda, case):
         preprocess_image(torch.from_numpy(img), S)                                 # CPU tensor: no fallback
 
 
+# ------------------------------------------------------------------------------------------ training-time input path
+
+def test_train_augment_against_reference_vectors(cuda):
+    """TrainAugment (csrc/augment.cu) on the reference's own outputs: tests/golden/augment_train.npz was written by the
+    unmodified FullDataset(mode="train") transform (dataset.py:288-313) with `random.seed(seed)`; the device pipeline
+    draws from `random` in the same order, so the same seed must give the same sample.  Labels bit-exact; image within
+    3e-5 (fp32, values in [-2.2, 2.7]; pow / division orders of the colour ops differ in the last bit)."""
+    import os
+    import random
+    import numpy as np
+    from oracle.make_golden_augment import inputs
+    from sam2_unet_b200 import TrainAugment
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augment_train.npz"))
+    S = int(g["size"])
+    aug = TrainAugment(S, cuda)
+    for seed in g["seeds"].tolist():
+        img, lab = inputs(seed)
+        random.seed(seed)
+        out = aug(img, lab)
+        assert torch.equal(out["label"].cpu(), torch.from_numpy(g[f"label_{seed}"])), seed
+        err = (out["image"].cpu() - torch.from_numpy(g[f"image_{seed}"])).abs().max().item()
+        assert err <= 3e-5, (seed, err)
+    with pytest.raises(Exception):
+        TrainAugment(S, "cpu")                                                     # no CPU fallback
+
+
+@pytest.mark.parametrize("size,hw", [(352, (300, 420)), (352, (1080, 1920)), (96, (97, 41)), (1024, (700, 500))])
+def test_train_augment_against_oracle(cuda, size, hw):
+    """30 seeded samples per shape against oracle/augment_port.py (pinned to the live reference by tests/test_cpu.py), at
+    the network sizes; plus every colour op / blur size / rotation forced once through explicit parameters."""
+    import random
+    import numpy as np
+    from oracle import augment_port as ap
+    from sam2_unet_b200 import TrainAugment
+    H, W = hw
+    rng = np.random.default_rng(H * 7 + W)
+    base = rng.integers(0, 256, (H // 8 + 2, W // 8 + 2, 3)).astype(np.float32)
+    img = np.clip(np.kron(base, np.ones((8, 8, 1), np.float32))[:H, :W] + rng.normal(0, 12, (H, W, 3)), 0, 255).astype(np.uint8)
+    lab = (np.kron(rng.random((H // 8 + 2, W // 8 + 2)), np.ones((8, 8)))[:H, :W] > 0.5).astype(np.uint8) * 255
+    aug = TrainAugment(size, cuda)
+    img_d, lab_d = torch.from_numpy(img).to(cuda), torch.from_numpy(lab).to(cuda)
+    n = 30 if size <= 352 else 6
+    plist = []
+    for seed in range(n):
+        random.seed(seed)
+        plist.append(ap.draw(size, H, W))
+    forced = [("brightness", 0.7), ("contrast", 1.3), ("saturation", 0.6), ("hue", -0.37), ("hue", 0.5), ("gamma", 1.4)]
+    for i, op in enumerate(forced):
+        plist.append({"geom": ("crop", 3, 5, H - 7, W - 9) if i % 2 else ("pad", 11, 4, H + 30, W + 17), "rot": i % 4,
+                      "gray": False, "color": [op], "blur": (0, 3, 5)[i % 3]})
+    for p in plist:
+        ref = ap.apply(p, torch.from_numpy(img), torch.from_numpy(lab), size)
+        q = dict(p, geom=(0 if p["geom"][0] == "pad" else 1,) + tuple(p["geom"][1:]))
+        out = aug(img_d, lab_d, params=q)
+        assert torch.equal(out["label"].cpu(), ref["label"]), p
+        err = (out["image"].cpu() - ref["image"]).abs().max().item()
+        assert err <= 3e-5, (p, err)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(5808, 576, 32), (1452, 1152, 32), (3000, 144, 32), (777, 64, 64)])
 def test_wgrad_pair(cuda, dtype, shape):

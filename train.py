@@ -7,9 +7,10 @@ reference's file names, train.py:127-149), same state-dict files.  The step itse
 captured in one CUDA graph, with the loss read back only when it is printed (the reference syncs every step at
 train.py:81).  Under torchrun the batch is sharded over ranks and gradients are all-reduced over NCCL.
 
-Data: the reference's own `dataset.py` / `eval.py` (CPU image I/O, augmentation and metrics: out of scope of this
-package) are used unchanged when they are importable; otherwise a minimal folder loader and an on-device IoU stand
-in, and `--synthetic N` trains on N seeded synthetic images without any files.
+Data: files are decoded to uint8 on the host workers; the reference's training transform (dataset.py:288-313) runs on
+the device (`sam2_unet_b200.TrainAugment`, random decisions drawn in the reference's order), the evaluation set goes
+through `preprocess_image` / `infer_tail` and the on-device metrics.  `--cpu_augment` uses the reference's own
+`dataset.FullDataset` unchanged when it is importable; `--synthetic N` trains on N seeded synthetic images, no files.
 """
 from __future__ import annotations
 
@@ -19,7 +20,6 @@ import time
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from sam2_unet_b200 import (SAM2UNet, TrainStep, cosine_lr, evaluate_dataset, evaluate_segmentation_performance,
                             infer_tail, preprocess_image)
@@ -31,14 +31,16 @@ def structure_loss(pred, mask):
     return _sl(pred, mask)
 
 
-class _FolderData(torch.utils.data.Dataset):
-    """Longest-side resize + zero pad to `size`, ImageNet normalisation (dataset.py:34-143 without augmentation)."""
+class _RawFiles(torch.utils.data.Dataset):
+    """The training FILES of the reference's FullDataset (dataset.py:288-333: sorted .jpg/.png images, .png masks), decoded
+    to uint8 on the host workers; the transform itself (ToTensor ... Normalize, dataset.py:300-310) runs on the device in
+    `sam2_unet_b200.TrainAugment`, with the random decisions drawn like the reference draws them."""
 
-    def __init__(self, image_root, gt_root, size):
-        from PIL import Image  # noqa: F401
+    def __init__(self, image_root, gt_root):
         self.images = sorted(os.path.join(image_root, f) for f in os.listdir(image_root) if f.endswith((".jpg", ".png")))
         self.gts = sorted(os.path.join(gt_root, f) for f in os.listdir(gt_root) if f.endswith(".png"))
-        self.size = size
+        if len(self.images) != len(self.gts):
+            raise ValueError(f"{len(self.images)} training images but {len(self.gts)} masks")
 
     def __len__(self):
         return len(self.images)
@@ -46,16 +48,23 @@ class _FolderData(torch.utils.data.Dataset):
     def __getitem__(self, i):
         import numpy as np
         from PIL import Image
-        img = torch.from_numpy(np.asarray(Image.open(self.images[i]).convert("RGB"), dtype=np.float32) / 255).permute(2, 0, 1)
-        gt = torch.from_numpy(np.asarray(Image.open(self.gts[i]).convert("L"), dtype=np.float32) / 255)[None]
-        s = self.size / max(img.shape[1:])
-        hw = (max(1, round(img.shape[1] * s)), max(1, round(img.shape[2] * s)))
-        img = F.interpolate(img[None], size=hw, mode="bilinear", align_corners=False)[0]
-        gt = (F.interpolate(gt[None], size=hw, mode="nearest")[0] > 0.5).float()
-        pad = (0, self.size - hw[1], 0, self.size - hw[0])
-        mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
-        std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
-        return {"image": F.pad((img - mean) / std, pad), "label": F.pad(gt, pad)}
+        img = np.ascontiguousarray(np.asarray(Image.open(self.images[i]).convert("RGB")))
+        gt = np.ascontiguousarray(np.asarray(Image.open(self.gts[i]).convert("L")))
+        return torch.from_numpy(img), torch.from_numpy(gt)
+
+
+class _DeviceAugmentLoader:
+    """Wraps a DataLoader of raw uint8 (image, mask) pairs: every batch is augmented on the GPU and handed on as the
+    {"image": [B,3,S,S], "label": [B,1,S,S]} dictionary the reference's loader yields."""
+
+    def __init__(self, loader, size, device):
+        from sam2_unet_b200 import TrainAugment
+        self.loader, self.aug = loader, TrainAugment(size, device)
+
+    def __iter__(self):
+        for raw in self.loader:
+            items = [self.aug(img, gt) for img, gt in raw]
+            yield {"image": torch.stack([d["image"] for d in items]), "label": torch.stack([d["label"] for d in items])}
 
 
 class _Synthetic(torch.utils.data.Dataset):
@@ -106,11 +115,10 @@ def _datasets(args):
         ds = _Synthetic(args.synthetic, args.size)
         return ds, ds
     test = _TestFiles(args.test_image_path, args.test_gt_path)
-    try:                                             # the reference's own pipeline, unchanged, when it is on the path
+    if args.cpu_augment:                             # the reference's own CPU pipeline, unchanged (needs dataset.py)
         from dataset import FullDataset
         return FullDataset(args.train_image_path, args.train_mask_path, args.size, mode="train"), test
-    except ImportError:
-        return _FolderData(args.train_image_path, args.train_mask_path, args.size), test
+    return _RawFiles(args.train_image_path, args.train_mask_path), test
 
 
 @torch.no_grad()
@@ -149,8 +157,12 @@ def main(args):
     torch.cuda.set_device(device)
     train_ds, test_ds = _datasets(args)
     sampler = torch.utils.data.distributed.DistributedSampler(train_ds, shuffle=True) if ddp else None
+    raw = isinstance(train_ds, _RawFiles)
     loader = torch.utils.data.DataLoader(train_ds, batch_size=args.batch_size, shuffle=sampler is None, sampler=sampler,
-                                         num_workers=0 if args.synthetic else 8, drop_last=ddp, pin_memory=True)
+                                         num_workers=0 if args.synthetic else 8, drop_last=ddp, pin_memory=not raw,
+                                         collate_fn=(lambda items: items) if raw else None)
+    if raw:                                          # dataset.py:300-310 on the device (csrc/augment.cu)
+        loader = _DeviceAugmentLoader(loader, args.size, device)
     if os.path.exists(args.hiera_path):
         hiera = args.hiera_path
     elif args.synthetic > 0 or args.random_trunk or len(args.checkpoint) > 0:
@@ -246,6 +258,8 @@ if __name__ == "__main__":
     parser.add_argument("--model_cfg", default="sam2_hiera_s.yaml", help="trunk yaml: sam2_hiera_{t,s,b+,l}.yaml")
     parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    parser.add_argument("--cpu_augment", action="store_true",
+                        help="augment on the host with the reference's dataset.py instead of the device pipeline")
     parser.add_argument("--synthetic", type=int, default=0, help="train on N seeded synthetic images (no files needed)")
     parser.add_argument("--random_trunk", action="store_true", help="allow training without the pretrained Hiera weights")
     main(parser.parse_args())
