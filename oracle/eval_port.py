@@ -4,8 +4,10 @@ Follows /root/reference/eval.py:55-171 (`evaluate_segmentation_performance`) and
 line.  The reference labels connected components with skimage.measure.label / regionprops, which is NOT installed in
 this image (scikit-image, un-pinned in the reference's requirements): the labelling is restated with
 scipy.ndimage.label and a full 3x3 structuring element, i.e. skimage's documented default for 2-D input (connectivity =
-ndim = 8-neighbourhood, labels numbered in raster order of each component's first pixel).  PARITY UNPINNED against
-skimage itself for that one call; everything else is the reference's own numpy arithmetic.
+ndim = 8-neighbourhood, labels numbered in raster order of each component's first pixel).  Pinning: tests/test_cpu.py
+runs the UNMODIFIED reference eval.py (with a stand-in `skimage.measure` module, because skimage cannot be imported
+here) against this file and requires identical dictionaries, and checks the labelling three ways (scipy, a flood fill
+stating skimage's documented semantics, OpenCV).  PARITY UNPINNED against skimage's own binary for that one call.
 """
 import numpy as np
 from scipy import ndimage
@@ -54,3 +56,25 @@ def evaluate_segmentation_performance(pred_mask: np.ndarray, gt_mask: np.ndarray
         result[f"instance_recall_{suffix}"] = recall
         result[f"instance_f1_{suffix}"] = f1
     return result
+
+
+def evaluate_dataset(all_image_results: list) -> dict:
+    """eval.py:170-224: mean IoU / Dice over images; instance precision / recall / F1 from the true-positive counts
+    re-derived as precision * count_pred and summed over the data set (note: the reference stores the GROUND-TRUTH
+    component total under the key "images_count")."""
+    if not all_image_results:
+        return {}
+    total_gt = sum(r["count_gt"] for r in all_image_results)
+    total_pred = sum(r["count_pred"] for r in all_image_results)
+    out = {"mIoU": np.mean([r["semantic_iou"] for r in all_image_results]),
+           "mDice": np.mean([r["dice_coefficient"] for r in all_image_results]), "images_count": total_gt}
+    for thresh in IOU_THRESHOLDS:
+        suffix = int(thresh * 100)
+        tp = sum(r[f"instance_precision_{suffix}"] * r["count_pred"] for r in all_image_results)
+        precision = tp / total_pred if total_pred > 0 else 0.0
+        recall = tp / total_gt if total_gt > 0 else 0.0
+        f1 = (2 * precision * recall) / (precision + recall) if (precision + recall) > 0 else 0.0
+        out[f"Precision_{suffix}"] = precision
+        out[f"Recall_{suffix}"] = recall
+        out[f"F1_Score_{suffix}"] = f1
+    return out

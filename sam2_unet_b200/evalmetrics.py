@@ -10,6 +10,7 @@ aggregation (eval.py:170-224), pure host arithmetic.  No CPU fallback for the pi
 """
 from typing import Dict, List
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -113,8 +114,8 @@ def evaluate_dataset(all_image_results: List[Dict[str, float]]) -> Dict[str, flo
     """eval.py:170-224: mean IoU / Dice over images, instance precision / recall / F1 from the summed counts."""
     if not all_image_results:
         return {}
-    mean_iou = sum(r[SEMANTIC_IOU] for r in all_image_results) / len(all_image_results)
-    mean_dice = sum(r[DICE_COEFFICIENT] for r in all_image_results) / len(all_image_results)
+    mean_iou = float(np.mean([r[SEMANTIC_IOU] for r in all_image_results]))       # np.mean like the reference: the
+    mean_dice = float(np.mean([r[DICE_COEFFICIENT] for r in all_image_results]))  # same (pairwise) summation order
     total_gt = sum(r[COUNT_GT] for r in all_image_results)
     total_pred = sum(r[COUNT_PRED] for r in all_image_results)
     final = {MIOU: mean_iou, MDICE: mean_dice, "images_count": total_gt}

@@ -302,6 +302,113 @@ def test_eval_oracle_known_answers():
     assert r["count_pred"] == 0 and r["instance_precision_50"] == 0.0 and r["dice_coefficient"] == 0.0
 
 
+def _blob_masks(seed, H=72, W=96):
+    """A prediction / ground-truth pair with several touching, diagonal and competing components (uint8 0..255)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    gt = np.zeros((H, W), np.uint8)
+    pred = np.zeros((H, W), np.float32)
+    for _ in range(int(rng.integers(1, 7))):
+        cy, cx, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(3, 14)
+        gt[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 255
+        dy, dx, s = rng.normal(0, 3), rng.normal(0, 3), rng.uniform(0.6, 1.3)
+        pred[(yy - cy - dy) ** 2 + (xx - cx - dx) ** 2 <= (r * s) ** 2] = rng.uniform(20, 255)
+    speck = rng.random((H, W)) < 0.004                                  # isolated / diagonal specks
+    pred[speck] = 200
+    return pred.astype(np.uint8), gt
+
+
+def _label_flood_fill(binary):
+    """An independent statement of what skimage.measure.label(binary) documents for a 2-D input with the default
+    connectivity (= ndim: the 8-neighbourhood), background 0, labels 1..n in raster order of each component's first
+    pixel: plain stack-based flood fill, no scipy / cv2."""
+    H, W = binary.shape
+    out = np.zeros((H, W), np.int64)
+    n = 0
+    for y in range(H):
+        for x in range(W):
+            if binary[y, x] and not out[y, x]:
+                n += 1
+                out[y, x] = n
+                stack = [(y, x)]
+                while stack:
+                    cy, cx = stack.pop()
+                    for ny in (cy - 1, cy, cy + 1):
+                        for nx in (cx - 1, cx, cx + 1):
+                            if 0 <= ny < H and 0 <= nx < W and binary[ny, nx] and not out[ny, nx]:
+                                out[ny, nx] = n
+                                stack.append((ny, nx))
+    return out
+
+
+def test_eval_oracle_labelling_three_ways():
+    """The one call of eval.py that cannot be run here (skimage.measure.label, eval.py:105-106; scikit-image is not in
+    this image): the oracle's scipy labelling, the flood-fill statement of skimage's documented semantics and OpenCV's
+    8-connected labelling give the same components, and the first two the same label ORDER (which the greedy matching
+    of eval.py:120-150 depends on)."""
+    from scipy import ndimage
+    cv2 = pytest.importorskip("cv2")
+    for seed in range(12):
+        pred, gt = _blob_masks(seed)
+        for m in (pred > 25.5, gt > 25.5):
+            b = m.astype(np.uint8)
+            a, na = ndimage.label(b, structure=np.ones((3, 3), np.uint8))
+            f = _label_flood_fill(b)
+            assert na == f.max() and np.array_equal(a, f)
+            nc, c = cv2.connectedComponents(b, connectivity=8)
+            assert nc - 1 == na
+            pairs = np.unique(np.stack([a[b > 0], c[b > 0]], 1), axis=0)          # a bijection between the label sets
+            assert len(pairs) == na and len(set(pairs[:, 0])) == na and len(set(pairs[:, 1])) == na
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/eval.py"), reason="reference not present")
+def test_eval_oracle_against_live_reference_eval_py():
+    """The UNMODIFIED /root/reference/eval.py executed here, with `skimage.measure` supplied by a stand-in module whose
+    `label` is the flood fill above and whose `regionprops` lists the labels in ascending order (skimage's documented
+    order): every line of evaluate_segmentation_performance / evaluate_dataset except the labelling call itself is the
+    reference's own code.  oracle/eval_port.py must reproduce its dictionaries exactly."""
+    import importlib.util
+    import sys
+    import types
+    pytest.importorskip("cv2")
+    from oracle import eval_port
+    sk, skm = types.ModuleType("skimage"), types.ModuleType("skimage.measure")
+    skm.label = _label_flood_fill
+    skm.regionprops = lambda lab: [types.SimpleNamespace(label=int(v)) for v in range(1, int(lab.max()) + 1)]
+    sk.measure = skm
+    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.measure")}
+    sys.modules.update({"skimage": sk, "skimage.measure": skm})
+    try:
+        spec = importlib.util.spec_from_file_location("ref_eval", "/root/reference/eval.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    theirs, mine = [], []
+    for seed in range(24):
+        pred, gt = _blob_masks(100 + seed)
+        if seed == 5:
+            pred[:] = 0
+        if seed == 6:
+            gt[:] = 0
+        a, b = ref.evaluate_segmentation_performance(pred, gt), eval_port.evaluate_segmentation_performance(pred, gt)
+        assert set(a) == set(b)
+        for k in a:
+            assert float(a[k]) == float(b[k]), (seed, k, a[k], b[k])
+        theirs.append(a)
+        mine.append(b)
+    A, B = ref.evaluate_dataset(theirs), eval_port.evaluate_dataset(mine)
+    assert list(A) == list(B)
+    for k in A:
+        assert float(A[k]) == float(B[k]), k
+    with pytest.raises(ValueError):
+        eval_port.evaluate_segmentation_performance(np.zeros((4, 4), np.uint8), np.zeros((4, 5), np.uint8))
+
+
 def _fake_upstream_checkpoint(model, path, seed=7):
     """A file shaped like Meta's sam2_hiera_*.pt: {"model": {"image_encoder.trunk.<hiera key>": tensor, ...other
     SAM2Base keys...}} (/root/reference/sam2/build_sam.py:79-89; SAM2-UNet keeps the trunk only, SAM2UNet.py:136-144)."""

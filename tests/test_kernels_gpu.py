@@ -583,8 +583,10 @@ def test_eval_metrics_vs_oracle(cuda, case):
         for k in ref:
             assert got[k] == ref[k], (k, got[k], ref[k])
         results.append(got)
-    agg = evaluate_dataset(results)
-    assert agg["mIoU"] == sum(r["semantic_iou"] for r in results) / len(results)
+    agg, agg_ref = evaluate_dataset(results), eval_port.evaluate_dataset(results)      # eval.py:170-224
+    assert list(agg) == list(agg_ref)
+    for k in agg_ref:
+        assert float(agg[k]) == float(agg_ref[k]), k
     with pytest.raises(Exception):
         evaluate_segmentation_performance(torch.from_numpy(pred), torch.from_numpy(gt))      # CPU tensors: no fallback
 
