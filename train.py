@@ -48,8 +48,8 @@ class _RawFiles(torch.utils.data.Dataset):
     def __getitem__(self, i):
         import numpy as np
         from PIL import Image
-        img = np.ascontiguousarray(np.asarray(Image.open(self.images[i]).convert("RGB")))
-        gt = np.ascontiguousarray(np.asarray(Image.open(self.gts[i]).convert("L")))
+        img = np.array(Image.open(self.images[i]).convert("RGB"))
+        gt = np.array(Image.open(self.gts[i]).convert("L"))
         return torch.from_numpy(img), torch.from_numpy(gt)
 
 
@@ -105,8 +105,8 @@ class _TestFiles:
     def __getitem__(self, i):
         import numpy as np
         from PIL import Image
-        img = np.ascontiguousarray(np.asarray(Image.open(self.images[i]).convert("RGB")))
-        gt = np.ascontiguousarray(np.asarray(Image.open(self.gts[i]).convert("L")))
+        img = np.array(Image.open(self.images[i]).convert("RGB"))
+        gt = np.array(Image.open(self.gts[i]).convert("L"))
         return torch.from_numpy(img), torch.from_numpy(gt)
 
 
