@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const __grid_constant__ 
 #endif
 constexpr int WS_EPI_WARPS = S2U_EPI_WARPS;            // 8 or 16: 2 or 4 warps per TMEM lane quarter
 constexpr int EPI_PARTS = WS_EPI_WARPS / 4;            // warps sharing a lane quarter take every EPI_PARTS-th 32-column chunk
-constexpr bool EPI_DB = EPI_PARTS == 2;                // side inputs prefetched one chunk ahead (two slots); with four warps
+constexpr bool EPI_DB = EPI_PARTS <= 3;               // side inputs prefetched one chunk ahead (two slots); with four warps
                                                        // per scheduler the other warps hide that latency and one slot suffices
 constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
 constexpr int EPI_BUF_BYTES = 32 * 64;                 // one staging tile: 32 rows x 64 bytes, 16-byte chunks XOR-swizzled
