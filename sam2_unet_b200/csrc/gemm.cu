@@ -365,6 +365,9 @@ constexpr int epi_warp_bytes(bool f32s) { return epi_tile_bytes(f32s) + EPI_BIAS
 constexpr int SMEM_BUDGET = 227 * 1024 - 512;
 constexpr int epi_bytes(bool f32s) { return (WS_EPI_WARPS * epi_warp_bytes(f32s) + 1023) & ~1023; }
 // deepest operand ring (<= 8 stages) that fits next to the epilogue staging
+#ifndef S2U_STAGE_DELTA
+#define S2U_STAGE_DELTA 0                              // tuning: -1 = the CTA-pair kernel with one operand stage fewer than fits
+#endif
 constexpr int fit_stages(int stage_bytes, bool f32s) {
   const int n = (SMEM_BUDGET - 1024 - epi_bytes(f32s)) / stage_bytes;
   return n > 8 ? 8 : n;
@@ -490,7 +493,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int BN, bool F32S>
 __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, uint32_t sbias, int q, int part, int lane,
                                               bf16* __restrict__ C, int ldc, int M, int N,
-                                              const EpiView<bf16>& epi, const CUtensorMap* mc, const CUtensorMap* mp) {
+                                              const EpiView<bf16>& epi, const CUtensorMap* mc, const CUtensorMap* mp,
+                                              bool direct) {
   const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
   const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;              // residual in the compute dtype
   const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
@@ -518,8 +522,21 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
   auto ring_tile = [&](uint32_t n) { return ring3 ? stg + (n % 3u) * (uint32_t)EPI_BUF_BYTES : so; };
   // one bf16 output chunk: registers -> staging tile -> global (TMA store when the chunk is a full box or is clipped
   // by the matrix edge, which the TMA unit handles; a chunk cut by the TILE edge (BN = 144) takes the per-lane path)
+  // `direct`: every lane stores its own 64-byte row segment straight from registers (no shared-memory round trip:
+  // the staging traffic competes with the tensor core's operand reads for the SM's shared-memory bandwidth)
+  auto row_store = [&](const float* v, bf16* dst, long long ld, long long row0, int col0, int rows_ok) {
+    if (lane < rows_ok) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst + (row0 + lane) * ld + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d4[j] = pack8(v + 8 * j);
+    }
+  };
   auto out16 = [&](const float* v, const CUtensorMap* map, bf16* dst, long long ld, long long row0, int col0,
                    int rows_ok, int cols_ok) {
+    if (!F32S && direct && cols_ok == 32) {
+      row_store(v, dst, ld, row0, col0, rows_ok);
+      return;
+    }
     if (map != nullptr && cols_ok == min(32, N - col0)) {
       const uint32_t tile = ring_tile(sn);
       if (lane == 0) {
@@ -636,6 +653,19 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       }
       if ((epi.flags & GEMM_GELU) && epi.pre_out && !pre_final && (epi.flags & GEMM_SAVE_DGELU)) {
         // v <- gelu(v), pre_out <- gelu'(v): both from one erf evaluation
+        if (!F32S && direct && dg_stage && cols_ok == 32) {
+          float dd[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 gg, d2;
+            gelu_dgelu2(make_float2(v[j], v[j + 1]), gg, d2);
+            v[j] = gg.x; v[j + 1] = gg.y;
+            dd[j] = d2.x; dd[j + 1] = d2.y;
+          }
+          row_store(dd, epi.pre_out, epi.ld_pre, row0, col0, rows_ok);
+          row_store(v, C, ldc, row0, col0, rows_ok);
+          continue;
+        }
         const bool dg_tma = dg_stage && ring3 && tma_c && tma_p && cols_ok == min(32, N - col0);
         const uint32_t td = dg_tma ? ring_tile(sn) : (dg_stage ? h0 : so), tg = dg_tma ? ring_tile(sn + 1) : so;
         if (tma_any) {                                                      // the tiles written below are free again
@@ -878,7 +908,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
                             smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
                             warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr);
+                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -999,7 +1029,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
     epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
                             smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
                             warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr);
+                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0);
   }
   tc_fence_before();
   cluster_sync_all();          // nobody leaves while the partner may still read its smem or signal its barriers
@@ -1216,7 +1246,9 @@ static int make_out_map(CUtensorMap* out, const void* ptr, long long rows, long 
 static int out_maps(CUtensorMap* mc, CUtensorMap* mp, bf16* C, int ldc, int M, int N, const GemmEpi& e, int* tma_out) {
   static int on = -1;
   if (on < 0) { const char* v = getenv("S2U_GEMM_TMA_STORE"); on = (v && v[0] == '1') ? 1 : 0; }
-  *tma_out = 0;
+  static int direct = -1;
+  if (direct < 0) { const char* v = getenv("S2U_GEMM_DIRECT_STORE"); direct = (v && v[0] == '1') ? 1 : 0; }
+  *tma_out = direct ? 4 : 0;
   memset(mc, 0, sizeof(*mc));
   memset(mp, 0, sizeof(*mp));
   if (!on || (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL))) return 0;
@@ -1307,7 +1339,8 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
 template <int BN>
 static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
                        const GemmEpi& e, cudaStream_t st) {
-  constexpr int STP = fit_stages((BM + BN / 2) * BK * 2, false), STS = fit_stages((BM + BN / 2) * BK * 2, true);
+  constexpr int STP = fit_stages((BM + BN / 2) * BK * 2, false) + S2U_STAGE_DELTA,
+                STS = fit_stages((BM + BN / 2) * BK * 2, true) + S2U_STAGE_DELTA;
   static_assert(STP >= 3 && STS >= 3, "operand ring");
   using cfgp = Cfg2<BN, STP, false>;
   using cfgs = Cfg2<BN, STS, true>;
