@@ -436,6 +436,36 @@ __device__ __forceinline__ void s2g_rows(uint32_t stg, char* __restrict__ dst, l
       *reinterpret_cast<uint4*>(dst + (long long)r * pitch + c * 16) = lds16(stg_addr(stg, r, c));
   }
 }
+// Two staging tiles side by side = rows of 128 bytes (32 fp32 columns: tile 0 holds columns 0..15, tile 1 columns
+// 16..31).  8 lanes move one row, so every instruction touches 4 FULL 128-byte lines instead of 8 half lines (the
+// epilogue is bound by the number of load / store requests, profiles/r2_gemm_bench_direct_store.txt).  Within a
+// quarter-warp the four lanes on tile 0 read row R and the four on tile 1 row R ^ 1: different banks.
+__device__ __forceinline__ void rows128_map(int lane, int i, int& r, int& half, int& c) {
+  const int ph = lane >> 3;
+  half = (lane >> 2) & 1;
+  c = lane & 3;
+  r = i * 4 + (ph >> 1) * 2 + ((ph & 1) ^ half);
+}
+__device__ __forceinline__ void g2s_async128(uint32_t t0, uint32_t t1, const char* __restrict__ src, long long pitch,
+                                             int rows_ok, int bytes_ok, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r, half, c;
+    rows128_map(lane, i, r, half, c);
+    if (r < rows_ok && half * 64 + c * 16 < bytes_ok)
+      cp_async16(stg_addr(half ? t1 : t0, r, c), src + (long long)r * pitch + half * 64 + c * 16);
+  }
+}
+__device__ __forceinline__ void s2g_rows128(uint32_t t0, uint32_t t1, char* __restrict__ dst, long long pitch,
+                                            int rows_ok, int bytes_ok, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r, half, c;
+    rows128_map(lane, i, r, half, c);
+    if (r < rows_ok && half * 64 + c * 16 < bytes_ok)
+      *reinterpret_cast<uint4*>(dst + (long long)r * pitch + half * 64 + c * 16) = lds16(stg_addr(half ? t1 : t0, r, c));
+  }
+}
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -494,7 +524,7 @@ template <int BN, bool F32S>
 __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, uint32_t sbias, int q, int part, int lane,
                                               bf16* __restrict__ C, int ldc, int M, int N,
                                               const EpiView<bf16>& epi, const CUtensorMap* mc, const CUtensorMap* mp,
-                                              bool direct) {
+                                              bool direct, bool half_lines) {
   const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
   const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;              // residual in the compute dtype
   const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
@@ -577,8 +607,12 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       g2s_async(b, reinterpret_cast<const char*>(side16 + row0 * ld16 + col0), ld16 * 2, rows_ok, cols_ok * 2, lane);
     } else {
       const char* s = reinterpret_cast<const char*>(side32 + row0 * epi.ld_res + col0);
-      g2s_async(b, s, (long long)epi.ld_res * 4, rows_ok, min(cols_ok, 16) * 4, lane);
-      if (cols_ok > 16) g2s_async(b + EPI_BUF_BYTES, s + 64, (long long)epi.ld_res * 4, rows_ok, (cols_ok - 16) * 4, lane);
+      if (half_lines) {
+        g2s_async(b, s, (long long)epi.ld_res * 4, rows_ok, min(cols_ok, 16) * 4, lane);
+        if (cols_ok > 16) g2s_async(b + EPI_BUF_BYTES, s + 64, (long long)epi.ld_res * 4, rows_ok, (cols_ok - 16) * 4, lane);
+      } else {
+        g2s_async128(b, b + EPI_BUF_BYTES, s, (long long)epi.ld_res * 4, rows_ok, cols_ok * 4, lane);
+      }
     }
   };
   // bf16 rows of this warp's chunk: registers -> output staging tile -> global
@@ -767,18 +801,21 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       if (F32S && out_f32) {
         // 16 fp32 columns per staging tile; with an fp32 residual each thread overwrites exactly the row it just read
         char* cdst = reinterpret_cast<char*>(reinterpret_cast<float*>(C) + row0 * ldc + col0);
+        const uint32_t x0 = side32 ? h0 : so, x1 = h1;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int cok = cols_ok - hh * 16;
-          if (cok <= 0) break;
-          const uint32_t x = side32 ? (hh ? h1 : h0) : (hh ? h1 : so);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            sts16(stg_addr(x, lane, j),
+            sts16(stg_addr(hh ? x1 : x0, lane, j),
                   make_uint4(__float_as_uint(v[hh * 16 + 4 * j]), __float_as_uint(v[hh * 16 + 4 * j + 1]),
                              __float_as_uint(v[hh * 16 + 4 * j + 2]), __float_as_uint(v[hh * 16 + 4 * j + 3])));
-          __syncwarp();
-          s2g_rows(x, cdst + hh * 64, (long long)ldc * 4, rows_ok, min(cok, 16) * 4, lane);
+        }
+        __syncwarp();
+        if (half_lines) {
+          s2g_rows(x0, cdst, (long long)ldc * 4, rows_ok, min(cols_ok, 16) * 4, lane);
+          if (cols_ok > 16) s2g_rows(x1, cdst + 64, (long long)ldc * 4, rows_ok, (cols_ok - 16) * 4, lane);
+        } else {
+          s2g_rows128(x0, x1, cdst, (long long)ldc * 4, rows_ok, cols_ok * 4, lane);
         }
         __syncwarp();
         if (epi.pre_out && pre_final)                                       // compute-dtype copy of the final value
@@ -908,7 +945,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
                             smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
                             warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0);
+                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0, (tma_out & 8) != 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -1029,7 +1066,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
     epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
                             smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
                             warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0);
+                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0, (tma_out & 8) != 0);
   }
   tc_fence_before();
   cluster_sync_all();          // nobody leaves while the partner may still read its smem or signal its barriers
@@ -1248,7 +1285,9 @@ static int out_maps(CUtensorMap* mc, CUtensorMap* mp, bf16* C, int ldc, int M, i
   if (on < 0) { const char* v = getenv("S2U_GEMM_TMA_STORE"); on = (v && v[0] == '1') ? 1 : 0; }
   static int direct = -1;
   if (direct < 0) { const char* v = getenv("S2U_GEMM_DIRECT_STORE"); direct = (v && v[0] == '1') ? 1 : 0; }
-  *tma_out = direct ? 4 : 0;
+  static int half_lines = -1;                 // S2U_GEMM_HALF_LINES=0: the stream epilogue moves full 128-byte lines
+  if (half_lines < 0) { const char* v = getenv("S2U_GEMM_HALF_LINES"); half_lines = (v && v[0] == '0') ? 0 : 1; }
+  *tma_out = (direct ? 4 : 0) | (half_lines ? 8 : 0);
   memset(mc, 0, sizeof(*mc));
   memset(mp, 0, sizeof(*mp));
   if (!on || (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL))) return 0;
