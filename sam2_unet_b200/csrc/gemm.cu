@@ -436,36 +436,6 @@ __device__ __forceinline__ void s2g_rows(uint32_t stg, char* __restrict__ dst, l
       *reinterpret_cast<uint4*>(dst + (long long)r * pitch + c * 16) = lds16(stg_addr(stg, r, c));
   }
 }
-// Two staging tiles side by side = rows of 128 bytes (32 fp32 columns: tile 0 holds columns 0..15, tile 1 columns
-// 16..31).  8 lanes move one row, so every instruction touches 4 FULL 128-byte lines instead of 8 half lines (the
-// epilogue is bound by the number of load / store requests, profiles/r2_gemm_bench_direct_store.txt).  Within a
-// quarter-warp the four lanes on tile 0 read row R and the four on tile 1 row R ^ 1: different banks.
-__device__ __forceinline__ void rows128_map(int lane, int i, int& r, int& half, int& c) {
-  const int ph = lane >> 3;
-  half = (lane >> 2) & 1;
-  c = lane & 3;
-  r = i * 4 + (ph >> 1) * 2 + ((ph & 1) ^ half);
-}
-__device__ __forceinline__ void g2s_async128(uint32_t t0, uint32_t t1, const char* __restrict__ src, long long pitch,
-                                             int rows_ok, int bytes_ok, int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int r, half, c;
-    rows128_map(lane, i, r, half, c);
-    if (r < rows_ok && half * 64 + c * 16 < bytes_ok)
-      cp_async16(stg_addr(half ? t1 : t0, r, c), src + (long long)r * pitch + half * 64 + c * 16);
-  }
-}
-__device__ __forceinline__ void s2g_rows128(uint32_t t0, uint32_t t1, char* __restrict__ dst, long long pitch,
-                                            int rows_ok, int bytes_ok, int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int r, half, c;
-    rows128_map(lane, i, r, half, c);
-    if (r < rows_ok && half * 64 + c * 16 < bytes_ok)
-      *reinterpret_cast<uint4*>(dst + (long long)r * pitch + half * 64 + c * 16) = lds16(stg_addr(half ? t1 : t0, r, c));
-  }
-}
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -523,8 +493,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int BN, bool F32S>
 __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, uint32_t sbias, int q, int part, int lane,
                                               bf16* __restrict__ C, int ldc, int M, int N,
-                                              const EpiView<bf16>& epi, const CUtensorMap* mc, const CUtensorMap* mp,
-                                              bool direct, bool half_lines) {
+                                              const EpiView<bf16>& epi, const CUtensorMap* mc, const CUtensorMap* mp) {
   const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
   const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;              // residual in the compute dtype
   const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
@@ -552,21 +521,8 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
   auto ring_tile = [&](uint32_t n) { return ring3 ? stg + (n % 3u) * (uint32_t)EPI_BUF_BYTES : so; };
   // one bf16 output chunk: registers -> staging tile -> global (TMA store when the chunk is a full box or is clipped
   // by the matrix edge, which the TMA unit handles; a chunk cut by the TILE edge (BN = 144) takes the per-lane path)
-  // `direct`: every lane stores its own 64-byte row segment straight from registers (no shared-memory round trip:
-  // the staging traffic competes with the tensor core's operand reads for the SM's shared-memory bandwidth)
-  auto row_store = [&](const float* v, bf16* dst, long long ld, long long row0, int col0, int rows_ok) {
-    if (lane < rows_ok) {
-      uint4* d4 = reinterpret_cast<uint4*>(dst + (row0 + lane) * ld + col0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) d4[j] = pack8(v + 8 * j);
-    }
-  };
   auto out16 = [&](const float* v, const CUtensorMap* map, bf16* dst, long long ld, long long row0, int col0,
                    int rows_ok, int cols_ok) {
-    if (!F32S && direct && cols_ok == 32) {
-      row_store(v, dst, ld, row0, col0, rows_ok);
-      return;
-    }
     if (map != nullptr && cols_ok == min(32, N - col0)) {
       const uint32_t tile = ring_tile(sn);
       if (lane == 0) {
@@ -607,12 +563,8 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       g2s_async(b, reinterpret_cast<const char*>(side16 + row0 * ld16 + col0), ld16 * 2, rows_ok, cols_ok * 2, lane);
     } else {
       const char* s = reinterpret_cast<const char*>(side32 + row0 * epi.ld_res + col0);
-      if (half_lines) {
-        g2s_async(b, s, (long long)epi.ld_res * 4, rows_ok, min(cols_ok, 16) * 4, lane);
-        if (cols_ok > 16) g2s_async(b + EPI_BUF_BYTES, s + 64, (long long)epi.ld_res * 4, rows_ok, (cols_ok - 16) * 4, lane);
-      } else {
-        g2s_async128(b, b + EPI_BUF_BYTES, s, (long long)epi.ld_res * 4, rows_ok, cols_ok * 4, lane);
-      }
+      g2s_async(b, s, (long long)epi.ld_res * 4, rows_ok, min(cols_ok, 16) * 4, lane);
+      if (cols_ok > 16) g2s_async(b + EPI_BUF_BYTES, s + 64, (long long)epi.ld_res * 4, rows_ok, (cols_ok - 16) * 4, lane);
     }
   };
   // bf16 rows of this warp's chunk: registers -> output staging tile -> global
@@ -687,19 +639,6 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       }
       if ((epi.flags & GEMM_GELU) && epi.pre_out && !pre_final && (epi.flags & GEMM_SAVE_DGELU)) {
         // v <- gelu(v), pre_out <- gelu'(v): both from one erf evaluation
-        if (!F32S && direct && dg_stage && cols_ok == 32) {
-          float dd[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float2 gg, d2;
-            gelu_dgelu2(make_float2(v[j], v[j + 1]), gg, d2);
-            v[j] = gg.x; v[j + 1] = gg.y;
-            dd[j] = d2.x; dd[j + 1] = d2.y;
-          }
-          row_store(dd, epi.pre_out, epi.ld_pre, row0, col0, rows_ok);
-          row_store(v, C, ldc, row0, col0, rows_ok);
-          continue;
-        }
         const bool dg_tma = dg_stage && ring3 && tma_c && tma_p && cols_ok == min(32, N - col0);
         const uint32_t td = dg_tma ? ring_tile(sn) : (dg_stage ? h0 : so), tg = dg_tma ? ring_tile(sn + 1) : so;
         if (tma_any) {                                                      // the tiles written below are free again
@@ -801,21 +740,18 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       if (F32S && out_f32) {
         // 16 fp32 columns per staging tile; with an fp32 residual each thread overwrites exactly the row it just read
         char* cdst = reinterpret_cast<char*>(reinterpret_cast<float*>(C) + row0 * ldc + col0);
-        const uint32_t x0 = side32 ? h0 : so, x1 = h1;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+          const int cok = cols_ok - hh * 16;
+          if (cok <= 0) break;
+          const uint32_t x = side32 ? (hh ? h1 : h0) : (hh ? h1 : so);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            sts16(stg_addr(hh ? x1 : x0, lane, j),
+            sts16(stg_addr(x, lane, j),
                   make_uint4(__float_as_uint(v[hh * 16 + 4 * j]), __float_as_uint(v[hh * 16 + 4 * j + 1]),
                              __float_as_uint(v[hh * 16 + 4 * j + 2]), __float_as_uint(v[hh * 16 + 4 * j + 3])));
-        }
-        __syncwarp();
-        if (half_lines) {
-          s2g_rows(x0, cdst, (long long)ldc * 4, rows_ok, min(cols_ok, 16) * 4, lane);
-          if (cols_ok > 16) s2g_rows(x1, cdst + 64, (long long)ldc * 4, rows_ok, (cols_ok - 16) * 4, lane);
-        } else {
-          s2g_rows128(x0, x1, cdst, (long long)ldc * 4, rows_ok, cols_ok * 4, lane);
+          __syncwarp();
+          s2g_rows(x, cdst + hh * 64, (long long)ldc * 4, rows_ok, min(cok, 16) * 4, lane);
         }
         __syncwarp();
         if (epi.pre_out && pre_final)                                       // compute-dtype copy of the final value
@@ -945,7 +881,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
                             smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
                             warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0, (tma_out & 8) != 0);
+                            (tma_out & 2) ? &tma_p : nullptr);
   }
   tc_fence_before();
   __syncthreads();
@@ -1066,7 +1002,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
     epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
                             smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
                             warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr, (tma_out & 4) != 0, (tma_out & 8) != 0);
+                            (tma_out & 2) ? &tma_p : nullptr);
   }
   tc_fence_before();
   cluster_sync_all();          // nobody leaves while the partner may still read its smem or signal its barriers
@@ -1280,14 +1216,14 @@ static int make_out_map(CUtensorMap* out, const void* ptr, long long rows, long 
 // (S2U_GEMM_TMA_STORE=1): measured on the stage-3 shapes it is a wash - fc1 with both outputs 25.6 -> 24.3 us, but the
 // single-tile cases (side input in the other slots) 20.3 -> 20.8 us and the whole step 684 -> 678 img/s
 // (profiles/r2_gemm_bench_tma_store.txt): the epilogue is not bound by the issue slots of its stores.
+// Two further store variants were measured and REMOVED again (their extra code paths cost the default path a stack
+// frame and ~5 % of the step): per-lane stores straight from registers (commit b439910: 4x the store requests, plain
+// 17.3 -> 25.5 us, profiles/r2_gemm_bench_direct_store.txt) and full 128-byte-line moves of the fp32 stream (commit
+// bcf06e9: 5-25 % slower, profiles/r2_gemm_bench_stream_full_lines.txt).
 static int out_maps(CUtensorMap* mc, CUtensorMap* mp, bf16* C, int ldc, int M, int N, const GemmEpi& e, int* tma_out) {
   static int on = -1;
   if (on < 0) { const char* v = getenv("S2U_GEMM_TMA_STORE"); on = (v && v[0] == '1') ? 1 : 0; }
-  static int direct = -1;
-  if (direct < 0) { const char* v = getenv("S2U_GEMM_DIRECT_STORE"); direct = (v && v[0] == '1') ? 1 : 0; }
-  static int half_lines = -1;                 // S2U_GEMM_HALF_LINES=0: the stream epilogue moves full 128-byte lines
-  if (half_lines < 0) { const char* v = getenv("S2U_GEMM_HALF_LINES"); half_lines = (v && v[0] == '0') ? 0 : 1; }
-  *tma_out = (direct ? 4 : 0) | (half_lines ? 8 : 0);
+  *tma_out = 0;
   memset(mc, 0, sizeof(*mc));
   memset(mp, 0, sizeof(*mp));
   if (!on || (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL))) return 0;
