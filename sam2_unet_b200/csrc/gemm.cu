@@ -357,10 +357,7 @@ constexpr int EPI_BUF_BYTES = 32 * 64;                 // one staging tile: 32 r
 // double-buffered) + one output tile
 // + two 128-byte bias segments (the chunk's 32 bias values, prefetched with the side input)
 constexpr int EPI_BIAS_BYTES = 256;
-// (the tiles of all warps come first, so that every tile is 512-byte aligned as the TMA 64-byte swizzle needs, then the
-// bias segments)
-constexpr int epi_tile_bytes(bool f32s) { return ((EPI_DB ? 2 : 1) * (f32s ? 2 : 1) + 1) * EPI_BUF_BYTES; }
-constexpr int epi_warp_bytes(bool f32s) { return epi_tile_bytes(f32s) + EPI_BIAS_BYTES; }
+constexpr int epi_warp_bytes(bool f32s) { return ((EPI_DB ? 2 : 1) * (f32s ? 2 : 1) + 1) * EPI_BUF_BYTES + EPI_BIAS_BYTES; }
 
 constexpr int SMEM_BUDGET = 227 * 1024 - 512;
 constexpr int epi_bytes(bool f32s) { return (WS_EPI_WARPS * epi_warp_bytes(f32s) + 1023) & ~1023; }
@@ -379,7 +376,6 @@ struct CfgWS {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARP_BYTES = epi_warp_bytes(F32S);
-  static constexpr int EPI_TILE_BYTES = epi_tile_bytes(F32S);
   static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -395,7 +391,6 @@ struct Cfg2 {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARP_BYTES = epi_warp_bytes(F32S);
-  static constexpr int EPI_TILE_BYTES = epi_tile_bytes(F32S);
   static constexpr int EPI_BYTES = (WS_EPI_WARPS * EPI_WARP_BYTES + 1023) & ~1023;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
   static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // accumulator stride
@@ -443,15 +438,6 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
   return u;
 }
-// packed fp32 x 2 add / multiply on two adjacent accumulator values (the epilogue is bound by FMA-pipe issue slots)
-__device__ __forceinline__ void add2(float* v, float x, float y) {
-  const float2 r = __fadd2_rn(make_float2(v[0], v[1]), make_float2(x, y));
-  v[0] = r.x; v[1] = r.y;
-}
-__device__ __forceinline__ void mul2(float* v, float x, float y) {
-  const float2 r = __fmul2_rn(make_float2(v[0], v[1]), make_float2(x, y));
-  v[0] = r.x; v[1] = r.y;
-}
 // this thread's row of the staging tile <- 32 floats as bf16
 __device__ __forceinline__ void regs_to_stage(uint32_t stg, int lane, const float* v) {
 #pragma unroll
@@ -468,6 +454,13 @@ __device__ __forceinline__ void regs_to_stage(uint32_t stg, int lane, const floa
 // F32S = true: "stream" epilogue (fp32 output and/or fp32 residual and/or a compute-dtype copy of the final value, no
 // GELU'); false: everything in the compute dtype.  Two instantiations keep each epilogue's register footprint small.
 // ------------------------------------------------------------------------------------------------------------
+// Store variants that were measured on the stage-3 shapes and REMOVED again (every one of them, merely present as a
+// run-time branch, cost the default path 0.6-5 % of the step; the code is in the named commits, the numbers under
+// profiles/): bulk-tensor (TMA) stores of the bf16 outputs from the staging tiles, whose swizzle is the TMA 64-byte
+// swizzle (commit 265c8ef: fc1 25.6 -> 24.3 us, single-tile epilogues 20.3 -> 20.8 us, step 684 -> 678 img/s,
+// r2_gemm_bench_tma_store.txt); per-lane stores straight from registers (b439910: 4x the store requests, plain 17.3 ->
+// 25.5 us, r2_gemm_bench_direct_store.txt); full 128-byte-line moves of the fp32 stream (bcf06e9: 5-25 % slower,
+// r2_gemm_bench_stream_full_lines.txt); 12 / 16 epilogue warps (-DS2U_EPI_WARPS, r2_gemm_bench_1[26]_epilogue_warps.txt).
 struct EpiTiles {
   int first, stride, num_tiles, m_tiles;   // this CTA's tile walk
   int tile_rows, row_off;                  // rows per (pair) tile and this CTA's row offset inside it
@@ -476,24 +469,10 @@ struct EpiTiles {
   uint32_t tfull0, tempty0;                // barrier addresses (tempty0 is a shared::cluster address)
 };
 
-// bulk-tensor (TMA) store of one 32 x 32 bf16 staging tile (64-byte rows, the staging swizzle IS the TMA 64-byte
-// swizzle) to (col, row) of an output matrix; rows / columns beyond the matrix are clipped by the TMA unit
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// mc / mp: tensor maps of C / pre_out for TMA stores of the compute-dtype outputs (null: per-lane 16-byte stores)
 template <int BN, bool F32S>
-__device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, uint32_t sbias, int q, int part, int lane,
+__device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, int q, int part, int lane,
                                               bf16* __restrict__ C, int ldc, int M, int N,
-                                              const EpiView<bf16>& epi, const CUtensorMap* mc, const CUtensorMap* mp) {
+                                              const EpiView<bf16>& epi) {
   const bool resid_f32 = F32S && (epi.flags & GEMM_RESID) && (epi.flags & GEMM_RESID_F32);
   const bool resid_t = (epi.flags & GEMM_RESID) && !resid_f32;              // residual in the compute dtype
   const bool out_f32 = F32S && (epi.flags & GEMM_OUT_F32), pre_final = F32S && (epi.flags & GEMM_PRE_FINAL);
@@ -511,44 +490,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
   const int nch = (BN - part * 32 + CSTRIDE - 1) / CSTRIDE;                 // this warp's chunks per tile (may be 0)
   constexpr uint32_t SLOT = (F32S ? 2 : 1) * EPI_BUF_BYTES;                 // one chunk's side input
   const uint32_t so = stg + (EPI_DB ? 2 : 1) * SLOT;                        // output staging tile
-  // TMA stores read the staging tile asynchronously.  Without a side input the two side slots are free, so the stores
-  // rotate through three tiles (a tile is rewritten when at most two younger stores are pending); with one, `so` is the
-  // only tile and is rewritten after the previous store has read it (a whole chunk of TMEM load + arithmetic later).
-  constexpr bool RING3 = EPI_DB && !F32S;
-  const bool tma_c = !F32S && mc != nullptr, tma_p = !F32S && mp != nullptr, tma_any = tma_c || tma_p;
-  const bool ring3 = RING3 && !has_side;
-  uint32_t sn = 0;                                                          // TMA stores issued by this warp
-  auto ring_tile = [&](uint32_t n) { return ring3 ? stg + (n % 3u) * (uint32_t)EPI_BUF_BYTES : so; };
-  // one bf16 output chunk: registers -> staging tile -> global (TMA store when the chunk is a full box or is clipped
-  // by the matrix edge, which the TMA unit handles; a chunk cut by the TILE edge (BN = 144) takes the per-lane path)
-  auto out16 = [&](const float* v, const CUtensorMap* map, bf16* dst, long long ld, long long row0, int col0,
-                   int rows_ok, int cols_ok) {
-    if (map != nullptr && cols_ok == min(32, N - col0)) {
-      const uint32_t tile = ring_tile(sn);
-      if (lane == 0) {
-        if (ring3) bulk_wait_read<2>();
-        else bulk_wait_read<0>();
-      }
-      __syncwarp();
-      regs_to_stage(tile, lane, v);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(map, tile, col0, (int)row0);
-        bulk_commit();
-      }
-      ++sn;
-      return;
-    }
-    if (tma_any) {
-      if (lane == 0) bulk_wait_read<0>();
-      __syncwarp();
-    }
-    regs_to_stage(so, lane, v);
-    __syncwarp();
-    s2g_rows(so, reinterpret_cast<char*>(dst + row0 * ld + col0), ld * 2, rows_ok, cols_ok * 2, lane);
-    __syncwarp();
-  };
+  const uint32_t sbias = so + EPI_BUF_BYTES;                                // [parity][32] bias values of a chunk
 
   auto prefetch = [&](int tile, int ci, int par) {
     const long long row0 = (long long)(tile % t.m_tiles) * t.tile_rows + t.row_off + q * 32;
@@ -569,10 +511,6 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
   };
   // bf16 rows of this warp's chunk: registers -> output staging tile -> global
   auto store16 = [&](const float* v, bf16* dst, long long ld, int rows_ok, int cols_ok) {
-    if (tma_any) {
-      if (lane == 0) bulk_wait_read<0>();
-      __syncwarp();
-    }
     regs_to_stage(so, lane, v);
     __syncwarp();
     s2g_rows(so, reinterpret_cast<char*>(dst), ld * 2, rows_ok, cols_ok * 2, lane);
@@ -620,16 +558,15 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 b4 = lds16(sbias + (uint32_t)(par * 128 + j * 16));
-          add2(v + 4 * j, __uint_as_float(b4.x), __uint_as_float(b4.y));
-          add2(v + 4 * j + 2, __uint_as_float(b4.z), __uint_as_float(b4.w));
+          v[4 * j] += __uint_as_float(b4.x); v[4 * j + 1] += __uint_as_float(b4.y);
+          v[4 * j + 2] += __uint_as_float(b4.z); v[4 * j + 3] += __uint_as_float(b4.w);
         }
       } else if (epi.bias) {
         if (cols_ok == 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
-            add2(v + 4 * j, b4.x, b4.y);
-            add2(v + 4 * j + 2, b4.z, b4.w);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
         } else {
 #pragma unroll
@@ -639,15 +576,6 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
       }
       if ((epi.flags & GEMM_GELU) && epi.pre_out && !pre_final && (epi.flags & GEMM_SAVE_DGELU)) {
         // v <- gelu(v), pre_out <- gelu'(v): both from one erf evaluation
-        const bool dg_tma = dg_stage && ring3 && tma_c && tma_p && cols_ok == min(32, N - col0);
-        const uint32_t td = dg_tma ? ring_tile(sn) : (dg_stage ? h0 : so), tg = dg_tma ? ring_tile(sn + 1) : so;
-        if (tma_any) {                                                      // the tiles written below are free again
-          if (lane == 0) {
-            if (dg_tma) bulk_wait_read<1>();
-            else bulk_wait_read<0>();
-          }
-          __syncwarp();
-        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float d[8];
@@ -658,21 +586,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
             v[8 * j + e] = gg.x; v[8 * j + e + 1] = gg.y;
             d[e] = dd.x; d[e + 1] = dd.y;
           }
-          sts16(stg_addr(td, lane, j), pack8(d));
-        }
-        if (dg_tma) {
-          // both outputs leave as TMA stores: two 2 KB boxes instead of 2 x 4 (LDS + STG) per lane
-          regs_to_stage(tg, lane, v);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(mp, td, col0, (int)row0);
-            bulk_commit();
-            tma_store_2d(mc, tg, col0, (int)row0);
-            bulk_commit();
-          }
-          sn += 2;
-          continue;
+          sts16(stg_addr(dg_stage ? h0 : so, lane, j), pack8(d));
         }
         if (dg_stage) {
           // gelu' waits in the (unused) side-input slot, gelu goes to the output tile: ONE round trip through shared
@@ -690,10 +604,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
                  cols_ok * 2, lane);
         __syncwarp();
       } else {
-        if (epi.pre_out && !pre_final) {
-          if (F32S) store16(v, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok);
-          else out16(v, tma_p ? mp : nullptr, epi.pre_out, epi.ld_pre, row0, col0, rows_ok, cols_ok);
-        }
+        if (epi.pre_out && !pre_final) store16(v, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok);
         if (epi.flags & GEMM_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -714,9 +625,11 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
               v[j * 8 + 2 * e] *= dgelu_fast(f.x);
               v[j * 8 + 2 * e + 1] *= dgelu_fast(f.y);
             } else if (mulaux) {
-              mul2(v + j * 8 + 2 * e, f.x, f.y);
+              v[j * 8 + 2 * e] *= f.x;
+              v[j * 8 + 2 * e + 1] *= f.y;
             } else {
-              add2(v + j * 8 + 2 * e, f.x, f.y);
+              v[j * 8 + 2 * e] += f.x;
+              v[j * 8 + 2 * e + 1] += f.y;
             }
           }
         }
@@ -728,8 +641,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 u = lds16(stg_addr(hh ? h1 : h0, lane, j));
-            add2(v + hh * 16 + 4 * j, __uint_as_float(u.x), __uint_as_float(u.y));
-            add2(v + hh * 16 + 4 * j + 2, __uint_as_float(u.z), __uint_as_float(u.w));
+            v[hh * 16 + 4 * j] += __uint_as_float(u.x);
+            v[hh * 16 + 4 * j + 1] += __uint_as_float(u.y);
+            v[hh * 16 + 4 * j + 2] += __uint_as_float(u.z);
+            v[hh * 16 + 4 * j + 3] += __uint_as_float(u.w);
           }
         }
       }
@@ -758,10 +673,6 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
           store16(v, epi.pre_out + row0 * epi.ld_pre + col0, epi.ld_pre, rows_ok, cols_ok);
         continue;
       }
-      if (!F32S) {
-        out16(v, tma_c ? mc : nullptr, C, ldc, row0, col0, rows_ok, cols_ok);
-        continue;
-      }
       regs_to_stage(so, lane, v);
       __syncwarp();
       s2g_rows(so, reinterpret_cast<char*>(C + row0 * ldc + col0), (long long)ldc * 2, rows_ok, cols_ok * 2, lane);
@@ -776,17 +687,13 @@ __device__ __forceinline__ void epilogue_warp(const EpiTiles& t, uint32_t stg, u
     if (lane == 0) mbar_arrive_cluster(t.tempty0 + 8u * acc);
   }
   cp_async_wait<0>();
-  if (tma_any && lane == 0) bulk_wait_all();      // the staging tiles must outlive their stores
 }
 
 template <int BN, int STAGES, bool F32S>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                    const __grid_constant__ CUtensorMap tma_b,
                                                                    bf16* __restrict__ C, int ldc, int M, int N, int K,
-                                                                   EpiView<bf16> epi,
-                                                                   const __grid_constant__ CUtensorMap tma_c,
-                                                                   const __grid_constant__ CUtensorMap tma_p,
-                                                                   int tma_out) {
+                                                                   EpiView<bf16> epi) {
   using cfg = CfgWS<BN, STAGES, F32S>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -878,10 +785,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
     t.tile_rows = BM; t.row_off = 0;
     t.tmem_base = tmem_base; t.acc_cols = cfg::ACC_COLS;
     t.tfull0 = tfull_bar(0); t.tempty0 = tempty_bar(0);
-    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
-                            smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
-                            warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr);
+    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
+                            ldc, M, N, epi);
   }
   tc_fence_before();
   __syncthreads();
@@ -901,10 +806,7 @@ template <int BN, int STAGES, bool F32S>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                      const __grid_constant__ CUtensorMap tma_b,
                                                                      bf16* __restrict__ C, int ldc, int M, int N,
-                                                                     int K, EpiView<bf16> epi,
-                                                                     const __grid_constant__ CUtensorMap tma_c,
-                                                                     const __grid_constant__ CUtensorMap tma_p,
-                                                                     int tma_out) {
+                                                                     int K, EpiView<bf16> epi) {
   using cfg = Cfg2<BN, STAGES, F32S>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -999,10 +901,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
     t.tile_rows = 2 * BM; t.row_off = (int)rank * BM;
     t.tmem_base = tmem_base; t.acc_cols = cfg::ACC_COLS;
     t.tfull0 = tfull_bar(0); t.tempty0 = tempty_bar(0) & PEER_MASK;
-    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_TILE_BYTES),
-                            smem_base + (uint32_t)(WS_EPI_WARPS * cfg::EPI_TILE_BYTES + (warp - 2) * EPI_BIAS_BYTES),
-                            warp & 3, (warp - 2) >> 2, lane, C, ldc, M, N, epi, (tma_out & 1) ? &tma_c : nullptr,
-                            (tma_out & 2) ? &tma_p : nullptr);
+    epilogue_warp<BN, F32S>(t, smem_base + (uint32_t)((warp - 2) * cfg::EPI_WARP_BYTES), warp & 3, (warp - 2) >> 2, lane, C,
+                            ldc, M, N, epi);
   }
   tc_fence_before();
   cluster_sync_all();          // nobody leaves while the partner may still read its smem or signal its barriers
@@ -1186,58 +1086,6 @@ static int make_map(CUtensorMap* out, const void* ptr, long long rows, long long
   return 0;
 }
 
-// output matrix [rows, cols] bf16 with pitch ld for the epilogue's TMA stores: box = 32 rows x 32 columns (64-byte rows),
-// 64-byte swizzle = the epilogue staging tile's own layout
-static int make_out_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld) {
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  static std::mutex mu;
-  const MapKey key{ptr, rows, cols, ld, 32};
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it != cache.end()) {
-    *out = it->second;
-    return 0;
-  }
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return S2U_EUNSUPPORTED;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return -100 - (int)r;
-  if (cache.size() > 65536) cache.clear();
-  cache.emplace(key, *out);
-  return 0;
-}
-// -> bit 0: C leaves through TMA stores, bit 1: pre_out does (compute-dtype epilogues only).  OPT-IN
-// (S2U_GEMM_TMA_STORE=1): measured on the stage-3 shapes it is a wash - fc1 with both outputs 25.6 -> 24.3 us, but the
-// single-tile cases (side input in the other slots) 20.3 -> 20.8 us and the whole step 684 -> 678 img/s
-// (profiles/r2_gemm_bench_tma_store.txt): the epilogue is not bound by the issue slots of its stores.
-// Two further store variants were measured and REMOVED again (their extra code paths cost the default path a stack
-// frame and ~5 % of the step): per-lane stores straight from registers (commit b439910: 4x the store requests, plain
-// 17.3 -> 25.5 us, profiles/r2_gemm_bench_direct_store.txt) and full 128-byte-line moves of the fp32 stream (commit
-// bcf06e9: 5-25 % slower, profiles/r2_gemm_bench_stream_full_lines.txt).
-static int out_maps(CUtensorMap* mc, CUtensorMap* mp, bf16* C, int ldc, int M, int N, const GemmEpi& e, int* tma_out) {
-  static int on = -1;
-  if (on < 0) { const char* v = getenv("S2U_GEMM_TMA_STORE"); on = (v && v[0] == '1') ? 1 : 0; }
-  *tma_out = 0;
-  memset(mc, 0, sizeof(*mc));
-  memset(mp, 0, sizeof(*mp));
-  if (!on || (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL))) return 0;
-  int rc = make_out_map(mc, C, M, N, ldc);
-  if (rc) return rc;
-  *tma_out |= 1;
-  if (e.pre_out) {
-    rc = make_out_map(mp, e.pre_out, M, N, e.ld_pre);
-    if (rc) return rc;
-    *tma_out |= 2;
-  }
-  return 0;
-}
-
 template <int BN, int STAGES>
 static int launch(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, int ldc, int M, int N, int K,
                   const GemmEpi& e, cudaStream_t st) {
@@ -1293,17 +1141,13 @@ static int launch_ws(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, in
   }
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  CUtensorMap mc, mp;
-  int tma_out = 0;
-  rc = out_maps(&mc, &mp, C, ldc, M, N, e, &tma_out);
-  if (rc) return rc;
   if (e.flags & (GEMM_OUT_F32 | GEMM_RESID_F32 | GEMM_PRE_FINAL)) {
     if (e.flags & (GEMM_DGELU | GEMM_MULAUX)) return S2U_EUNSUPPORTED;
     S2U_LAUNCH((gemm_umma_ws_kernel<BN, STAGES, true>), grid, WS_THREADS, cfg::SMEM_BYTES, st, ma, mb, C, ldc, M, N, K,
-                                                                                  EpiView<bf16>(e), mc, mp, tma_out);
+                                                                                  EpiView<bf16>(e));
   } else {
     S2U_LAUNCH((gemm_umma_ws_kernel<BN, STAGES, false>), grid, WS_THREADS, cfg::SMEM_BYTES, st, ma, mb, C, ldc, M, N, K,
-                                                                                   EpiView<bf16>(e), mc, mp, tma_out);
+                                                                                   EpiView<bf16>(e));
   }
   S2U_LAUNCH_CHECK();
   return 0;
@@ -1353,14 +1197,10 @@ static int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, bf16* C, 
   lc.attrs = at;
   lc.numAttrs = s2u_pdl_enabled() ? 2 : 1;
   if (f32s && (e.flags & (GEMM_DGELU | GEMM_MULAUX))) return S2U_EUNSUPPORTED;
-  CUtensorMap mc, mp;
-  int tma_out = 0;
-  rc = out_maps(&mc, &mp, C, ldc, M, N, e, &tma_out);
-  if (rc) return rc;
   cudaError_t ce = f32s ? cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STS, true>, ma, mb, C, ldc, M, N, K,
-                                             EpiView<bf16>(e), mc, mp, tma_out)
+                                             EpiView<bf16>(e))
                         : cudaLaunchKernelEx(&lc, gemm_umma_pair_kernel<BN, STP, false>, ma, mb, C, ldc, M, N, K,
-                                             EpiView<bf16>(e), mc, mp, tma_out);
+                                             EpiView<bf16>(e));
   if (ce != cudaSuccess) return (int)ce;
   S2U_LAUNCH_CHECK();
   return 0;
