@@ -9,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import port  # noqa: E402  (synthetic batch only)
+from sam2_unet_b200.synthetic import synthetic_batch  # noqa: E402
 from sam2_unet_b200 import SAM2UNet, TrainStep, _lib  # noqa: E402
 from sam2_unet_b200.params import fill_deterministic_  # noqa: E402
 
@@ -21,7 +21,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 model = SAM2UNet(model_cfg="sam2_hiera_l.yaml", dtype="bf16")
 fill_deterministic_(model, 0)
 model = model.to(dev).train()
-x, m = port.synthetic_batch(B, 352, seed=0)
+x, m = synthetic_batch(B, 352, seed=0)
 x, m = x.to(dev), m.to(dev)
 step = TrainStep(model, lr=1e-3, weight_decay=5e-4, use_graph=False, sync_grads=False)
 eng = model._engine(dev)
