@@ -10,9 +10,9 @@ from .config import trunk_config  # noqa: F401
 from .loss import structure_loss, structure_loss3  # noqa: F401
 from .model import SAM2UNet  # noqa: F401
 from .optim import FusedAdamW, Predictor, TrainStep, cosine_lr  # noqa: F401
-from .evalmetrics import evaluate_dataset, evaluate_segmentation_performance  # noqa: F401
+from .evalmetrics import evaluate_dataset, evaluate_segmentation_performance, print_eval_report  # noqa: F401
 from .postprocess import infer_tail, preprocess_image  # noqa: F401
 from .augment import TrainAugment, draw_train_params  # noqa: F401
 
 __all__ = ["SAM2UNet", "structure_loss", "structure_loss3", "FusedAdamW", "TrainStep", "Predictor", "cosine_lr",
-           "infer_tail", "preprocess_image", "TrainAugment", "draw_train_params", "evaluate_segmentation_performance", "evaluate_dataset", "trunk_config"]
+           "infer_tail", "preprocess_image", "TrainAugment", "draw_train_params", "evaluate_segmentation_performance", "evaluate_dataset", "print_eval_report", "trunk_config"]

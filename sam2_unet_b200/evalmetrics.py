@@ -129,3 +129,24 @@ def evaluate_dataset(all_image_results: List[Dict[str, float]]) -> Dict[str, flo
         final[f"Recall_{suffix}"] = recall
         final[f"F1_Score_{suffix}"] = f1
     return final
+
+
+def print_eval_report(results: Dict, title: str = "Evaluation Results", log_path: str = None) -> str:
+    """eval.py:23-52: the reference's report layout (centred title between rules, one `name : value` line per entry with
+    underscores shown as spaces, floats to four decimals), printed and - when `log_path` is given - appended to that
+    file.  Returns the text."""
+    width = max(len(title) + 2, 25)
+    lines = ["\n" + "=" * width, f"{title:^{width}}", "-" * width]
+    for metric, value in results.items():
+        name = str(metric).replace("_", " ")
+        if isinstance(value, float):
+            lines.append(f"{name:<{width - 8}}: {value:>6.4f}")
+        else:
+            lines.append(f"{name:<{width - 8}}: {value:>6}")
+    lines.append("=" * width + "\n")
+    text = "\n".join(lines)
+    print(text)
+    if log_path:
+        with open(log_path, "a") as f:
+            f.write(text)
+    return text

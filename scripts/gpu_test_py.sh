@@ -1,5 +1,5 @@
 #!/bin/bash
-# test.py end to end on synthetic files: a checkpoint from a short train.py run, a few random images
+# test.py and eval.py end to end on synthetic files: a checkpoint from a short train.py run, a few random images
 set -u
 mkdir -p gpurun_out/tp/img gpurun_out/tp/gt gpurun_out/tp/out
 python - <<'PY'
@@ -19,4 +19,5 @@ for i in range(3):
     a = np.asarray(Image.open(f"gpurun_out/tp/out/im{i}.png"))
     print(a.shape, a.dtype, a.min(), a.max())
 PY
+timeout 200 python eval.py --pred_path gpurun_out/tp/out --gt_path gpurun_out/tp/gt/ 2>&1 | tail -16
 rm -rf gpurun_out/tp

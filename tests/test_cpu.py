@@ -559,3 +559,37 @@ def test_augment_oracle_against_live_reference():
         out = ap.apply(ap.draw(S, *lab.shape), torch.from_numpy(img), torch.from_numpy(lab), S)
         assert torch.equal(out["label"], ref["label"]), seed
         assert (out["image"] - ref["image"]).abs().max().item() <= 1e-5, seed
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/eval.py"), reason="reference not present")
+def test_print_eval_report_matches_the_reference(tmp_path, capsys):
+    """The report text (eval.py:23-52) of the package equals the reference function's, character for character."""
+    import importlib.util
+    import sys
+    import types
+    pytest.importorskip("cv2")
+    from sam2_unet_b200.evalmetrics import print_eval_report
+    sk, skm = types.ModuleType("skimage"), types.ModuleType("skimage.measure")
+    skm.label = skm.regionprops = None
+    sk.measure = skm
+    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.measure")}
+    sys.modules.update({"skimage": sk, "skimage.measure": skm})
+    try:
+        spec = importlib.util.spec_from_file_location("ref_eval2", "/root/reference/eval.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    res = {"semantic_iou": 0.81234567, "dice_coefficient": 0.9, "count_gt": 3, "count_pred": 12, "instance_f1_50": 0.0}
+    for title in ("Segmentation Evaluation", "[3/17] a_rather_long_file_name_0001.png", "x"):
+        a, b = str(tmp_path / "a.txt"), str(tmp_path / "b.txt")
+        ref.print_eval_report(res, title=title, log_path=a)
+        theirs = capsys.readouterr().out
+        print_eval_report(res, title=title, log_path=b)
+        mine = capsys.readouterr().out
+        assert mine == theirs
+        assert open(a).read() == open(b).read()

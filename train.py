@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from sam2_unet_b200 import (SAM2UNet, TrainStep, cosine_lr, evaluate_dataset, evaluate_segmentation_performance,
+                            print_eval_report,
                             infer_tail, preprocess_image)
 
 
@@ -219,10 +220,8 @@ def main(args):
             final = evaluate_dataset(mine)
             mean_iou = final.get("mIoU", 0.0)
             epoch_name = f"epoch-{epoch + 1}_loss-{epoch_loss:.3f}"
-            line = f"{epoch_name}: " + ", ".join(f"{k} {v:.4f}" for k, v in final.items())
-            print("\n" + line)
-            with open(log_path, "a") as f:
-                f.write(line + "\n")
+            print()
+            print_eval_report(final, title=epoch_name, log_path=log_path)           # train.py:126-128, same layout
             if mean_iou > base_mean_iou:                                              # train.py:133-143
                 base_mean_iou = mean_iou
                 path = os.path.join(args.save_path, f"SAM2-UNet_{epoch_name}_iou-{mean_iou:.3f}.pth")
