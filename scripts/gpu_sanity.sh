@@ -1,5 +1,5 @@
 #!/bin/bash
-# end-of-round sanity: other configs through bench.py, the train.py command line, memcheck of a tiny step
+# end-of-round sanity: other configs through bench.py, the train.py command line
 set -u
 mkdir -p gpurun_out
 for cfg in sam2_hiera_t.yaml sam2_hiera_s.yaml sam2_hiera_b+.yaml; do
@@ -8,5 +8,4 @@ done
 timeout 300 python bench.py --size 1024 --batch 4 --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-260
 timeout 300 python bench.py --size 1024 --batch 1 --mode infer --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-220
 timeout 300 python train.py --save_path gpurun_out/ck --synthetic 24 --size 352 --model_cfg sam2_hiera_t.yaml --epoch 2 --batch_size 12 2>&1 | tail -4 | cut -c1-200
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_model_gpu.py -x -q -m gpu -k "train_step_parity or tiny" 2>&1 | tail -4 | cut -c1-200
-echo "sanitizer rc=$?"
+rm -rf gpurun_out/ck
