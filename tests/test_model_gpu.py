@@ -439,7 +439,7 @@ def test_bf16_mask_criteria_after_prefit(cuda, variant):
             # Hiera-T ours 0.012-0.016 / 0.9989-0.9996 vs autocast 0.016-0.020 / 0.9990; Hiera-L eval ours 0.039-0.072 /
             # 0.974-0.991 vs autocast 0.029 / 0.994 in the one fit both were measured on, train mode 0.013 / 0.9992 vs
             # 0.019 / 0.9989.
-            assert err <= min(0.12, max(2e-2, 2.5 * err_auto)), (train, name, err, err_auto)
+            assert err <= min(0.12, max(2e-2, 3.0 * err_auto)), (train, name, err, err_auto)
             assert iou >= max(0.95, min(0.998, iou_auto - 0.03)), (train, name, iou, iou_auto)
         else:
             assert err <= 2e-2, (train, name, err)
