@@ -699,7 +699,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_ws_kernel(const __gri
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_holder;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (role,
+  // TMEM lane quarter, staging-tile addresses) in uniform registers instead of spilling loop invariants of the epilogue
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base + cfg::EPI_BYTES;
   const uint32_t bar0 = smem_u32(bars);
@@ -812,7 +814,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_umma_pair_kernel(const __g
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_holder;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform, see above
   const uint32_t rank = cluster_ctarank();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base + cfg::EPI_BYTES;
