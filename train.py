@@ -56,16 +56,28 @@ class _RawFiles(torch.utils.data.Dataset):
 
 class _DeviceAugmentLoader:
     """Wraps a DataLoader of raw uint8 (image, mask) pairs: every batch is augmented on the GPU and handed on as the
-    {"image": [B,3,S,S], "label": [B,1,S,S]} dictionary the reference's loader yields."""
+    {"image": [B,3,S,S], "label": [B,1,S,S]} dictionary the reference's loader yields.  The augmentation kernels run on
+    their own stream, so the batch for step i+1 (requested right after step i was launched) overlaps step i."""
 
     def __init__(self, loader, size, device):
         from sam2_unet_b200 import TrainAugment
-        self.loader, self.aug = loader, TrainAugment(size, device)
+        self.loader, self.aug, self.device = loader, TrainAugment(size, device), device
+        self.stream = torch.cuda.Stream(device=device)
+
+    def __len__(self):
+        return len(self.loader)
 
     def __iter__(self):
         for raw in self.loader:
-            items = [self.aug(img, gt) for img, gt in raw]
-            yield {"image": torch.stack([d["image"] for d in items]), "label": torch.stack([d["label"] for d in items])}
+            main = torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(self.stream):
+                items = [self.aug(img, gt) for img, gt in raw]
+                batch = {"image": torch.stack([d["image"] for d in items]),
+                         "label": torch.stack([d["label"] for d in items])}
+            main.wait_stream(self.stream)                    # the consumer's stream sees the finished batch
+            for t in batch.values():
+                t.record_stream(main)                        # allocated on the side stream, used on the main one
+            yield batch
 
 
 class _Synthetic(torch.utils.data.Dataset):
